@@ -361,19 +361,21 @@ void Scene::build_node(uint32_t ni, uint32_t begin, uint32_t end, std::vector<Bo
     build_node(left + 1, mid, end, boxes, cent);
 }
 
-// slab test; returns entry distance or +inf.  Conservative: interval widened by a few ulps.
-inline float box_entry(const Box& b, const float o[3], const float inv[3], float tnear, float tbest) {
+// slab test: true when [tnear, tbest] overlaps the box; entry distance in `entry`.
+// Conservative: the interval is widened by a few ulps.
+inline bool box_hit(const Box& b, const float o[3], const float inv[3], float tnear, float tbest, float& entry) {
     float t0 = tnear, t1 = tbest;
     for (int a = 0; a < 3; a++) {
         float ta = (b.lo[a] - o[a]) * inv[a];
         float tb = (b.hi[a] - o[a]) * inv[a];
         float tmn = std::fmin(ta, tb), tmx = std::fmax(ta, tb);  // fmin/fmax drop NaN (0*inf)
-        tmn = tmn - std::fabs(tmn) * 4.8e-7f;
-        tmx = tmx + std::fabs(tmx) * 4.8e-7f;
+        tmn = tmn * (tmn >= 0.0f ? 0.9999995f : 1.0000005f);
+        tmx = tmx * (tmx >= 0.0f ? 1.0000005f : 0.9999995f);
         t0 = std::fmax(t0, tmn);
         t1 = std::fmin(t1, tmx);
     }
-    return t0 <= t1 ? t0 : std::numeric_limits<float>::infinity();
+    entry = t0;
+    return t0 <= t1;
 }
 
 thread_local unsigned long long t_rays = 0;
@@ -408,18 +410,23 @@ void Scene::intersect(RTCRayHit* rh) const {
             const Node& n = nodes[stack[--sp]];
             // ties (entry == best.t) must still be visited: a lower-index primitive may sit there
             float limit = std::fmin(tfar, best.t);
-            if (!(box_entry(n.box, o, inv, tnear, limit) <= limit)) continue;
+            float dn;
+            if (!box_hit(n.box, o, inv, tnear, limit, dn)) continue;
             if (n.count) {
                 for (uint32_t i = 0; i < n.count; i++) {
                     uint32_t r = refs_sorted[n.left + i];
                     prim_test(prims[r], r, O, D, tnear, tfar, best);
                 }
             } else {
-                float dl = box_entry(nodes[n.left].box, o, inv, tnear, limit);
-                float dr = box_entry(nodes[n.left + 1].box, o, inv, tnear, limit);
-                // push far child first
-                if (dl <= dr) { if (dr <= limit) stack[sp++] = n.left + 1; if (dl <= limit) stack[sp++] = n.left; }
-                else { if (dl <= limit) stack[sp++] = n.left; if (dr <= limit) stack[sp++] = n.left + 1; }
+                float dl, dr;
+                bool hl = box_hit(nodes[n.left].box, o, inv, tnear, limit, dl);
+                bool hr = box_hit(nodes[n.left + 1].box, o, inv, tnear, limit, dr);
+                // push the far child first
+                if (hl && hr) {
+                    if (dl <= dr) { stack[sp++] = n.left + 1; stack[sp++] = n.left; }
+                    else { stack[sp++] = n.left; stack[sp++] = n.left + 1; }
+                } else if (hl) stack[sp++] = n.left;
+                else if (hr) stack[sp++] = n.left + 1;
             }
         }
     }

@@ -1,0 +1,131 @@
+// Ray / primitive intersection.  The reference delegates this to Embree's rtcIntersect1
+// (scene.cpp:41-59); the arithmetic is the one the oracle's Embree shim defines
+// (oracle/embree_shim/rtcore_shim.cpp, restating Embree 4.3's Moeller-Trumbore triangle /
+// quad / grid and sphere-point intersectors) and is repeated here operation for operation so
+// that t, u, v and Ng are bit-identical.  Closest hit = minimum t, ties to the lower
+// primitive index (geomID, primID, cell order), which makes the result independent of the
+// BVH traversal order.
+#pragma once
+
+#include "scene.cuh"
+
+namespace qz {
+
+struct Hit {
+    float t, u, v;
+    uint32_t prim;  // slot in the (leaf-ordered) primitive array; 0xffffffff = miss
+    V3 ng;          // unnormalised geometric normal as Embree reports it
+    uint32_t key;   // tie-break key: primitive index in (geomID, primID, cell) order
+};
+
+#define QZ_NO_HIT 0xffffffffu
+#define QZ_TNEAR 0.0001f /* scene.cpp:49; in ray-parameter units */
+
+QZ_HD float xor_sign(float v, uint32_t s) { return u32_as_float(float_as_u32(v) ^ s); }
+
+struct PrimHit {
+    float t, u, v;
+    V3 ng;
+};
+
+// Moeller-Trumbore, Embree operation order; `flip` = second triangle of a quad
+QZ_HD bool tri_test(V3 O, V3 D, float tnear, float tfar, V3 v0, V3 v1, V3 v2, bool flip, PrimHit& h) {
+    V3 e1 = v0 - v1;
+    V3 e2 = v2 - v0;
+    V3 ng = cross(e2, e1);
+    V3 C = v0 - O;
+    V3 R = cross(C, D);
+    float den = dot(ng, D);
+    float absDen = fabsf(den);
+    uint32_t s = float_as_u32(den) & 0x80000000u;
+    float U = xor_sign(dot(R, e2), s);
+    float V = xor_sign(dot(R, e1), s);
+    if (!(den != 0.0f) || !(U >= 0.0f) || !(V >= 0.0f) || !(U + V <= absDen)) return false;
+    float T = xor_sign(dot(ng, C), s);
+    if (!(absDen * tnear < T) || !(T <= absDen * tfar)) return false;
+    h.t = T / absDen;
+    if (flip) {
+        h.u = (absDen - U) / absDen;
+        h.v = (absDen - V) / absDen;
+    } else {
+        h.u = U / absDen;
+        h.v = V / absDen;
+    }
+    h.ng = ng;
+    return true;
+}
+
+QZ_HD bool sphere_test(V3 O, V3 D, float tnear, float tfar, V3 c, float r, PrimHit& h) {
+    float rd2 = 1.0f / dot(D, D);
+    V3 c0 = c - O;
+    float projC0 = dot(c0, D) * rd2;
+    V3 perp = c0 - D * projC0;
+    float l2 = dot(perp, perp);
+    float r2 = r * r;
+    if (!(l2 <= r2)) return false;
+    float td = sqrtf((r2 - l2) * rd2);
+    float t_front = projC0 - td;
+    float t_back = projC0 + td;
+    if (tnear <= t_front && t_front <= tfar) {
+        h.t = t_front;
+        h.ng = D * (-td) - perp;
+    } else if (tnear <= t_back && t_back <= tfar) {
+        h.t = t_back;
+        h.ng = D * td - perp;
+    } else {
+        return false;
+    }
+    h.u = 0.0f;
+    h.v = 0.0f;
+    return true;
+}
+
+QZ_HD V3 xyz(const F4& f) { return v3(f.x, f.y, f.z); }
+
+QZ_HD F4 load_f4(const F4* p) {
+#if defined(__CUDA_ARCH__)
+    const float4 v = __ldg(reinterpret_cast<const float4*>(p));
+    F4 r; r.x = v.x; r.y = v.y; r.z = v.z; r.w = v.w; return r;
+#else
+    return *p;
+#endif
+}
+
+// word 2 of a primitive record: kind in the low 2 bits, tie-break key above
+QZ_HD uint32_t prim_kind(uint32_t w2) { return w2 & 3u; }
+QZ_HD uint32_t prim_key(uint32_t w2) { return w2 >> 2; }
+
+// Tests primitive slot `slot`; updates `best` under the (t, key) order.  tfar is the ray's
+// own far limit (infinity for path rays): validity never depends on the running best.
+QZ_HD void prim_test(const DScene& sc, uint32_t slot, V3 O, V3 D, float tnear, float tfar, Hit& best) {
+    const F4* rec = sc.prims + (size_t)slot * 4;
+    const F4 a = load_f4(rec), b = load_f4(rec + 1), c = load_f4(rec + 2), d = load_f4(rec + 3);
+    const uint32_t w2 = float_as_u32(c.w);
+    const uint32_t kind = prim_kind(w2);
+    PrimHit h;
+    bool found = false;
+    if (kind == QZ_PRIM_SPHERE) {
+        found = sphere_test(O, D, tnear, tfar, xyz(a), b.x, h);
+    } else if (kind == QZ_PRIM_TRIANGLE) {
+        found = tri_test(O, D, tnear, tfar, xyz(a), xyz(b), xyz(c), false, h);
+    } else {
+        PrimHit ha, hb;
+        bool fa = tri_test(O, D, tnear, tfar, xyz(a), xyz(b), xyz(d), false, ha);
+        bool fb = tri_test(O, D, tnear, tfar, xyz(c), xyz(d), xyz(b), true, hb);
+        if (fa && (!fb || ha.t <= hb.t)) { h = ha; found = true; }
+        else if (fb) { h = hb; found = true; }
+        if (found && kind == QZ_PRIM_GRIDCELL) {
+            const uint32_t cell = float_as_u32(d.w);
+            const uint32_t dims = sc.grid_dims[float_as_u32(a.w)];
+            h.u = ((float)(cell & 0xffffu) + h.u) / (float)(dims & 0xffffu);
+            h.v = ((float)(cell >> 16) + h.v) / (float)(dims >> 16);
+        }
+    }
+    if (!found) return;
+    const uint32_t key = prim_key(w2);
+    if (h.t < best.t || (h.t == best.t && key < best.key)) {
+        best.t = h.t; best.u = h.u; best.v = h.v; best.ng = h.ng; best.prim = slot; best.key = key;
+    }
+}
+
+}  // namespace qz

@@ -1,0 +1,218 @@
+// Owen-scrambled Halton sampler, bit-exact restatement of the reference's Sampler
+// (sampler.cpp:161-198 permutation_element / mix_bits, :298-314 radical_inv, :316-324
+// inv_radical_inv, :335-352 owen_scrambled_radical_inv, :383-454 Sampler).  Everything up
+// to the final float multiply is integer arithmetic, so the device values equal the
+// oracle's bit for bit (tests/test_sampler.py checks the known answers of SURVEY.md
+// section 4 and random (x, y, s, dim) tuples).
+//
+// B200 shaping: per-dimension constants live in a 16-byte record (one LDG.128): the prime
+// base with its digit count, floor(2^32/base) for multiply-high division (one correction
+// step, exact for every 32-bit numerator because base <= 7919), the per-dimension hash
+// uint32(mix_bits(1 + (dim << 4))) and base^-ndigits accumulated in float exactly as the
+// reference's loop does.  The Halton index fits 32 bits (spp * 31104 < 2^31, the
+// reference's own int overflow limit at sampler.cpp:420).
+#pragma once
+
+#include "common.cuh"
+
+namespace qz {
+
+#define QZ_N_PRIMES 1000
+#define QZ_MAX_HALTON_RESOLUTION 128
+#define QZ_ONE_MINUS_EPS 0.99999994f /* 0x1.fffffep-1 (util.hpp:3) */
+
+struct SamplerDim {
+    uint32_t base_nd;  // base | ndigits << 16
+    uint32_t magic;    // floor(2^32 / base)
+    uint32_t hash;     // uint32(mix_bits(1 + (dim << 4)))
+    uint32_t scale;    // float bits of base^-ndigits (sequential float products)
+};
+
+// per-render constants of Sampler's constructor (sampler.cpp:383-402)
+struct SamplerParams {
+    uint32_t scale0, scale1;  // base_scales: powers of 2 / 3 covering min(res, 128)
+    uint32_t exp0, exp1;      // base_exps
+    uint32_t mult_inv0, mult_inv1;
+    uint32_t stride;          // scale0 * scale1
+    uint32_t pad;
+};
+
+QZ_HD uint64_t mix_bits(uint64_t v) {
+    v ^= (v >> 31);
+    v *= 0x7fb5d329728ea185ull;
+    v ^= (v >> 27);
+    v *= 0x81dadef4bc2dd44dull;
+    v ^= (v >> 33);
+    return v;
+}
+
+// x / d and x % d for any 32-bit x, with m = floor(2^32 / d): the estimate is low by at most 1
+QZ_HD uint32_t div_magic(uint32_t x, uint32_t d, uint32_t m, uint32_t& rem) {
+    uint32_t q = umulhi32(x, m);
+    uint32_t r = x - q * d;
+    if (r >= d) { r -= d; q++; }
+    rem = r;
+    return q;
+}
+
+// sampler.cpp:161-189
+QZ_HD uint32_t permutation_element(uint32_t i, uint32_t l, uint32_t magic, uint32_t w, uint32_t p) {
+    do {
+        i ^= p;
+        i *= 0xe170893du;
+        i ^= p >> 16;
+        i ^= (i & w) >> 4;
+        i ^= p >> 8;
+        i *= 0x0929eb3fu;
+        i ^= p >> 23;
+        i ^= (i & w) >> 1;
+        i *= 1u | p >> 27;
+        i *= 0x6935fa69u;
+        i ^= (i & w) >> 11;
+        i *= 0x74dcb303u;
+        i ^= (i & w) >> 2;
+        i *= 0x9e501cc3u;
+        i ^= (i & w) >> 2;
+        i *= 0xc860a3dfu;
+        i &= w;
+        i ^= i >> 5;
+    } while (i >= l);
+    uint32_t rem;
+    div_magic(i + p, l, magic, rem);
+    return rem;
+}
+
+// sampler.cpp:335-352 for one table entry; `a` is the Halton index
+QZ_HD float owen_scrambled_radical_inv(const SamplerDim dimrec, uint32_t a) {
+    const uint32_t base = dimrec.base_nd & 0xffffu;
+    const uint32_t nd = dimrec.base_nd >> 16;
+    // w = (next power of two >= base) - 1, as the or-shift cascade of permutation_element computes it
+    uint32_t w = base - 1;
+    w |= w >> 1; w |= w >> 2; w |= w >> 4; w |= w >> 8; w |= w >> 16;
+    uint64_t reversed = 0;
+    for (uint32_t k = 0; k < nd; k++) {
+        uint32_t digit;
+        a = div_magic(a, base, dimrec.magic, digit);
+        uint32_t digit_hash = (uint32_t)mix_bits((uint64_t)dimrec.hash ^ reversed);
+        digit = permutation_element(digit, base, dimrec.magic, w, digit_hash);
+        reversed = reversed * base + digit;
+    }
+    float r = u32_as_float(dimrec.scale) * (float)reversed;
+    return std_min(r, QZ_ONE_MINUS_EPS);
+}
+
+// sampler.cpp:298-314 (unscrambled; used for the pixel jitter only)
+QZ_HD float radical_inv(uint32_t base, uint32_t a) {
+    float inv_base = 1.0f / (float)base, inv_base_m = 1.0f;
+    uint64_t reversed = 0;
+    while (a) {
+        uint32_t next = a / base;
+        uint32_t digit = a - next * base;
+        reversed = reversed * base + digit;
+        inv_base_m *= inv_base;
+        a = next;
+    }
+    return std_min((float)reversed * inv_base_m, QZ_ONE_MINUS_EPS);
+}
+
+struct Sampler {
+    uint32_t index;  // halton_index
+    uint32_t dim;    // next dimension
+};
+
+// Sampler::start_pixel_sample (sampler.cpp:404-422); y is the flipped image y
+QZ_HD Sampler sampler_start(const SamplerParams& sp, uint32_t x, uint32_t y, uint32_t s) {
+    Sampler smp;
+    uint32_t idx = 0;
+    if (sp.stride > 1) {
+        uint32_t px = x & (QZ_MAX_HALTON_RESOLUTION - 1), py = y & (QZ_MAX_HALTON_RESOLUTION - 1);
+        uint32_t off0 = 0, off1 = 0;
+        for (uint32_t i = 0; i < sp.exp0; i++) { off0 = off0 * 2 + (px & 1u); px >>= 1; }
+        for (uint32_t i = 0; i < sp.exp1; i++) { off1 = off1 * 3 + (py % 3u); py /= 3u; }
+        idx = off0 * (sp.stride / sp.scale0) * sp.mult_inv0 + off1 * (sp.stride / sp.scale1) * sp.mult_inv1;
+        idx %= sp.stride;
+    }
+    smp.index = idx + s * sp.stride;
+    smp.dim = 2;
+    return smp;
+}
+
+// Sampler::sample_pixel (sampler.cpp:449-454)
+QZ_HD V2 sampler_pixel_jitter(const SamplerParams& sp, const Sampler& smp) {
+    return v2(radical_inv(2, smp.index >> sp.exp0), radical_inv(3, smp.index / sp.scale1));
+}
+
+QZ_HD float sample_dimension(const SamplerDim* __restrict__ table, const Sampler& smp, uint32_t dim) {
+#if defined(__CUDA_ARCH__)
+    const uint4 raw = __ldg(reinterpret_cast<const uint4*>(table) + dim);
+    SamplerDim rec; rec.base_nd = raw.x; rec.magic = raw.y; rec.hash = raw.z; rec.scale = raw.w;
+#else
+    const SamplerDim rec = table[dim];
+#endif
+    return owen_scrambled_radical_inv(rec, smp.index);
+}
+
+// Sampler::sample_1d / sample_2d (sampler.cpp:433-447): dimensions wrap to 2 past the table
+QZ_HD float sample_1d(const SamplerDim* __restrict__ table, Sampler& smp) {
+    if (smp.dim >= QZ_N_PRIMES) smp.dim = 2;
+    return sample_dimension(table, smp, smp.dim++);
+}
+QZ_HD V2 sample_2d(const SamplerDim* __restrict__ table, Sampler& smp) {
+    if (smp.dim + 1 >= QZ_N_PRIMES) smp.dim = 2;
+    uint32_t d = smp.dim;
+    smp.dim += 2;
+    float a = sample_dimension(table, smp, d);
+    float b = sample_dimension(table, smp, d + 1);
+    return v2(a, b);
+}
+
+// ---- host-side table construction (runs once per process) ---------------------------
+#if !defined(__CUDA_ARCH__)
+inline void build_sampler_table(SamplerDim* out /* QZ_N_PRIMES entries */) {
+    uint32_t count = 0;
+    for (uint32_t n = 2; count < QZ_N_PRIMES; n++) {
+        bool prime = true;
+        for (uint32_t d = 2; d * d <= n; d++) if (n % d == 0) { prime = false; break; }
+        if (!prime) continue;
+        const uint32_t dim = count++;
+        // digit count and scale: the loop of sampler.cpp:341-350 in float
+        float inv_base = 1.0f / (float)n, inv_base_m = 1.0f;
+        uint32_t nd = 0;
+        while (1.0f - inv_base_m < 1.0f) { inv_base_m *= inv_base; nd++; }
+        SamplerDim rec;
+        rec.base_nd = n | (nd << 16);
+        rec.magic = (uint32_t)((1ull << 32) / n);
+        rec.hash = (uint32_t)mix_bits((uint64_t)(1 + (int)(dim << 4)));
+        rec.scale = float_as_u32(inv_base_m);
+        out[dim] = rec;
+    }
+}
+
+inline SamplerParams make_sampler_params(int x_res, int y_res) {
+    SamplerParams sp;
+    const int res[2] = {x_res, y_res};
+    uint32_t scales[2], exps[2];
+    for (int i = 0; i < 2; i++) {
+        int base = i == 0 ? 2 : 3;
+        int64_t scale = 1, e = 0;
+        int lim = res[i] < QZ_MAX_HALTON_RESOLUTION ? res[i] : QZ_MAX_HALTON_RESOLUTION;
+        while (scale < lim) { scale *= base; e++; }
+        scales[i] = (uint32_t)scale; exps[i] = (uint32_t)e;
+    }
+    // multiplicative inverses by brute force (sampler.cpp:354-376 uses extended Euclid)
+    auto minv = [](uint32_t a, uint32_t n) -> uint32_t {
+        if (n == 1) return 0;
+        for (uint32_t x = 0; x < n; x++) if ((uint64_t)a * x % n == 1) return x;
+        return 0;
+    };
+    sp.scale0 = scales[0]; sp.scale1 = scales[1];
+    sp.exp0 = exps[0]; sp.exp1 = exps[1];
+    sp.mult_inv0 = minv(scales[1] % scales[0], scales[0]);
+    sp.mult_inv1 = minv(scales[0] % scales[1], scales[1]);
+    sp.stride = scales[0] * scales[1];
+    sp.pad = 0;
+    return sp;
+}
+#endif
+
+}  // namespace qz

@@ -1,0 +1,348 @@
+// One bounce of the reference's path loop (render.cpp:107-209 sample_pixel, :54-87
+// sample_lights, :45-52 power_heuristic) plus what it calls: surface interaction from a hit
+// (scene.cpp:61-117), emission (interaction.hpp:32-37, light.cpp:48-53), materials
+// (material.cpp:4-60, material.hpp:94-97 MixedMaterial), textures (texture.cpp:5-61) and
+// light sampling (light.cpp:8-42, shape.hpp:46-49,78-83, scene.cpp:119-134).
+//
+// The wavefront kernels and the per-path replay kernel both call shade_bounce(); the only
+// difference between them is where the path state lives between bounces.
+#pragma once
+
+#include "bvh.cuh"
+#include "bxdf.cuh"
+#include "spectra.cuh"
+
+namespace qz {
+
+// ------------------------------------------------------------------ path state
+#define QZ_FLAG_SPECULAR_BOUNCE 1u
+#define QZ_FLAG_HAS_SHADOW 2u     /* a next-event shadow ray is pending for this bounce */
+
+struct PathState {
+    Ray ray;
+    Spec4 weight, L, lambda, pdf;
+    Sampler smp;
+    uint32_t depth;
+    uint32_t flags;
+    float p_b;
+    float ior_scale;
+    uint32_t n_rays;  // closest-hit + occlusion queries issued (the oracle's per-path ray count)
+};
+
+struct PathAov {
+    V3 normal;
+    Spec4 albedo;
+};
+
+struct ShadowRequest {
+    V3 o, d;         // Scene::occluded(start, end): ray start -> end - start (scene.cpp:136-138)
+    Spec4 contrib;   // weight * sample_lights(...) assuming the light is visible
+};
+
+QZ_HD float power_heuristic(float f_pdf, float g_pdf) {
+    float f = 1 * f_pdf;
+    float g = 1 * g_pdf;
+    if (is_inf(f * f)) return 1.0f;
+    return f * f / (f * f + g * g);
+}
+
+// scene.cpp:27-39
+QZ_HD V2 sphere_uv(V3 n) {
+    float phi = (float)((double)qz_atan2f(n.z, n.x) + QZ_PI);
+    float u = (float)((double)phi / (2.0 * QZ_PI));
+    if (u >= 1.0f) u -= 1.1920929e-07f;
+    float theta = qz_acosf(n.y);
+    float v = (float)((double)theta / QZ_PI);
+    if (v >= 1.0f) v -= 1.1920929e-07f;
+    return v2(u, v);
+}
+
+// Texture::value (texture.cpp)
+QZ_HD Spec4 texture_value(const DScene& sc, int32_t tex_id, V2 uv, const Spec4& lambda) {
+    const qz_texture t = sc.textures[tex_id];
+    if (t.kind == QZ_TEX_SOLID) return from_spectrum(sc, t.a, lambda);
+    if (t.kind == QZ_TEX_DUMMY) {
+        float u = uv.x * 10.0f;  // float(double(uv.x) * 10.) is the same value
+        float v = uv.y * 10.0f;
+        int cell = (int)(floorf(u) + floorf(v));
+        return from_spectrum(sc, (cell % 2 == 0) ? t.a : t.b, lambda);
+    }
+    // ImageTexture: nearest texel, RGB -> sigmoid spectrum through the table on every lookup
+    uint32_t x = (uint32_t)(uv.x * (float)t.width);
+    if (x == t.width) x = t.width - 1;
+    uint32_t y = (uint32_t)(uv.y * (float)t.height);
+    if (y == t.height) y = t.height - 1;
+    const float* px = sc.pool + t.offset + 3 * ((size_t)y * t.width + x);
+    V3 c = rgb_to_sigmoid(sc, px[0], px[1], px[2]);
+    return spec4(sigmoid_poly(c.x, c.y, c.z, lambda.v[0]), sigmoid_poly(c.x, c.y, c.z, lambda.v[1]),
+                 sigmoid_poly(c.x, c.y, c.z, lambda.v[2]), sigmoid_poly(c.x, c.y, c.z, lambda.v[3]));
+}
+
+// material kind after resolving MixedMaterial with the bounce's material sample
+// (material.hpp:94-97: child floor(sample * N), the same sample passed down)
+QZ_HD int32_t resolve_material(const DScene& sc, int32_t mat, float sample) {
+    for (int guard = 0; guard < 8; guard++) {
+        const qz_material m = sc.materials[mat];
+        if (m.kind != QZ_MAT_MIXED) return mat;
+        uint32_t idx = (uint32_t)(sample * (float)m.count);
+        mat = sc.mixed_children[m.a + (int32_t)idx];
+    }
+    return mat;
+}
+
+struct SurfacePoint {
+    V3 point, wo, normal;
+    V2 uv;
+    int32_t material, light;
+    bool is_sphere;
+};
+
+// Scene::ray_intersect after the Embree call (scene.cpp:72-116)
+QZ_HD SurfacePoint make_surface_point(const DScene& sc, const Ray& ray, const Hit& hit) {
+    SurfacePoint sp;
+    const F4* rec = sc.prims + (size_t)hit.prim * 4;
+    const uint32_t geom_id = float_as_u32(load_f4(rec).w);
+    const uint32_t prim_id = float_as_u32(load_f4(rec + 1).w);
+    const qz_geometry g = sc.geoms[geom_id];
+    sp.uv = v2(hit.u, hit.v);
+    if (g.normal_offset >= 0 && g.shape == QZ_SHAPE_OBJ) {
+        const int32_t* fi = sc.nidx + 4 * ((size_t)g.nindex_offset + prim_id);
+        V3 n[4];
+        for (int k = 0; k < 4; k++) {
+            const float* p = sc.normals + 3 * ((size_t)g.normal_offset + (size_t)fi[k]);
+            n[k] = v3(p[0], p[1], p[2]);
+        }
+        float u = hit.u, v = hit.v;
+        V3 blend = n[0] * ((1.0f - u) * (1.0f - v)) + n[1] * (u * (1.0f - v)) + n[2] * (u * v) + n[3] * ((1.0f - u) * v);
+        sp.normal = normalized(blend);
+    } else {
+        sp.normal = normalized(hit.ng);
+    }
+    sp.is_sphere = g.shape == QZ_SHAPE_SPHERE;
+    sp.point = ray.o + ray.d * hit.t;
+    sp.wo = normalized(-ray.d);
+    sp.material = g.material;
+    sp.light = g.light;
+    return sp;
+}
+
+// Material::bsdf for a resolved (non-mixed) material; may terminate secondary wavelengths
+template <int KH>
+QZ_HD Bsdf make_bsdf(const DScene& sc, int32_t mat, SurfacePoint& sp, const Spec4& lambda, Spec4& pdf) {
+    const qz_material m = sc.materials[mat];
+    Bsdf f;
+    f.a = spec4(0.0f); f.b = spec4(0.0f); f.rough.ax = 0.0f; f.rough.ay = 0.0f; f.ior = 1.0f;
+    make_basis(sp.normal, f.u0, f.u1, f.u2);
+    if (KH == KH_DIFFUSE || (KH == KH_ANY && m.kind == QZ_MAT_DIFFUSE)) {
+        f.kind = BX_DIFFUSE;
+        // sphere uv are only ever consumed by textures: evaluate them lazily
+        const uint32_t tk = sc.textures[m.a].kind;
+        if (sp.is_sphere && tk != QZ_TEX_SOLID) sp.uv = sphere_uv(sp.normal);
+        f.a = texture_value(sc, m.a, sp.uv, lambda);
+    } else if (KH == KH_CONDUCTOR || (KH == KH_ANY && m.kind == QZ_MAT_CONDUCTOR)) {
+        f.kind = BX_CONDUCTOR;
+        f.a = from_spectrum(sc, m.a, lambda);
+        f.b = from_spectrum(sc, m.b, lambda);
+        f.rough.ax = m.alpha_x; f.rough.ay = m.alpha_y;
+    } else {
+        f.kind = m.kind == QZ_MAT_DIELECTRIC ? BX_DIELECTRIC : BX_THIN;
+        f.ior = eval_spectrum(sc, m.a, lambda.v[0]);
+        if (!m.is_constant) terminate_secondary(pdf);
+    }
+    return f;
+}
+
+// Light emission towards w from a point with normal n (light.cpp:48-53)
+QZ_HD Spec4 light_emission(const DScene& sc, const qz_light& l, V3 n, V3 w, const Spec4& lambda) {
+    if (!l.two_sided && dot(n, w) < 0.0f) return spec4(0.0f);
+    return from_spectrum(sc, l.spectrum, lambda) * l.scale;
+}
+
+// sample_lights (render.cpp:54-87) without the occlusion test: returns the contribution for a
+// visible light and the shadow segment to test; `has_shadow` false means the term is zero
+template <int KH>
+QZ_HD void sample_lights(const DScene& sc, const SurfacePoint& sp, const Bsdf& f, const Spec4& lambda, Sampler& smp,
+                         bool& has_shadow, V3& p_light_out, Spec4& result) {
+    has_shadow = false;
+    result = spec4(0.0f);
+    const SamplerDim* tab = sc.sampler_table;
+    int32_t li = -1;
+    float proba = 0.0f;
+    if (sc.n_lights != 0) {
+        float u = sample_1d(tab, smp);
+        li = (int32_t)(uint32_t)(u * (float)sc.n_lights);
+        proba = 1.0f / (float)sc.n_lights;
+    }
+    V2 u2 = sample_2d(tab, smp);
+    if (li < 0) {
+        sample_2d(tab, smp);  // keeps the dimension count even (render.cpp:62-66)
+        return;
+    }
+    const qz_light l = sc.lights[li];
+    const V3 lp = v3(l.p[0], l.p[1], l.p[2]);
+    Spec4 spec;
+    V3 wi, p_light;
+    float pdf;
+    if (l.kind == QZ_LIGHT_POINT) {
+        V3 dv = lp - sp.point;
+        wi = normalized(dv);
+        spec = from_spectrum(sc, l.spectrum, lambda) * (l.scale / norm_squared(dv));
+        pdf = 1.0f;
+        p_light = lp;
+    } else {
+        V3 n;
+        if (l.kind == QZ_LIGHT_AREA_QUAD) {
+            p_light = lp + v3(l.du[0], l.du[1], l.du[2]) * u2.x + v3(l.dv[0], l.dv[1], l.dv[2]) * u2.y;
+            n = v3(l.normal[0], l.normal[1], l.normal[2]);
+        } else {
+            n = sample_uniform_sphere(u2);
+            p_light = lp + n * l.radius;
+        }
+        pdf = l.inv_area;
+        V3 dv = p_light - sp.point;
+        if (pdf == 0.0f || norm_squared(dv) == 0.0f) return;
+        wi = normalized(dv);
+        spec = light_emission(sc, l, n, -wi, lambda);
+        if (is_zero(spec)) return;
+    }
+    if (is_zero(spec) || pdf == 0.0f) return;
+    Spec4 fv = bsdf_f<KH>(f, sp.wo, wi) * fabsf(dot(wi, sp.normal));
+    if (is_zero(fv)) return;
+    float p_l = proba * pdf;
+    if (l.kind != QZ_LIGHT_POINT) {
+        float p_b = bsdf_pdf<KH>(f, sp.wo, wi);
+        float w_l = power_heuristic(p_l, p_b);
+        result = spec * fv * (w_l / p_l);
+    } else {
+        result = spec * fv / p_l;
+    }
+    has_shadow = true;
+    p_light_out = p_light;
+}
+
+// One iteration of the while loop of sample_pixel() AFTER the closest-hit query.
+// Returns true when the path continues (ps.ray holds the next ray).
+template <int KH>
+QZ_HD bool shade_bounce(const DScene& sc, PathState& ps, PathAov& aov, const Hit& hit, uint32_t max_bounces,
+                        ShadowRequest& shadow) {
+    ps.flags &= ~QZ_FLAG_HAS_SHADOW;
+    const SamplerDim* tab = sc.sampler_table;
+    if (hit.prim == QZ_NO_HIT) {
+        if (sc.bg_spectrum >= 0) ps.L = ps.L + ps.weight * from_spectrum(sc, sc.bg_spectrum, ps.lambda) * sc.bg_scale;
+        return false;
+    }
+    SurfacePoint sp = make_surface_point(sc, ps.ray, hit);
+    if (ps.depth == 0) aov.normal = sp.normal;
+
+    if (sp.light >= 0) {
+        const qz_light l = sc.lights[sp.light];
+        Spec4 emitted = light_emission(sc, l, sp.normal, -ps.ray.d, ps.lambda);
+        if (!is_zero(emitted)) {
+            if (ps.depth == 0 || (ps.flags & QZ_FLAG_SPECULAR_BOUNCE)) {
+                ps.L = ps.L + ps.weight * emitted;
+            } else {
+                // light_sample_pmf * light->pdf: uniform light pick, area-measure pdf (scene.cpp:132-134, light.cpp:44-46)
+                float light_proba = (1.0f / (float)sc.n_lights) * l.inv_area;
+                float light_weight = power_heuristic(ps.p_b, light_proba);
+                ps.L = ps.L + emitted * (ps.weight * light_weight);
+            }
+        }
+    }
+    if (ps.depth == max_bounces) return false;
+
+    float mat_sample = sample_1d(tab, ps.smp);
+    if (sp.material < 0) {
+        // emitter geometry has no material: pass straight through, depth unchanged (render.cpp:142-148)
+        ps.flags |= QZ_FLAG_SPECULAR_BOUNCE;
+        ps.ray.o = sp.point;
+        return !is_zero(ps.weight);
+    }
+    const int32_t mat = KH == KH_ANY ? resolve_material(sc, sp.material, mat_sample) : sp.material;
+    Bsdf f = make_bsdf<KH>(sc, mat, sp, ps.lambda, ps.pdf);
+
+    if (ps.depth == 0) aov.albedo = bsdf_rho_hd<KH>(sc, f, sp.wo);
+
+    if (!bsdf_is_specular<KH>(f)) {
+        bool has_shadow;
+        V3 p_light;
+        Spec4 direct;
+        sample_lights<KH>(sc, sp, f, ps.lambda, ps.smp, has_shadow, p_light, direct);
+        if (has_shadow) {
+            shadow.o = sp.point;
+            shadow.d = p_light - sp.point;
+            shadow.contrib = ps.weight * direct;
+            ps.flags |= QZ_FLAG_HAS_SHADOW;
+        }
+    }
+
+    // g++ evaluates the arguments of bsdf->sample(wo, sample_1d(), sample_2d()) right to left:
+    // the 2-D sample takes the next two dimensions, the 1-D sample the one after (render.cpp:177)
+    V2 u2 = sample_2d(tab, ps.smp);
+    float u1 = sample_1d(tab, ps.smp);
+    BsdfSample bs = bsdf_sample<KH>(f, sp.wo, u1, u2);
+    if (!bs.valid) return false;
+
+    ps.weight = ps.weight * (bs.spec * fabsf(dot(bs.wi, sp.normal)) / bs.pdf);
+    ps.p_b = bs.pdf;  // pdf_is_proportional is never set by any BxDF
+    if (bs.specular) ps.flags |= QZ_FLAG_SPECULAR_BOUNCE; else ps.flags &= ~QZ_FLAG_SPECULAR_BOUNCE;
+    if (bs.transmission) ps.ior_scale *= bs.ior;
+    ps.ray.o = sp.point;
+    ps.ray.d = bs.wi;
+    ps.depth++;
+
+    float roulette = sample_1d(tab, ps.smp);
+    Spec4 rr = ps.weight * ps.ior_scale;
+    if (max_component(rr) < 1.f && ps.depth > 1) {
+        float q = std_max(0.0f, 1.0f - max_component(rr));
+        if (roulette < q) return false;
+        ps.weight = ps.weight / (1.0f - q);
+    }
+    return !is_zero(ps.weight);
+}
+
+// render_pixels() prologue for one pixel-sample (render.cpp:268-273); y is the flipped image y
+QZ_HD void start_path(const DScene& sc, const DCamera& cam, const SamplerParams& spar, uint32_t x, uint32_t y, uint32_t s,
+                      PathState& ps, PathAov& aov) {
+    ps.smp = sampler_start(spar, x, y, s);
+    V2 jitter = sampler_pixel_jitter(spar, ps.smp);
+    float u = (float)x + jitter.x;
+    float v = (float)y + jitter.y;
+    ps.ray.o = cam.pos;
+    ps.ray.d = cam.bottom_left + cam.du * u + cam.dv * v - cam.pos;
+    float ul = sample_1d(sc.sampler_table, ps.smp);
+    sample_wavelengths(ul, ps.lambda, ps.pdf);
+    ps.weight = spec4(1.0f);
+    ps.L = spec4(0.0f);
+    ps.depth = 0;
+    ps.flags = 0;
+    ps.p_b = 1.0f;
+    ps.ior_scale = 1.0f;
+    ps.n_rays = 0;
+    aov.normal = v3(0.0f, 0.0f, 0.0f);
+    aov.albedo = spec4(0.0f);
+}
+
+// A whole path in one thread: the per-path replay kernel (qz_trace_paths) and the host
+// emulation use this; the wavefront pipeline runs the same three calls as separate kernels.
+template <bool COUNT>
+QZ_HD void run_path(const DScene& sc, const DCamera& cam, const SamplerParams& spar, uint32_t x, uint32_t y, uint32_t s,
+                    uint32_t max_bounces, PathState& ps, PathAov& aov, Spec4& lambda0, TraversalCounters* cnt) {
+    start_path(sc, cam, spar, x, y, s, ps, aov);
+    lambda0 = ps.lambda;
+    for (;;) {
+        Hit hit;
+        closest_hit<COUNT>(sc, ps.ray, hit, cnt);
+        ps.n_rays++;
+        ShadowRequest sh;
+        bool alive = shade_bounce<KH_ANY>(sc, ps, aov, hit, max_bounces, sh);
+        if (ps.flags & QZ_FLAG_HAS_SHADOW) {
+            Ray sr;
+            sr.o = sh.o; sr.d = sh.d;
+            ps.n_rays++;
+            if (!occluded<COUNT>(sc, sr, cnt)) ps.L = ps.L + sh.contrib;
+        }
+        if (!alive) break;
+    }
+}
+
+}  // namespace qz

@@ -1,0 +1,172 @@
+// Spectrum evaluation on the device: tagged-union restatement of the reference's virtual
+// Spectrum::operator() family (color/spectrum.cpp:47-53 dense, :101-109 piecewise linear
+// with its two quirks, :113-133 blackbody; color/rgb.cpp:51-67 sigmoid polynomial,
+// :176-178 unbounded, :191-196 illuminant), the RGB -> spectrum table lookup used by
+// ImageTexture (rgb.cpp:50-57, 78-140), wavelength sampling (spectrum_sample.cpp:11-42)
+// and PixelSensor::to_sensor_rgb (sensor.cpp:57-70).
+#pragma once
+
+#include "math.cuh"
+#include "scene.cuh"
+
+namespace qz {
+
+QZ_HD float sigmoidf(float x) {
+    if (is_inf(x)) return x > 0.0f ? 1.0f : 0.0f;
+    return 0.5f + 0.5f * x / (sqrtf(1.0f + x * x));
+}
+
+QZ_HD float sigmoid_poly(float c0, float c1, float c2, float lambda) {
+    return sigmoidf(c0 + c1 * lambda + c2 * lambda * lambda);
+}
+
+// every kind except RGB_ILLUMINANT (which multiplies by another spectrum)
+QZ_HD float eval_spectrum_leaf(const DScene& sc, const qz_spectrum& s, float lambda) {
+    {
+        switch (s.kind) {
+            case QZ_SPEC_CONSTANT:
+                return s.a;
+            case QZ_SPEC_DENSE: {
+                long idx = lroundf(lambda - (float)s.aux);
+                if (idx < 0 || idx >= (long)s.count) return 0.0f;
+                return sc.pool[s.offset + idx];
+            }
+            case QZ_SPEC_PIECEWISE: {
+                const float* l = sc.pool + s.offset;
+                const float* v = l + s.count + 1;
+                if (s.count == 0 || lambda < l[0] || lambda > l[s.count - 1]) return 0.0f;
+                // std::lower_bound: first knot >= lambda
+                uint32_t first = 0, len = s.count;
+                while (len > 0) {
+                    uint32_t half = len >> 1;
+                    if (l[first + half] < lambda) { first += half + 1; len -= half + 1; }
+                    else len = half;
+                }
+                // l[count] and v[count] are the zero pads standing in for the reference's
+                // one-past-the-end read
+                float t = (lambda - l[first]) / (l[first + 1] - l[first]);
+                return v[first] * (1.0f - t) + v[first + 1] * t;
+            }
+            case QZ_SPEC_SIGMOID:
+                return sigmoid_poly(s.a, s.b, s.c, lambda);
+            case QZ_SPEC_RGB_UNBOUNDED:
+                return s.scale * sigmoid_poly(s.a, s.b, s.c, lambda);
+            case QZ_SPEC_BLACKBODY: {
+                // spectrum.cpp:113-133; pow(lambda, 5) is a double pow, expm1f a float one
+                if (s.a <= 0.f) return s.b * 0.f;
+                const float c = 299792458.f, h = 6.62606957e-34f, kb = 1.3806488e-23f;
+                float l = lambda * 1e-9f;
+                double den = pow((double)lambda, 5.0) * (double)expm1f(h * c / (l * kb * s.a));
+                float le = (float)((double)(2.0f * h * c * c) / den);
+                return s.b * le;
+            }
+            default:
+                return 0.0f;
+        }
+    }
+}
+
+QZ_HD float eval_spectrum(const DScene& sc, int32_t id, float lambda) {
+    const qz_spectrum s = sc.spectra[id];
+    if (s.kind == QZ_SPEC_RGB_ILLUMINANT) {
+        if (s.aux < 0) return 0.0f;
+        // m_scale * m_polynomial(lambda) * illuminant(lambda), left to right (rgb.cpp:191-196);
+        // the illuminant is never itself an RGBIlluminantSpectrum (it is the colour space's D65)
+        float head = s.scale * sigmoid_poly(s.a, s.b, s.c, lambda);
+        const qz_spectrum ill = sc.spectra[s.aux];
+        return head * eval_spectrum_leaf(sc, ill, lambda);
+    }
+    return eval_spectrum_leaf(sc, s, lambda);
+}
+
+// SpectrumSample::from_spectrum (spectrum_sample.cpp:49-58)
+QZ_HD Spec4 from_spectrum(const DScene& sc, int32_t id, const Spec4& lambda) {
+    return spec4(eval_spectrum(sc, id, lambda.v[0]), eval_spectrum(sc, id, lambda.v[1]),
+                 eval_spectrum(sc, id, lambda.v[2]), eval_spectrum(sc, id, lambda.v[3]));
+}
+
+// RGBColorSpace::to_spectrum + RGBToSpectrumTable::operator() (rgb.cpp:50-57, 78-140);
+// returns (c0, c1, c2) of the sigmoid polynomial
+QZ_HD V3 rgb_to_sigmoid(const DScene& sc, float r, float g, float b) {
+    r = std_clamp(r, 0.0f, 1.0f); g = std_clamp(g, 0.0f, 1.0f); b = std_clamp(b, 0.0f, 1.0f);
+    if (r == g && g == b) {
+        return v3(0.0f, 0.0f, (r - 0.5f) / sqrtf(std_max(0.0f, r * (1.0f - r))));
+    }
+    const float comps[3] = {r, g, b};
+    uint32_t maxc = (comps[0] > comps[1]) ? ((comps[0] > comps[2]) ? 0u : 2u) : ((comps[1] > comps[2]) ? 1u : 2u);
+    float z = comps[maxc];
+    float x = comps[(maxc + 1) % 3] * 31.0f / z;
+    float y = comps[(maxc + 2) % 3] * 31.0f / z;
+    uint32_t xi = (uint32_t)x; if (xi > 30u) xi = 30u;
+    uint32_t yi = (uint32_t)y; if (yi > 30u) yi = 30u;
+    // lower_bound over the 32 z nodes, then step back one
+    uint32_t first = 0, len = 32;
+    while (len > 0) {
+        uint32_t half = len >> 1;
+        if (sc.lut_z[first + half] < z) { first += half + 1; len -= half + 1; }
+        else len = half;
+    }
+    uint32_t zi = first;
+    if (zi != 0) zi--;
+    if (zi > 30u) zi = 30u;
+    float dx = x - (float)xi, dy = y - (float)yi;
+    float dz = (z - sc.lut_z[zi]) / (sc.lut_z[zi + 1] - sc.lut_z[zi]);
+    float c[3];
+    const float* base = sc.lut_coeffs + (size_t)maxc * 32 * 32 * 32 * 3;
+    for (uint32_t i = 0; i < 3; i++) {
+#define QZ_CO(a, bb, d) base[((zi + (d)) * 32 * 32 + (yi + (bb)) * 32 + (xi + (a))) * 3 + i]
+        c[i] = lerpf(lerpf(lerpf(QZ_CO(0, 0, 0), QZ_CO(1, 0, 0), dx), lerpf(QZ_CO(0, 1, 0), QZ_CO(1, 1, 0), dx), dy),
+                     lerpf(lerpf(QZ_CO(0, 0, 1), QZ_CO(1, 0, 1), dx), lerpf(QZ_CO(0, 1, 1), QZ_CO(1, 1, 1), dx), dy), dz);
+#undef QZ_CO
+    }
+    return v3(c[2], c[1], c[0]);
+}
+
+// WavelengthSample::uniform (spectrum_sample.cpp:11-24) over [360, 830]
+QZ_HD void sample_wavelengths(float u, Spec4& lambda, Spec4& pdf) {
+    const float lmin = 360.0f, lmax = 830.0f;
+    lambda.v[0] = (1.0f - u) * lmin + u * lmax;
+    const float delta = (lmax - lmin) / 4.0f;
+    for (int i = 1; i < 4; i++) {
+        lambda.v[i] = lambda.v[i - 1] + delta;
+        if (lambda.v[i] > lmax) lambda.v[i] = lmin + (lambda.v[i] - lmax);
+    }
+    pdf = spec4(1.0f / (lmax - lmin));
+}
+
+// WavelengthSample::terminate_secondary (spectrum_sample.cpp:34-42)
+QZ_HD void terminate_secondary(Spec4& pdf) {
+    if (pdf.v[1] == 0.0f && pdf.v[2] == 0.0f && pdf.v[3] == 0.0f) return;
+    pdf.v[1] = 0.0f; pdf.v[2] = 0.0f; pdf.v[3] = 0.0f;
+    pdf.v[0] /= 4.0f;
+}
+
+// DenselySampledSpectrum lookup of one sensor curve (lambda_min 360, 471 samples)
+QZ_HD float sensor_curve(const float* curve, float lambda) {
+    long idx = lroundf(lambda - 360.0f);
+    if (idx < 0 || idx >= 471) return 0.0f;
+    return curve[idx];
+}
+
+// PixelSensor::to_sensor_rgb (sensor.cpp:57-70) incl. the per-sample saturation clamp at 40
+QZ_HD V3 to_sensor_rgb(const DCamera& cam, const Spec4& L, const Spec4& lambda, const Spec4& pdf) {
+    Spec4 l = L / pdf;
+    float rgb[3];
+    for (int k = 0; k < 3; k++) {
+        const float* curve = cam.sensor + k * 471;
+        Spec4 resp = spec4(sensor_curve(curve, lambda.v[0]), sensor_curve(curve, lambda.v[1]),
+                           sensor_curve(curve, lambda.v[2]), sensor_curve(curve, lambda.v[3]));
+        rgb[k] = average(resp * l) * cam.imaging_ratio;
+    }
+    // std::max({x, y, z})
+    float m = rgb[0];
+    if (m < rgb[1]) m = rgb[1];
+    if (m < rgb[2]) m = rgb[2];
+    if (m > 40.0f) {
+        float s = 40.0f / m;
+        rgb[0] *= s; rgb[1] *= s; rgb[2] *= s;
+    }
+    return v3(rgb[0], rgb[1], rgb[2]);
+}
+
+}  // namespace qz

@@ -1,0 +1,39 @@
+// Image / RenderResult (reference image.hpp:8-45): float RGB planes, row 0 = image top.
+// save() writes a binary PPM (".ppm") or PFM (anything else) -- the reference's PNG writer
+// is OpenCV and its denoiser is OIDN (image.cpp:7-95); both are out of scope and absent
+// here, so denoise() only reports that.
+#pragma once
+
+#include <cstddef>
+#include <string>
+#include <vector>
+
+class Image {
+public:
+    Image(size_t height_, size_t width_) : height(height_), width(width_), color_buffer(height_ * width_ * 3) {}
+    Image(const std::vector<float>& buffer, size_t height_, size_t width_) : height(height_), width(width_), color_buffer(buffer) {}
+    Image(std::vector<float>&& buffer, size_t height_, size_t width_) : height(height_), width(width_), color_buffer(buffer) {}
+    virtual ~Image() {}
+
+    void save(const std::string& filename, float gamma = 1.0) const;
+    virtual void denoise(bool verbose = false);
+
+    size_t height;
+    size_t width;
+    std::vector<float> color_buffer;
+};
+
+class RenderResult : public Image {
+public:
+    RenderResult(size_t height_, size_t width_)
+        : Image(height_, width_), normal_buffer(height_ * width_ * 3), albedo_buffer(height_ * width_ * 3) {}
+    RenderResult(std::vector<float>&& color, std::vector<float>&& normal, std::vector<float>&& albedo, size_t height_, size_t width_)
+        : Image(std::move(color), height_, width_), normal_buffer(std::move(normal)), albedo_buffer(std::move(albedo)) {}
+
+    void denoise(bool verbose = false) override;
+    void save_normal(const std::string& filename) const;
+    void save_albedo(const std::string& filename) const;
+
+    std::vector<float> normal_buffer;
+    std::vector<float> albedo_buffer;
+};

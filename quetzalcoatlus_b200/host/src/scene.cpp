@@ -1,0 +1,485 @@
+// Scene building, flattening and the render() entry of the host library.
+//
+// Reference behaviour followed (file:line into /root/reference/src):
+//   scene.cpp:145-188 add_triangle; :190-241 add_quad; :243-253 add_plane (quad from an
+//   OrthonormalBasis); :255-287 add_sphere; :289-373 add_obj (vertices transformed,
+//   1-based -> 0-based indices, triangles as degenerate quads, normals NOT transformed);
+//   :375-430 add_grid (vertex = pixel RGB as xyz, <= 65535 per side); :432-459 add_light
+//   (an area light also inserts its quad/sphere with a null material); :461-464
+//   set_bg_light; :22-25 commit; render.cpp:321-397 render().
+#include "../scene.hpp"
+
+#include <cstdlib>
+#include <cstring>
+
+#include "../obj/obj.hpp"
+#include "../onb.hpp"
+#include "../render.hpp"
+
+namespace {
+
+inline float bits_to_float(uint32_t b) {
+    float f;
+    std::memcpy(&f, &b, 4);
+    return f;
+}
+
+qz_prim make_prim(uint32_t kind, uint32_t geom_id, uint32_t prim_id, uint32_t cell, const Pt3* v, int nv) {
+    qz_prim p{};
+    for (int i = 0; i < nv; i++) {
+        p.v[i][0] = v[i].x;
+        p.v[i][1] = v[i].y;
+        p.v[i][2] = v[i].z;
+    }
+    p.v[0][3] = bits_to_float(geom_id);
+    p.v[1][3] = bits_to_float(prim_id);
+    p.v[2][3] = bits_to_float(kind);
+    p.v[3][3] = bits_to_float(cell);
+    return p;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------- device handle
+QzDevice initialize_device() {
+    QzDevice d;
+    const char* env = std::getenv("QZ_DEVICE");
+    if (!env) env = std::getenv("LOCAL_RANK");
+    d.ordinal = env ? std::atoi(env) : 0;
+    int rc = qz_init(d.ordinal);
+    if (rc != QZ_OK) {
+        std::cerr << "error code " << rc << ": cannot create device: " << qz_last_error() << std::endl;
+        return d;
+    }
+    d.ok = true;
+    return d;
+}
+
+// ---------------------------------------------------------------- Scene
+Scene::Scene(QzDevice&& device) : m_device(device) {
+    if (m_device.ok && qz_scene_create(&m_handle) != QZ_OK) {
+        std::cerr << "error: " << qz_last_error() << std::endl;
+        m_handle = nullptr;
+    }
+}
+
+Scene::~Scene() {
+    if (m_handle) qz_scene_destroy(m_handle);
+}
+
+size_t Scene::n_primitives() const {
+    size_t n = 0;
+    for (const auto& g : m_geom_data) n += g.prims.size();
+    return n;
+}
+
+GeometryData* Scene::new_geometry(ShapeType shape, const Material* material) {
+    m_geom_data.emplace_back();
+    GeometryData* g = &m_geom_data.back();
+    g->shape = shape;
+    g->material = material;
+    g->light = nullptr;
+    return g;
+}
+
+GeometryData* Scene::add_triangle(const Pt3& a, const Pt3& b, const Pt3& c, const Material* material) {
+    GeometryData* g = new_geometry(ShapeType::TRIANGLE, material);
+    const Pt3 v[3] = {a, b, c};
+    g->prims.push_back(make_prim(QZ_PRIM_TRIANGLE, uint32_t(m_geom_data.size() - 1), 0, 0, v, 3));
+    return g;
+}
+
+GeometryData* Scene::add_quad(const Pt3& a, const Pt3& b, const Pt3& c, const Pt3& d, const Material* material) {
+    GeometryData* g = new_geometry(ShapeType::QUAD, material);
+    const Pt3 v[4] = {a, b, c, d};
+    g->prims.push_back(make_prim(QZ_PRIM_QUAD, uint32_t(m_geom_data.size() - 1), 0, 0, v, 4));
+    return g;
+}
+
+GeometryData* Scene::add_plane(const Pt3& p, const Vec3& n, const Material* material, float half_size) {
+    OrthonormalBasis basis(n);
+    Pt3 a = p - basis.u[0] * half_size - basis.u[1] * half_size;
+    Pt3 b = p + basis.u[0] * half_size - basis.u[1] * half_size;
+    Pt3 c = p + basis.u[0] * half_size + basis.u[1] * half_size;
+    Pt3 d = p - basis.u[0] * half_size + basis.u[1] * half_size;
+    return add_quad(a, b, c, d, material);
+}
+
+GeometryData* Scene::add_sphere(const Pt3& center, float radius, const Material* material) {
+    GeometryData* g = new_geometry(ShapeType::SPHERE, material);
+    const Pt3 v[1] = {center};
+    qz_prim p = make_prim(QZ_PRIM_SPHERE, uint32_t(m_geom_data.size() - 1), 0, 0, v, 1);
+    p.v[1][0] = radius;
+    g->prims.push_back(p);
+    return g;
+}
+
+GeometryData* Scene::add_obj(const std::string& filename, const Material* material, const Transform& transform) {
+    auto obj_data = obj::load_obj(filename);
+    if (!obj_data) {
+        std::cerr << "Failed to load " << filename << std::endl;
+        return nullptr;
+    }
+    const obj::ObjData& mesh = *obj_data;
+    if (mesh.vertices.empty() || mesh.faces.empty()) return nullptr;
+
+    std::vector<Pt3> verts(mesh.vertices.size());
+    for (size_t i = 0; i < verts.size(); i++) verts[i] = transform * Pt3(mesh.vertices[i].x, mesh.vertices[i].y, mesh.vertices[i].z);
+
+    for (const auto& face : mesh.faces) {
+        for (int k = 0; k < 4; k++) {
+            if (face.vertices[k] < 1 || size_t(face.vertices[k]) > verts.size()) {
+                std::cerr << "Failed to create buffers for " << filename << " (face index out of range)" << std::endl;
+                return nullptr;
+            }
+        }
+    }
+
+    GeometryData* g = new_geometry(ShapeType::OBJ, material);
+    const uint32_t geom_id = uint32_t(m_geom_data.size() - 1);
+    g->prims.reserve(mesh.faces.size());
+    for (size_t i = 0; i < mesh.faces.size(); i++) {
+        const auto& idx = mesh.faces[i].vertices;
+        const Pt3 v[4] = {verts[idx[0] - 1], verts[idx[1] - 1], verts[idx[2] - 1], verts[idx[3] - 1]};
+        g->prims.push_back(make_prim(QZ_PRIM_QUAD, geom_id, uint32_t(i), 0, v, 4));
+    }
+    if (!mesh.vertex_normals.empty()) {
+        auto nd = std::make_unique<NormalData>();
+        nd->normals.reserve(mesh.vertex_normals.size());
+        for (const auto& n : mesh.vertex_normals) nd->normals.emplace_back(n.x, n.y, n.z);
+        nd->faces.reserve(mesh.faces.size());
+        for (const auto& face : mesh.faces) {
+            const auto& ns = face.normals;
+            nd->faces.push_back({ns[0] - 1, ns[1] - 1, ns[2] - 1, ns[3] - 1});
+        }
+        g->normals = std::move(nd);
+    }
+    return g;
+}
+
+GeometryData* Scene::add_grid(const Image& image, const Material* material, const Transform& transform) {
+    if (image.width > std::numeric_limits<unsigned short>::max() || image.height > std::numeric_limits<unsigned short>::max()) {
+        std::cerr << "Grid too large" << std::endl;
+        return nullptr;
+    }
+    if (image.width < 2 || image.height < 2) {
+        std::cerr << "Failed to create buffers for grid" << std::endl;
+        return nullptr;
+    }
+    const size_t W = image.width, H = image.height;
+    std::vector<Pt3> verts(W * H);
+    for (size_t i = 0; i < W * H; i++)
+        verts[i] = transform * Pt3(image.color_buffer[i * 3 + 0], image.color_buffer[i * 3 + 1], image.color_buffer[i * 3 + 2]);
+
+    GeometryData* g = new_geometry(ShapeType::GRID, material);
+    const uint32_t geom_id = uint32_t(m_geom_data.size() - 1);
+    g->grid_dims = uint32_t(W - 1) | (uint32_t(H - 1) << 16);
+    g->prims.reserve((W - 1) * (H - 1));
+    // one cell = one quad (p[y][x], p[y][x+1], p[y+1][x+1], p[y+1][x]); primID 0 (a single RTCGrid)
+    for (size_t y = 0; y + 1 < H; y++) {
+        for (size_t x = 0; x + 1 < W; x++) {
+            const Pt3 v[4] = {verts[y * W + x], verts[y * W + x + 1], verts[(y + 1) * W + x + 1], verts[(y + 1) * W + x]};
+            g->prims.push_back(make_prim(QZ_PRIM_GRIDCELL, geom_id, 0, uint32_t(x) | (uint32_t(y) << 16), v, 4));
+        }
+    }
+    return g;
+}
+
+void Scene::add_light(std::unique_ptr<Light>&& light) {
+    if (light->type() == LightType::AREA) {
+        auto area_light = static_cast<const AreaLight*>(light.get());
+        const Shape* shape = area_light->shape();
+        auto shape_type = shape->type();
+        if (shape_type == ShapeType::SPHERE) {
+            const Sphere* sphere = static_cast<const Sphere*>(shape);
+            if (auto g = add_sphere(sphere->m_center, sphere->m_radius, nullptr)) g->light = area_light;
+        } else if (shape_type == ShapeType::QUAD) {
+            const Quad* quad = static_cast<const Quad*>(shape);
+            auto [a, b, c, d] = quad->get_vertices();
+            if (auto g = add_quad(a, b, c, d, nullptr)) g->light = area_light;
+        } else {
+            std::cerr << "Shape type not yet supported as an area light: " << shape->type() << std::endl;
+            return;
+        }
+    }
+    m_lights.push_back(std::move(light));
+}
+
+void Scene::set_bg_light(std::shared_ptr<const Spectrum> spectrum, float scale) {
+    m_bg_light.spectrum = spectrum;
+    m_bg_light.scale = scale;
+}
+
+void Scene::commit() {
+    if (!m_handle) {
+        std::cerr << "error: scene has no CUDA device (initialize_device failed)" << std::endl;
+        return;
+    }
+    qzhost::Flattener f;
+    std::unordered_map<const Light*, int32_t> light_ids;
+    for (const auto& l : m_lights) light_ids[l.get()] = l->flatten(f);
+
+    for (const auto& g : m_geom_data) {
+        qz_geometry q{};
+        switch (g.shape) {
+            case ShapeType::SPHERE: q.shape = QZ_SHAPE_SPHERE; break;
+            case ShapeType::TRIANGLE: q.shape = QZ_SHAPE_TRIANGLE; break;
+            case ShapeType::QUAD: q.shape = QZ_SHAPE_QUAD; break;
+            case ShapeType::OBJ: q.shape = QZ_SHAPE_OBJ; break;
+            case ShapeType::GRID: q.shape = QZ_SHAPE_GRID; break;
+        }
+        q.material = g.material ? g.material->flatten(f) : -1;
+        q.light = -1;
+        if (g.light) {
+            auto it = light_ids.find(g.light);
+            if (it != light_ids.end()) q.light = it->second;
+        }
+        q.normal_offset = -1;
+        q.nindex_offset = -1;
+        if (g.normals && g.shape == ShapeType::OBJ) {
+            q.normal_offset = int32_t(f.normals.size() / 3);
+            for (const auto& n : g.normals->normals) {
+                f.normals.push_back(n.x); f.normals.push_back(n.y); f.normals.push_back(n.z);
+            }
+            q.nindex_offset = int32_t(f.normal_indices.size() / 4);
+            for (const auto& fi : g.normals->faces)
+                for (int k = 0; k < 4; k++) f.normal_indices.push_back(fi[k]);
+        }
+        q.first_prim = uint32_t(f.prims.size());
+        q.prim_count = uint32_t(g.prims.size());
+        f.prims.insert(f.prims.end(), g.prims.begin(), g.prims.end());
+        f.geometries.push_back(q);
+        f.grid_dims.push_back(g.grid_dims);
+    }
+
+    qz_scene_tables t{};
+    t.spectra = f.spectra.data(); t.n_spectra = uint32_t(f.spectra.size());
+    t.textures = f.textures.data(); t.n_textures = uint32_t(f.textures.size());
+    t.materials = f.materials.data(); t.n_materials = uint32_t(f.materials.size());
+    t.mixed_children = f.mixed_children.data(); t.n_mixed_children = uint32_t(f.mixed_children.size());
+    t.lights = f.lights.data(); t.n_lights = uint32_t(f.lights.size());
+    t.bg_spectrum = m_bg_light.spectrum ? m_bg_light.spectrum->flatten(f) : -1;
+    t.bg_scale = m_bg_light.scale;
+    // (flatten of the background may have grown the spectrum table / pool: take pointers last)
+    t.spectra = f.spectra.data(); t.n_spectra = uint32_t(f.spectra.size());
+    t.geometries = f.geometries.data(); t.n_geometries = uint32_t(f.geometries.size());
+    t.prims = f.prims.data(); t.n_prims = uint32_t(f.prims.size());
+    t.pool = f.pool.data(); t.n_pool = uint32_t(f.pool.size());
+    t.normals = f.normals.data(); t.n_normals = uint32_t(f.normals.size() / 3);
+    t.normal_indices = f.normal_indices.data(); t.n_normal_indices = uint32_t(f.normal_indices.size() / 4);
+    t.grid_dims = f.grid_dims.data();
+    auto table = RGBToSpectrumTable::sRGB();
+    t.rgb2spec_z = table->m_z_nodes.data();
+    t.rgb2spec_coeffs = table->m_coeffs.data();
+
+    if (qz_scene_commit(m_handle, &t) != QZ_OK) {
+        std::cerr << "error: " << qz_last_error() << std::endl;
+        return;
+    }
+    m_ready = true;
+}
+
+// ---------------------------------------------------------------- flatten hooks
+int32_t SolidColor::flatten(qzhost::Flattener& f) const {
+    qz_texture t{};
+    t.kind = QZ_TEX_SOLID;
+    t.a = m_spectrum->flatten(f);
+    f.textures.push_back(t);
+    return int32_t(f.textures.size()) - 1;
+}
+
+int32_t DummyTexture::flatten(qzhost::Flattener& f) const {
+    qz_texture t{};
+    t.kind = QZ_TEX_DUMMY;
+    t.a = white.flatten(f);
+    t.b = black.flatten(f);
+    f.textures.push_back(t);
+    return int32_t(f.textures.size()) - 1;
+}
+
+int32_t ImageTexture::flatten(qzhost::Flattener& f) const {
+    qz_texture t{};
+    t.kind = QZ_TEX_IMAGE;
+    t.offset = f.add_pool(image.color_buffer.data(), image.color_buffer.size());
+    t.width = uint32_t(image.width);
+    t.height = uint32_t(image.height);
+    f.textures.push_back(t);
+    return int32_t(f.textures.size()) - 1;
+}
+
+static int32_t add_material(qzhost::Flattener& f, const void* key, const qz_material& m) {
+    f.materials.push_back(m);
+    int32_t id = int32_t(f.materials.size()) - 1;
+    f.seen_materials[key] = id;
+    return id;
+}
+static int32_t find_material(const qzhost::Flattener& f, const void* key) {
+    auto it = f.seen_materials.find(key);
+    return it == f.seen_materials.end() ? -1 : it->second;
+}
+
+int32_t DiffuseMaterial::flatten(qzhost::Flattener& f) const {
+    int32_t id = find_material(f, this);
+    if (id >= 0) return id;
+    qz_material m{};
+    m.kind = QZ_MAT_DIFFUSE;
+    m.a = m_texture->flatten(f);
+    return add_material(f, this, m);
+}
+
+int32_t ConductiveMaterial::flatten(qzhost::Flattener& f) const {
+    int32_t id = find_material(f, this);
+    if (id >= 0) return id;
+    qz_material m{};
+    m.kind = QZ_MAT_CONDUCTOR;
+    m.a = m_ior->flatten(f);
+    m.b = m_absorption->flatten(f);
+    m.alpha_x = m_roughness.m_alpha_x;
+    m.alpha_y = m_roughness.m_alpha_y;
+    return add_material(f, this, m);
+}
+
+int32_t DielectricMaterial::flatten(qzhost::Flattener& f) const {
+    int32_t id = find_material(f, this);
+    if (id >= 0) return id;
+    qz_material m{};
+    m.kind = QZ_MAT_DIELECTRIC;
+    m.a = m_ior->flatten(f);
+    m.is_constant = is_constant ? 1u : 0u;
+    return add_material(f, this, m);
+}
+
+int32_t ThinDielectricMaterial::flatten(qzhost::Flattener& f) const {
+    int32_t id = find_material(f, this);
+    if (id >= 0) return id;
+    qz_material m{};
+    m.kind = QZ_MAT_THIN_DIELECTRIC;
+    m.a = m_ior->flatten(f);
+    m.is_constant = is_constant ? 1u : 0u;
+    return add_material(f, this, m);
+}
+
+int32_t qzhost::flatten_mixed(Flattener& f, const void* key, const Material* const* parts, size_t n) {
+    int32_t id = find_material(f, key);
+    if (id >= 0) return id;
+    std::vector<int32_t> children(n);
+    for (size_t i = 0; i < n; i++) children[i] = parts[i]->flatten(f);
+    qz_material m{};
+    m.kind = QZ_MAT_MIXED;
+    m.a = int32_t(f.mixed_children.size());
+    m.count = uint32_t(n);
+    f.mixed_children.insert(f.mixed_children.end(), children.begin(), children.end());
+    return add_material(f, key, m);
+}
+
+int32_t PointLight::flatten(qzhost::Flattener& f) const {
+    qz_light l{};
+    l.kind = QZ_LIGHT_POINT;
+    l.spectrum = m_spectrum->flatten(f);
+    l.scale = m_scale;
+    l.p[0] = m_point.x; l.p[1] = m_point.y; l.p[2] = m_point.z;
+    f.lights.push_back(l);
+    return int32_t(f.lights.size()) - 1;
+}
+
+int32_t AreaLight::flatten(qzhost::Flattener& f) const {
+    qz_light l{};
+    l.spectrum = m_spectrum->flatten(f);
+    l.scale = m_scale;
+    l.two_sided = m_two_sided ? 1u : 0u;
+    // ShapeSample::pdf and AreaLight::pdf are both 1.0f / area() (shape.hpp:47,52-55,82,89-91)
+    l.inv_area = 1.0f / m_shape->area();
+    if (m_shape->type() == ShapeType::QUAD) {
+        const Quad* q = static_cast<const Quad*>(m_shape.get());
+        l.kind = QZ_LIGHT_AREA_QUAD;
+        l.p[0] = q->p00().x; l.p[1] = q->p00().y; l.p[2] = q->p00().z;
+        l.du[0] = q->du().x; l.du[1] = q->du().y; l.du[2] = q->du().z;
+        l.dv[0] = q->dv().x; l.dv[1] = q->dv().y; l.dv[2] = q->dv().z;
+        l.normal[0] = q->normal().x; l.normal[1] = q->normal().y; l.normal[2] = q->normal().z;
+    } else {
+        const Sphere* s = static_cast<const Sphere*>(m_shape.get());
+        l.kind = QZ_LIGHT_AREA_SPHERE;
+        l.p[0] = s->m_center.x; l.p[1] = s->m_center.y; l.p[2] = s->m_center.z;
+        l.radius = s->m_radius;
+    }
+    f.lights.push_back(l);
+    return int32_t(f.lights.size()) - 1;
+}
+
+// ---------------------------------------------------------------- render()
+namespace qzhost {
+
+static thread_local qz_stats g_last_stats{};
+const qz_stats& last_render_stats() { return g_last_stats; }
+
+qz_camera flatten_camera(const Camera& camera, std::vector<float>& sensor_storage) {
+    qz_camera c{};
+    c.image_width = uint32_t(camera.image_width);
+    c.image_height = uint32_t(camera.image_height);
+    const Vec3* src[4] = {&camera.pos, &camera.viewport_bottom_left, &camera.pixel_delta_u, &camera.pixel_delta_v};
+    float* dst[4] = {c.pos, c.viewport_bottom_left, c.pixel_delta_u, c.pixel_delta_v};
+    for (int i = 0; i < 4; i++) { dst[i][0] = src[i]->x; dst[i][1] = src[i]->y; dst[i][2] = src[i]->z; }
+    // the sensor's curves are DenselySampledSpectrum copies over 360..830 nm (sensor.hpp:31-35)
+    const DenselySampledSpectrum* curves[3] = {&camera.sensor.curve_r(), &camera.sensor.curve_g(), &camera.sensor.curve_b()};
+    const size_t n = size_t(LAMBDA_MAX - LAMBDA_MIN + 1);
+    sensor_storage.assign(3 * n, 0.0f);
+    for (int k = 0; k < 3; k++)
+        for (size_t i = 0; i < n; i++) sensor_storage[k * n + i] = (*curves[k])(float(LAMBDA_MIN + int(i)));
+    c.sensor_rgb = sensor_storage.data();
+    c.imaging_ratio = camera.sensor.imaging_ratio();
+    return c;
+}
+
+}  // namespace qzhost
+
+RenderResult render(const Camera& camera, const Scene& scene, size_t n_samples, size_t max_bounces) {
+    RenderResult result(camera.image_height, camera.image_width);
+    if (!scene.ready()) {
+        std::cout << "Scene must be committed before rendering." << std::endl;
+        return result;
+    }
+    std::vector<float> sensor;
+    qz_camera cam = qzhost::flatten_camera(camera, sensor);
+    qz_stats stats{};
+    int rc = qz_render(scene.handle(), &cam, uint32_t(n_samples), uint32_t(max_bounces), nullptr, nullptr,
+                       result.color_buffer.data(), result.normal_buffer.data(), result.albedo_buffer.data(), &stats);
+    if (rc != QZ_OK) {
+        std::cerr << "error: render failed: " << qz_last_error() << std::endl;
+        return RenderResult(camera.image_height, camera.image_width);
+    }
+    qzhost::g_last_stats = stats;
+    std::cout << "Render time: " << stats.ms_total * 1e-3f << "s" << std::endl;
+    return result;
+}
+
+// ---------------------------------------------------------------- Image output
+static void write_image(const std::string& filename, const std::vector<float>& buf, size_t w, size_t h, float gamma) {
+    FILE* f = std::fopen(filename.c_str(), "wb");
+    if (!f) {
+        std::cerr << "Unable to open file " << filename << std::endl;
+        return;
+    }
+    bool ppm = filename.size() >= 4 && filename.compare(filename.size() - 4, 4, ".ppm") == 0;
+    if (ppm) {
+        // 8-bit: x255 with the gamma exponent applied the way the reference does (image.cpp:10-15)
+        std::fprintf(f, "P6\n%zu %zu\n255\n", w, h);
+        std::vector<unsigned char> row(w * 3);
+        for (size_t y = 0; y < h; y++) {
+            for (size_t i = 0; i < w * 3; i++) {
+                float v = 255.0f * powf(buf[y * w * 3 + i], gamma);
+                row[i] = (unsigned char)(v < 0.0f ? 0.0f : (v > 255.0f ? 255.0f : v));
+            }
+            std::fwrite(row.data(), 1, row.size(), f);
+        }
+    } else {
+        std::fprintf(f, "PF\n%zu %zu\n-1.0\n", w, h);
+        for (size_t row = h; row-- > 0;) std::fwrite(buf.data() + row * w * 3, sizeof(float), w * 3, f);
+    }
+    std::fclose(f);
+}
+
+void Image::save(const std::string& filename, float gamma) const { write_image(filename, color_buffer, width, height, gamma); }
+void Image::denoise(bool) { std::cerr << "denoise: OpenImageDenoise is not part of this build; image left unchanged" << std::endl; }
+void RenderResult::denoise(bool) { std::cerr << "denoise: OpenImageDenoise is not part of this build; image left unchanged" << std::endl; }
+void RenderResult::save_normal(const std::string& filename) const { write_image(filename, normal_buffer, width, height, 1.0f); }
+void RenderResult::save_albedo(const std::string& filename) const { write_image(filename, albedo_buffer, width, height, 1.0f); }

@@ -1,0 +1,197 @@
+// TEST INFRASTRUCTURE ONLY -- never built into, shipped with or loaded by the product.
+//
+// Host emulation of the CUDA library's C ABI (include/qz_b200.h): the device headers of
+// quetzalcoatlus_b200/csrc are compiled here with plain g++ (QZ_HD = inline) and every
+// kernel body is run in a sequential loop.  Purpose: let the CPU-only test-suite (no GPU in
+// the development container) check the device-code restatement -- sampler, spectra, BxDFs,
+// intersection, the LBVH build and traversal, the path loop -- against the oracle, bit for
+// bit except for nothing: in this build the transcendental functions are the host libm's.
+// What it cannot cover is the wavefront scheduling, queues and film kernels of
+// wavefront.cu; those are covered by the -m gpu tests.
+//
+// The product never routes through this file: bench.py, __graft_entry__.smoke() and the
+// quetzalcoatlus_b200 package load libqz_b200.so only, which fails loudly without a GPU.
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "scene_store.cuh"
+
+using namespace qz;
+
+namespace {
+
+struct SeqExec {
+    template <class T> T* alloc(size_t n) { return static_cast<T*>(std::malloc((n ? n : 1) * sizeof(T))); }
+    void free(void* p) { std::free(p); }
+    template <class T> void upload(T* dst, const T* src, size_t n) { std::memcpy(dst, src, n * sizeof(T)); }
+    template <class T> void download(T* dst, const T* src, size_t n) { std::memcpy(dst, src, n * sizeof(T)); }
+    void zero(void* p, size_t bytes) { std::memset(p, 0, bytes); }
+    template <class F> void parallel_for(uint32_t n, F f) { for (uint32_t i = 0; i < n; i++) f(i); }
+    void sort_u64(uint64_t* keys, uint32_t n) { std::sort(keys, keys + n); }
+};
+
+thread_local std::string g_error;
+SeqExec g_exec;
+SamplerDim g_sampler_table[QZ_N_PRIMES];
+float g_rho_tab[16 * 8];
+bool g_tables_ready = false;
+
+void ensure_tables() {
+    if (g_tables_ready) return;
+    build_sampler_table(g_sampler_table);
+    build_rho_table(g_rho_tab);
+    g_tables_ready = true;
+}
+
+DCamera make_camera(const qz_camera* c) {
+    DCamera d;
+    d.width = c->image_width; d.height = c->image_height;
+    d.pos = v3(c->pos[0], c->pos[1], c->pos[2]);
+    d.bottom_left = v3(c->viewport_bottom_left[0], c->viewport_bottom_left[1], c->viewport_bottom_left[2]);
+    d.du = v3(c->pixel_delta_u[0], c->pixel_delta_u[1], c->pixel_delta_u[2]);
+    d.dv = v3(c->pixel_delta_v[0], c->pixel_delta_v[1], c->pixel_delta_v[2]);
+    d.sensor = c->sensor_rgb;
+    d.imaging_ratio = c->imaging_ratio;
+    return d;
+}
+
+}  // namespace
+
+struct qz_scene_t {
+    SceneStore<SeqExec> store;
+};
+
+extern "C" {
+
+const char* qz_last_error(void) { return g_error.c_str(); }
+int qz_abi_version(void) { return QZ_ABI_VERSION; }
+int qz_init(int) { ensure_tables(); return QZ_OK; }
+int qz_device_name(char* buf, size_t n) { std::snprintf(buf, n, "host emulation (tests only)"); return QZ_OK; }
+
+int qz_scene_create(qz_scene* out) { ensure_tables(); *out = new qz_scene_t(); return QZ_OK; }
+int qz_scene_destroy(qz_scene s) { if (s) { s->store.release(g_exec); delete s; } return QZ_OK; }
+
+int qz_scene_commit(qz_scene s, const qz_scene_tables* t) {
+    std::string why = SceneStore<SeqExec>::validate(*t);
+    if (!why.empty()) { g_error = why; return QZ_ERR_INVALID; }
+    if (!s->store.commit(g_exec, *t, g_sampler_table, g_rho_tab)) { g_error = "BVH build failed"; return QZ_ERR_INVALID; }
+    return QZ_OK;
+}
+
+int qz_trace_paths(qz_scene s, const qz_camera* camera, uint32_t n_samples, uint32_t max_bounces, uint32_t n,
+                   const int32_t* xys, float* records) {
+    (void)n_samples;
+    if (!s->store.committed) { g_error = "scene not committed"; return QZ_ERR_NOT_COMMITTED; }
+    DCamera cam = make_camera(camera);
+    SamplerParams spar = make_sampler_params((int)cam.width, (int)cam.height);
+    for (uint32_t i = 0; i < n; i++) {
+        PathState ps; PathAov aov; Spec4 lambda0;
+        run_path<false>(s->store.view, cam, spar, (uint32_t)xys[3 * i], (uint32_t)xys[3 * i + 1], (uint32_t)xys[3 * i + 2],
+                        max_bounces, ps, aov, lambda0, nullptr);
+        V3 rgb = to_sensor_rgb(cam, ps.L, ps.lambda, ps.pdf);
+        V3 argb = to_sensor_rgb(cam, aov.albedo, ps.lambda, ps.pdf);
+        write_trace_record(records + (size_t)i * 32, ps, aov, lambda0, rgb, argb);
+    }
+    return QZ_OK;
+}
+
+// per-pixel loop in the reference's order (render.cpp:260-294); no wavefront here
+int qz_render(qz_scene s, const qz_camera* camera, uint32_t n_samples, uint32_t max_bounces, const qz_region* region,
+              const qz_render_options*, float* color, float* normal, float* albedo, qz_stats* stats) {
+    if (!s->store.committed) { g_error = "scene not committed"; return QZ_ERR_NOT_COMMITTED; }
+    DCamera cam = make_camera(camera);
+    SamplerParams spar = make_sampler_params((int)cam.width, (int)cam.height);
+    qz_stats st{};
+    for (uint32_t row = 0; row < cam.height; row++) {
+        if (region && region->strip_rows && region->n_shards > 1 && (row / region->strip_rows) % region->n_shards != region->shard) continue;
+        for (uint32_t x = 0; x < cam.width; x++) {
+            uint32_t y = cam.height - row - 1;
+            V3 c = v3(0, 0, 0), nn = v3(0, 0, 0), a = v3(0, 0, 0);
+            for (uint32_t sidx = 0; sidx < n_samples; sidx++) {
+                PathState ps; PathAov aov; Spec4 lambda0;
+                run_path<false>(s->store.view, cam, spar, x, y, sidx, max_bounces, ps, aov, lambda0, nullptr);
+                c = c + to_sensor_rgb(cam, ps.L, ps.lambda, ps.pdf);
+                a = a + to_sensor_rgb(cam, aov.albedo, ps.lambda, ps.pdf);
+                nn = nn + aov.normal;
+                st.paths++; st.rays_closest += ps.n_rays;
+            }
+            c = c / (float)n_samples; a = a / (float)n_samples; nn = nn / (float)n_samples;
+            size_t i = ((size_t)row * cam.width + x) * 3;
+            color[i] = c.x; color[i + 1] = c.y; color[i + 2] = c.z;
+            if (normal) { normal[i] = nn.x; normal[i + 1] = nn.y; normal[i + 2] = nn.z; }
+            if (albedo) { albedo[i] = a.x; albedo[i + 1] = a.y; albedo[i + 2] = a.z; }
+        }
+    }
+    if (stats) *stats = st;
+    return QZ_OK;
+}
+
+int qz_render_device(qz_scene, const qz_camera*, uint32_t, uint32_t, const qz_region*, const qz_render_options*, float*,
+                     float*, float*, void*, qz_stats*) {
+    g_error = "host emulation has no device path";
+    return QZ_ERR_NO_DEVICE;
+}
+
+int qz_sampler_eval(uint32_t, uint32_t width, uint32_t height, uint32_t n, const int32_t* q, float* out) {
+    ensure_tables();
+    SamplerParams spar = make_sampler_params((int)width, (int)height);
+    for (uint32_t i = 0; i < n; i++) {
+        Sampler smp = sampler_start(spar, (uint32_t)q[4 * i], (uint32_t)q[4 * i + 1], (uint32_t)q[4 * i + 2]);
+        int dim = q[4 * i + 3];
+        if (dim < 2) {
+            V2 j = sampler_pixel_jitter(spar, smp);
+            out[i] = dim == 0 ? j.x : j.y;
+        } else {
+            smp.dim = (uint32_t)dim;
+            out[i] = sample_1d(g_sampler_table, smp);
+        }
+    }
+    return QZ_OK;
+}
+
+int qz_intersect(qz_scene s, uint32_t n, const float* rays, float* out) {
+    if (!s->store.committed) { g_error = "scene not committed"; return QZ_ERR_NOT_COMMITTED; }
+    const DScene& sc = s->store.view;
+    for (uint32_t i = 0; i < n; i++) {
+        Ray r;
+        r.o = v3(rays[6 * i], rays[6 * i + 1], rays[6 * i + 2]);
+        r.d = v3(rays[6 * i + 3], rays[6 * i + 4], rays[6 * i + 5]);
+        Hit h;
+        float* o = out + 8 * i;
+        if (!closest_hit<false>(sc, r, h, nullptr)) {
+            o[0] = -1.0f;
+            for (int k = 1; k < 8; k++) o[k] = 0.0f;
+        } else {
+            const F4* rec = sc.prims + (size_t)h.prim * 4;
+            o[0] = h.t; o[1] = h.u; o[2] = h.v; o[3] = h.ng.x; o[4] = h.ng.y; o[5] = h.ng.z;
+            o[6] = (float)float_as_u32(rec[0].w);
+            o[7] = (float)float_as_u32(rec[1].w);
+        }
+    }
+    return QZ_OK;
+}
+
+int qz_eval_spectrum(qz_scene s, int32_t id, uint32_t n, const float* lambdas, float* out) {
+    if (!s->store.committed) { g_error = "scene not committed"; return QZ_ERR_NOT_COMMITTED; }
+    const DScene& sc = s->store.view;
+    if (id < 0) id = sc.bg_spectrum;
+    if (id < 0) { g_error = "no such spectrum"; return QZ_ERR_INVALID; }
+    for (uint32_t i = 0; i < n; i++) out[i] = eval_spectrum(sc, id, lambdas[i]);
+    return QZ_OK;
+}
+
+int qz_sensor_eval(const qz_camera* camera, uint32_t n, const float* in, float* out) {
+    DCamera cam = make_camera(camera);
+    for (uint32_t i = 0; i < n; i++) {
+        Spec4 lambda, pdf;
+        sample_wavelengths(in[5 * i], lambda, pdf);
+        V3 rgb = to_sensor_rgb(cam, spec4(in[5 * i + 1], in[5 * i + 2], in[5 * i + 3], in[5 * i + 4]), lambda, pdf);
+        out[3 * i] = rgb.x; out[3 * i + 1] = rgb.y; out[3 * i + 2] = rgb.z;
+    }
+    return QZ_OK;
+}
+
+}  // extern "C"
