@@ -124,7 +124,7 @@ typedef struct qz_geometry {
 /* One primitive = 64 bytes = four float4.  x,y,z of v[0..3] are vertices (sphere: v[0] = centre,
  * v[1].x = radius); the w lanes carry integers (bit patterns):
  *   v[0].w = geomID   v[1].w = primID (as Embree reports it)   v[2].w = qz_prim_kind
- *   v[3].w = grid cell: x | y << 16 (grid resolution minus one lives in v[2]/v[3] of... see grid_dims)
+ *   v[3].w = grid cell: x | y << 16 (the grid's resolution minus one is in grid_dims[geomID])
  * Primitives are ordered by (geomID, primID, cell); that order is the tie-break of the
  * closest-hit search.                                                                     */
 typedef enum qz_prim_kind { QZ_PRIM_TRIANGLE = 0, QZ_PRIM_QUAD = 1, QZ_PRIM_SPHERE = 2, QZ_PRIM_GRIDCELL = 3 } qz_prim_kind;
@@ -175,6 +175,7 @@ typedef struct qz_region {
 
 #define QZ_FLAG_UNSORTED_SHADING 1u /* one uber shading kernel over the unsorted queue (evidence runs only) */
 #define QZ_FLAG_COUNT_TRAVERSAL 2u  /* count wide-node visits and primitive tests (slower; for B_ray)        */
+#define QZ_FLAG_STAGE_TIMING 4u     /* CUDA events around every stage (serialises the pipeline; for profiles) */
 
 typedef struct qz_render_options {
     uint32_t flags;
@@ -244,7 +245,7 @@ int qz_sampler_eval(uint32_t n_samples, uint32_t width, uint32_t height, uint32_
 int qz_intersect(qz_scene scene, uint32_t n, const float* rays, float* out);
 
 /* Spectrum::operator() on the device, for table parity: evaluates spectrum `id` of the
- * committed scene at n wavelengths.                                                       */
+ * committed scene (id < 0: the background spectrum) at n wavelengths.                     */
 int qz_eval_spectrum(qz_scene scene, int32_t id, uint32_t n, const float* lambdas, float* out);
 
 /* PixelSensor::to_sensor_rgb on the device (sensor.cpp:57-70): n x (u, L0..L3) -> n x rgb */

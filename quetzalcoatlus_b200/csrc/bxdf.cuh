@@ -398,7 +398,6 @@ QZ_HD Spec4 bsdf_rho_hd(const DScene& sc, const Bsdf& f, V3 wo_r) {
     return acc / 16.0f;
 }
 
-#if !defined(__CUDA_ARCH__)
 inline void build_rho_table(float* out /* 16 x 8 */) {
     // render.cpp:153-167 (double literals narrowed to float, as the std::array initialisers do)
     const float uc[16] = {0.75741637, 0.37870818, 0.7083487, 0.18935409, 0.9149363, 0.35417435, 0.5990858, 0.09467703,
@@ -416,6 +415,5 @@ inline void build_rho_table(float* out /* 16 x 8 */) {
         t[6] = p.x; t[7] = p.y;
     }
 }
-#endif
 
 }  // namespace qz

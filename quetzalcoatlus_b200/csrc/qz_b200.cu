@@ -1,0 +1,589 @@
+// C ABI of the B200 path-tracing hot path (include/qz_b200.h) and the host-side driver of
+// the wavefront pipeline.  One translation unit, compiled for sm_100a only:
+//   nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false --extended-lambda -lineinfo
+// -fmad=false is part of the arithmetic contract (common.cuh): with contraction off the
+// float32 path is bit-identical to the reference's x86-64 build.
+//
+// No CPU fallback exists in this library: every entry point that computes needs a CUDA
+// device and fails with QZ_ERR_NO_DEVICE / QZ_ERR_CUDA otherwise.
+#include <cuda_runtime.h>
+
+#include <cub/device/device_radix_sort.cuh>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "scene_store.cuh"
+#include "wavefront.cuh"
+
+using namespace qz;
+
+namespace {
+
+thread_local std::string g_error;
+
+int fail(int code, const std::string& msg) {
+    g_error = msg;
+    return code;
+}
+
+#define QZ_CUDA(call)                                                                              \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            g_error = std::string(#call) + ": " + cudaGetErrorString(e_);                          \
+            return (e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver) ? QZ_ERR_NO_DEVICE \
+                   : (e_ == cudaErrorMemoryAllocation ? QZ_ERR_OOM : QZ_ERR_CUDA);                 \
+        }                                                                                          \
+    } while (0)
+
+template <class F>
+__global__ void k_parallel_for(uint32_t n, F f) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) f(i);
+}
+
+// Executor of the shared build / commit code (bvh_build.cuh, scene_store.cuh) on the GPU.
+// Errors are sticky: the first failing CUDA call is remembered and reported by commit.
+struct CudaExec {
+    cudaError_t err = cudaSuccess;
+    void note(cudaError_t e) { if (err == cudaSuccess && e != cudaSuccess) err = e; }
+
+    template <class T> T* alloc(size_t n) {
+        void* p = nullptr;
+        note(cudaMalloc(&p, (n ? n : 1) * sizeof(T)));
+        return static_cast<T*>(p);
+    }
+    void free(void* p) { if (p) cudaFree(p); }
+    template <class T> void upload(T* dst, const T* src, size_t n) { if (n) note(cudaMemcpy(dst, src, n * sizeof(T), cudaMemcpyHostToDevice)); }
+    template <class T> void download(T* dst, const T* src, size_t n) { if (n) note(cudaMemcpy(dst, src, n * sizeof(T), cudaMemcpyDeviceToHost)); }
+    void zero(void* p, size_t bytes) { if (bytes) note(cudaMemset(p, 0, bytes)); }
+    template <class F> void parallel_for(uint32_t n, F f) {
+        if (!n || err != cudaSuccess) return;
+        uint32_t blocks = std::min<uint32_t>((n + 255u) / 256u, 148u * 16u);
+        k_parallel_for<<<blocks, 256>>>(n, f);
+        note(cudaGetLastError());
+    }
+    void sort_u64(uint64_t* keys, uint32_t n) {
+        if (err != cudaSuccess) return;
+        uint64_t* tmp_keys = alloc<uint64_t>(n);
+        size_t bytes = 0;
+        note(cub::DeviceRadixSort::SortKeys(nullptr, bytes, keys, tmp_keys, (int)n));
+        void* scratch = nullptr;
+        note(cudaMalloc(&scratch, bytes ? bytes : 1));
+        note(cub::DeviceRadixSort::SortKeys(scratch, bytes, keys, tmp_keys, (int)n));
+        note(cudaMemcpy(keys, tmp_keys, (size_t)n * sizeof(uint64_t), cudaMemcpyDeviceToDevice));
+        cudaFree(scratch);
+        cudaFree(tmp_keys);
+    }
+};
+
+// per-device constant tables (sampler dimensions, depth-0 albedo sample warps)
+struct DeviceTables {
+    SamplerDim* sampler = nullptr;
+    float* rho = nullptr;
+};
+std::mutex g_tables_mutex;
+DeviceTables g_tables[64];
+
+int device_tables(int dev, DeviceTables& out) {
+    std::lock_guard<std::mutex> lock(g_tables_mutex);
+    if (dev < 0 || dev >= 64) return fail(QZ_ERR_INVALID, "device ordinal out of range");
+    DeviceTables& t = g_tables[dev];
+    if (!t.sampler) {
+        std::vector<SamplerDim> host(QZ_N_PRIMES);
+        build_sampler_table(host.data());
+        float rho[16 * 8];
+        build_rho_table(rho);
+        QZ_CUDA(cudaMalloc(&t.sampler, host.size() * sizeof(SamplerDim)));
+        QZ_CUDA(cudaMemcpy(t.sampler, host.data(), host.size() * sizeof(SamplerDim), cudaMemcpyHostToDevice));
+        QZ_CUDA(cudaMalloc(&t.rho, sizeof(rho)));
+        QZ_CUDA(cudaMemcpy(t.rho, rho, sizeof(rho), cudaMemcpyHostToDevice));
+    }
+    out = t;
+    return QZ_OK;
+}
+
+thread_local int g_device = -1;
+
+int ensure_device() {
+    if (g_device >= 0) {
+        QZ_CUDA(cudaSetDevice(g_device));
+        return QZ_OK;
+    }
+    return qz_init(0);
+}
+
+DCamera make_camera(const qz_camera* c, const float* d_sensor) {
+    DCamera d;
+    d.width = c->image_width; d.height = c->image_height;
+    d.pos = v3(c->pos[0], c->pos[1], c->pos[2]);
+    d.bottom_left = v3(c->viewport_bottom_left[0], c->viewport_bottom_left[1], c->viewport_bottom_left[2]);
+    d.du = v3(c->pixel_delta_u[0], c->pixel_delta_u[1], c->pixel_delta_u[2]);
+    d.dv = v3(c->pixel_delta_v[0], c->pixel_delta_v[1], c->pixel_delta_v[2]);
+    d.sensor = d_sensor;
+    d.imaging_ratio = c->imaging_ratio;
+    return d;
+}
+
+// ------------------------------------------------------------------ small kernels of the probes
+__global__ void k_trace_paths(DScene sc, DCamera cam, SamplerParams spar, uint32_t max_bounces, uint32_t n,
+                              const int32_t* xys, float* records) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    PathState ps;
+    PathAov aov;
+    Spec4 lambda0;
+    run_path<false>(sc, cam, spar, (uint32_t)xys[3 * i], (uint32_t)xys[3 * i + 1], (uint32_t)xys[3 * i + 2], max_bounces, ps,
+                    aov, lambda0, nullptr);
+    V3 rgb = to_sensor_rgb(cam, ps.L, ps.lambda, ps.pdf);
+    V3 argb = to_sensor_rgb(cam, aov.albedo, ps.lambda, ps.pdf);
+    write_trace_record(records + (size_t)i * 32, ps, aov, lambda0, rgb, argb);
+}
+
+__global__ void k_sampler_eval(const SamplerDim* table, SamplerParams spar, uint32_t n, const int32_t* q, float* out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Sampler smp = sampler_start(spar, (uint32_t)q[4 * i], (uint32_t)q[4 * i + 1], (uint32_t)q[4 * i + 2]);
+    const int dim = q[4 * i + 3];
+    if (dim < 2) {
+        V2 j = sampler_pixel_jitter(spar, smp);
+        out[i] = dim == 0 ? j.x : j.y;
+    } else {
+        smp.dim = (uint32_t)dim;
+        out[i] = sample_1d(table, smp);
+    }
+}
+
+__global__ void k_intersect(DScene sc, uint32_t n, const float* rays, float* out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Ray r;
+    r.o = v3(rays[6 * i], rays[6 * i + 1], rays[6 * i + 2]);
+    r.d = v3(rays[6 * i + 3], rays[6 * i + 4], rays[6 * i + 5]);
+    Hit h;
+    float* o = out + 8 * (size_t)i;
+    if (!closest_hit<false>(sc, r, h, nullptr)) {
+        o[0] = -1.0f;
+        for (int k = 1; k < 8; k++) o[k] = 0.0f;
+    } else {
+        const F4* rec = sc.prims + (size_t)h.prim * 4;
+        o[0] = h.t; o[1] = h.u; o[2] = h.v; o[3] = h.ng.x; o[4] = h.ng.y; o[5] = h.ng.z;
+        o[6] = (float)float_as_u32(rec[0].w);
+        o[7] = (float)float_as_u32(rec[1].w);
+    }
+}
+
+__global__ void k_eval_spectrum(DScene sc, int32_t id, uint32_t n, const float* lambdas, float* out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = eval_spectrum(sc, id, lambdas[i]);
+}
+
+__global__ void k_sensor_eval(DCamera cam, uint32_t n, const float* in, float* out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Spec4 lambda, pdf;
+    sample_wavelengths(in[5 * i], lambda, pdf);
+    V3 rgb = to_sensor_rgb(cam, spec4(in[5 * i + 1], in[5 * i + 2], in[5 * i + 3], in[5 * i + 4]), lambda, pdf);
+    out[3 * i] = rgb.x; out[3 * i + 1] = rgb.y; out[3 * i + 2] = rgb.z;
+}
+
+// RAII device buffer
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+    template <class T> T* as() { return static_cast<T*>(p); }
+};
+
+}  // namespace
+
+struct qz_scene_t {
+    SceneStore<CudaExec> store;
+    int device = 0;
+    DeviceTables tables;
+};
+
+extern "C" {
+
+const char* qz_last_error(void) { return g_error.c_str(); }
+int qz_abi_version(void) { return QZ_ABI_VERSION; }
+
+int qz_init(int device) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(QZ_ERR_NO_DEVICE, std::string("no CUDA device available (") + cudaGetErrorString(e) +
+                                          "); this library has no CPU fallback");
+    if (device < 0 || device >= count) return fail(QZ_ERR_INVALID, "device ordinal out of range");
+    QZ_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    QZ_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(QZ_ERR_NO_DEVICE, std::string("device '") + prop.name + "' is not a Blackwell (sm_100a) GPU; this library is built for sm_100a only");
+    g_device = device;
+    DeviceTables t;
+    return device_tables(device, t);
+}
+
+int qz_device_name(char* buf, size_t n) {
+    int rc = ensure_device();
+    if (rc) return rc;
+    cudaDeviceProp prop;
+    QZ_CUDA(cudaGetDeviceProperties(&prop, g_device));
+    std::snprintf(buf, n, "%s", prop.name);
+    return QZ_OK;
+}
+
+int qz_scene_create(qz_scene* out) {
+    if (!out) return fail(QZ_ERR_INVALID, "null output pointer");
+    int rc = ensure_device();
+    if (rc) return rc;
+    qz_scene s = new qz_scene_t();
+    s->device = g_device;
+    rc = device_tables(g_device, s->tables);
+    if (rc) { delete s; return rc; }
+    *out = s;
+    return QZ_OK;
+}
+
+int qz_scene_destroy(qz_scene s) {
+    if (!s) return QZ_OK;
+    cudaSetDevice(s->device);
+    CudaExec ex;
+    s->store.release(ex);
+    delete s;
+    return QZ_OK;
+}
+
+int qz_scene_commit(qz_scene s, const qz_scene_tables* t) {
+    if (!s || !t) return fail(QZ_ERR_INVALID, "null argument");
+    QZ_CUDA(cudaSetDevice(s->device));
+    std::string why = SceneStore<CudaExec>::validate(*t);
+    if (!why.empty()) return fail(QZ_ERR_INVALID, "invalid scene tables: " + why);
+    CudaExec ex;
+    bool ok = s->store.commit(ex, *t, s->tables.sampler, s->tables.rho);
+    ex.note(cudaDeviceSynchronize());
+    if (!ok || ex.err != cudaSuccess) {
+        s->store.committed = false;
+        return fail(ex.err == cudaErrorMemoryAllocation ? QZ_ERR_OOM : QZ_ERR_CUDA,
+                    std::string("scene commit failed: ") + cudaGetErrorString(ex.err));
+    }
+    return QZ_OK;
+}
+
+// ------------------------------------------------------------------ render
+static int render_impl(qz_scene s, const qz_camera* camera, uint32_t n_samples, uint32_t max_bounces, const qz_region* region,
+                       const qz_render_options* options, float* d_color, float* d_normal, float* d_albedo,
+                       cudaStream_t stream, qz_stats* stats_out) {
+    const DScene& sc = s->store.view;
+    const uint32_t W = camera->image_width, H = camera->image_height;
+    if (!W || !H || !n_samples) return fail(QZ_ERR_INVALID, "empty image or zero samples");
+    if (max_bounces > 255) return fail(QZ_ERR_INVALID, "max_bounces > 255 is not supported");
+    SamplerParams spar = make_sampler_params((int)W, (int)H);
+    if ((uint64_t)n_samples * spar.stride >= (1ull << 31)) return fail(QZ_ERR_INVALID, "n_samples too large for the 32-bit Halton index");
+    const uint32_t flags = options ? options->flags : 0u;
+
+    // rows owned by this call
+    std::vector<uint32_t> rows;
+    for (uint32_t r = 0; r < H; r++) {
+        if (region && region->strip_rows && region->n_shards > 1) {
+            if ((r / region->strip_rows) % region->n_shards != region->shard) continue;
+        }
+        rows.push_back(r);
+    }
+    qz_stats st{};
+    st.bvh_nodes = s->store.bvh.n_nodes;
+    st.bvh_bytes = (uint32_t)std::min<uint64_t>(0xffffffffull, (uint64_t)s->store.bvh.n_nodes * sizeof(BvhNode) + (uint64_t)sc.n_prims * 64);
+    if (rows.empty()) { if (stats_out) *stats_out = st; return QZ_OK; }
+    const uint64_t n_pix64 = (uint64_t)rows.size() * W;
+    if (n_pix64 >= (1ull << 31)) return fail(QZ_ERR_INVALID, "image too large");
+    const uint32_t n_pix = (uint32_t)n_pix64;
+
+    // pass size: result cells are 36 bytes per pixel-sample; keep a pass under ~6 GB and 2^31 cells
+    uint32_t s_pass = options && options->samples_per_pass ? options->samples_per_pass : 0;
+    if (!s_pass) {
+        uint64_t budget_cells = (6ull << 30) / 36ull;
+        s_pass = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(n_samples, budget_cells / n_pix));
+    }
+    s_pass = std::min(s_pass, n_samples);
+    while ((uint64_t)s_pass * n_pix >= (1ull << 31)) s_pass = std::max(1u, s_pass / 2);
+    const uint64_t cells = (uint64_t)s_pass * n_pix;
+    uint32_t pool = options && options->pool_paths ? options->pool_paths : (1u << 21);
+    pool = (uint32_t)std::min<uint64_t>(pool, cells);
+    pool = std::max(pool, 1u);
+
+    // ---- allocations
+    DevBuf f4bufs[14], qbufs[8], counters, statsb, res_a, res_b, res_c, rowsb, sensor, acc;
+    for (auto& b : f4bufs) QZ_CUDA(b.alloc((size_t)pool * 16));
+    for (auto& b : qbufs) QZ_CUDA(b.alloc((size_t)pool * 4));
+    QZ_CUDA(counters.alloc(C_WORDS * 4));
+    QZ_CUDA(statsb.alloc(S_WORDS * 8));
+    QZ_CUDA(res_a.alloc(cells * 16));
+    QZ_CUDA(res_b.alloc(cells * 16));
+    QZ_CUDA(res_c.alloc(cells * 4));
+    QZ_CUDA(rowsb.alloc(rows.size() * 4));
+    QZ_CUDA(sensor.alloc(3 * 471 * 4));
+    const bool multi_pass = s_pass < n_samples;
+    if (multi_pass) QZ_CUDA(acc.alloc((size_t)n_pix * 9 * 4));
+    QZ_CUDA(cudaMemcpyAsync(rowsb.p, rows.data(), rows.size() * 4, cudaMemcpyHostToDevice, stream));
+    QZ_CUDA(cudaMemcpyAsync(sensor.p, camera->sensor_rgb, 3 * 471 * 4, cudaMemcpyHostToDevice, stream));
+    QZ_CUDA(cudaMemsetAsync(statsb.p, 0, S_WORDS * 8, stream));
+
+    WfBuffers b{};
+    b.ray_o = f4bufs[0].as<float4>(); b.ray_d = f4bufs[1].as<float4>();
+    b.hit_a = f4bufs[2].as<float4>(); b.hit_b = f4bufs[3].as<float4>();
+    b.weight = f4bufs[4].as<float4>(); b.radiance = f4bufs[5].as<float4>();
+    b.lambda = f4bufs[6].as<float4>(); b.lpdf = f4bufs[7].as<float4>();
+    b.misc = f4bufs[8].as<uint4>();
+    b.aov_n = f4bufs[9].as<float4>(); b.aov_a = f4bufs[10].as<float4>();
+    b.sh_o = f4bufs[11].as<float4>(); b.sh_d = f4bufs[12].as<float4>(); b.sh_c = f4bufs[13].as<float4>();
+    b.q_trace[0] = qbufs[0].as<uint32_t>(); b.q_trace[1] = qbufs[1].as<uint32_t>();
+    for (int k = 0; k < SQ_COUNT; k++) b.q_shade[k] = qbufs[2 + k].as<uint32_t>();
+    b.q_shadow = qbufs[6].as<uint32_t>(); b.q_done = qbufs[7].as<uint32_t>();
+    b.counters = counters.as<uint32_t>();
+    b.stats = statsb.as<unsigned long long>();
+    b.res_a = res_a.as<float4>(); b.res_b = res_b.as<float4>(); b.res_c = res_c.as<float>();
+    b.pool = pool;
+
+    DCamera cam = make_camera(camera, sensor.as<float>());
+    const bool count_trav = (flags & QZ_FLAG_COUNT_TRAVERSAL) != 0;
+    const bool stage_timing = (flags & 4u) != 0;
+
+    int n_sm = 148;
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, s->device);
+    const int trav_blocks = n_sm * 8;   // persistent: 8 CTAs of 4 warps per SM
+    const int shade_blocks = n_sm * 8;
+
+    cudaEvent_t ev_begin, ev_end, ev_a, ev_b;
+    QZ_CUDA(cudaEventCreate(&ev_begin)); QZ_CUDA(cudaEventCreate(&ev_end));
+    QZ_CUDA(cudaEventCreate(&ev_a)); QZ_CUDA(cudaEventCreate(&ev_b));
+    QZ_CUDA(cudaEventRecord(ev_begin, stream));
+    uint32_t* h_counters = nullptr;
+    QZ_CUDA(cudaMallocHost(&h_counters, C_WORDS * 4));
+
+    auto timed = [&](float& acc_ms, auto&& launch) -> cudaError_t {
+        if (!stage_timing) { launch(); return cudaGetLastError(); }
+        cudaEventRecord(ev_a, stream);
+        launch();
+        cudaEventRecord(ev_b, stream);
+        cudaEventSynchronize(ev_b);
+        float ms = 0.0f;
+        cudaEventElapsedTime(&ms, ev_a, ev_b);
+        acc_ms += ms;
+        return cudaGetLastError();
+    };
+
+    int rc = QZ_OK;
+    for (uint32_t s_begin = 0; s_begin < n_samples && rc == QZ_OK; s_begin += s_pass) {
+        PassParams pp{};
+        pp.n_pix = n_pix;
+        pp.s_begin = s_begin;
+        pp.s_count = std::min(s_pass, n_samples - s_begin);
+        pp.total = pp.n_pix * pp.s_count;
+        pp.max_bounces = max_bounces;
+        pp.owned_rows = rowsb.as<uint32_t>();
+        pp.width = W; pp.height = H;
+        pp.spar = spar;
+
+        const uint32_t first = std::min<uint32_t>(pool, pp.total);
+        uint32_t init[C_WORDS] = {0};
+        init[C_TRACE0] = first;
+        init[C_NEXT_PATH] = first;
+        QZ_CUDA(cudaMemcpyAsync(b.counters, init, sizeof(init), cudaMemcpyHostToDevice, stream));
+        k_generate<<<shade_blocks, 256, 0, stream>>>(sc, cam, b, pp, first);
+        st.kernel_launches++;
+        QZ_CUDA(cudaGetLastError());
+
+        int cur = 0;
+        uint64_t it = 0;
+        for (;;) {
+            const int nxt = cur ^ 1;
+            QZ_CUDA(timed(st.ms_closest, [&] {
+                if (count_trav) k_closest_hit<true><<<trav_blocks, 128, 0, stream>>>(sc, b, cur, flags);
+                else k_closest_hit<false><<<trav_blocks, 128, 0, stream>>>(sc, b, cur, flags);
+            }));
+            QZ_CUDA(timed(st.ms_shade, [&] {
+                k_shade<KH_ANY><<<shade_blocks, 128, 0, stream>>>(sc, b, SQ_MISC, nxt, max_bounces);
+                if (!(flags & QZ_FLAG_UNSORTED_SHADING)) {
+                    k_shade<KH_DIFFUSE><<<shade_blocks, 128, 0, stream>>>(sc, b, SQ_DIFFUSE, nxt, max_bounces);
+                    k_shade<KH_CONDUCTOR><<<shade_blocks, 128, 0, stream>>>(sc, b, SQ_CONDUCTOR, nxt, max_bounces);
+                    k_shade<KH_DIELECTRIC><<<shade_blocks, 128, 0, stream>>>(sc, b, SQ_DIELECTRIC, nxt, max_bounces);
+                }
+            }));
+            QZ_CUDA(timed(st.ms_shadow, [&] {
+                if (count_trav) k_shadow<true><<<trav_blocks, 128, 0, stream>>>(sc, b);
+                else k_shadow<false><<<trav_blocks, 128, 0, stream>>>(sc, b);
+            }));
+            QZ_CUDA(timed(st.ms_other, [&] {
+                k_finish<<<shade_blocks, 256, 0, stream>>>(sc, cam, b, pp, nxt);
+                k_next_iteration<<<1, 32, 0, stream>>>(b, cur);
+            }));
+            st.kernel_launches += (flags & QZ_FLAG_UNSORTED_SHADING) ? 5 : 8;
+            st.iterations++;
+            it++;
+            cur = nxt;
+            // the active count is read back every 4th iteration (every iteration would serialise host and device)
+            if ((it & 3u) == 0) {
+                QZ_CUDA(cudaMemcpyAsync(h_counters, b.counters, C_WORDS * 4, cudaMemcpyDeviceToHost, stream));
+                QZ_CUDA(cudaStreamSynchronize(stream));
+                if (h_counters[C_TRACE0 + cur] == 0) break;
+            }
+            if (it > 1000000ull) { rc = fail(QZ_ERR_CUDA, "wavefront did not terminate"); break; }
+        }
+        if (rc != QZ_OK) break;
+        const bool first_pass = s_begin == 0, last_pass = s_begin + pp.s_count >= n_samples;
+        k_film<<<shade_blocks, 256, 0, stream>>>(b, pp, acc.as<float>(), first_pass, last_pass, n_samples, d_color, d_normal, d_albedo);
+        st.kernel_launches++;
+        QZ_CUDA(cudaGetLastError());
+    }
+    QZ_CUDA(cudaEventRecord(ev_end, stream));
+    QZ_CUDA(cudaEventSynchronize(ev_end));
+    QZ_CUDA(cudaEventElapsedTime(&st.ms_total, ev_begin, ev_end));
+    unsigned long long h_stats[S_WORDS];
+    QZ_CUDA(cudaMemcpy(h_stats, b.stats, sizeof(h_stats), cudaMemcpyDeviceToHost));
+    st.paths = (uint64_t)n_pix * n_samples;
+    st.rays_closest = h_stats[S_RAYS_CLOSEST];
+    st.rays_shadow = h_stats[S_RAYS_SHADOW];
+    st.shade_calls = h_stats[S_SHADE];
+    st.node_visits = h_stats[S_NODES];
+    st.prim_tests = h_stats[S_PRIMS];
+    cudaFreeHost(h_counters);
+    cudaEventDestroy(ev_begin); cudaEventDestroy(ev_end); cudaEventDestroy(ev_a); cudaEventDestroy(ev_b);
+    if (rc == QZ_OK && h_stats[S_PATHS_DONE] != st.paths) rc = fail(QZ_ERR_CUDA, "internal error: finished path count does not match");
+    if (stats_out) *stats_out = st;
+    return rc;
+}
+
+int qz_render_device(qz_scene s, const qz_camera* camera, uint32_t n_samples, uint32_t max_bounces, const qz_region* region,
+                     const qz_render_options* options, float* d_color, float* d_normal, float* d_albedo, void* cuda_stream,
+                     qz_stats* stats) {
+    if (!s || !camera || !d_color) return fail(QZ_ERR_INVALID, "null argument");
+    if (!s->store.committed) return fail(QZ_ERR_NOT_COMMITTED, "Scene must be committed before rendering.");
+    QZ_CUDA(cudaSetDevice(s->device));
+    return render_impl(s, camera, n_samples, max_bounces, region, options, d_color, d_normal, d_albedo,
+                       static_cast<cudaStream_t>(cuda_stream), stats);
+}
+
+int qz_render(qz_scene s, const qz_camera* camera, uint32_t n_samples, uint32_t max_bounces, const qz_region* region,
+              const qz_render_options* options, float* color, float* normal, float* albedo, qz_stats* stats) {
+    if (!s || !camera || !color) return fail(QZ_ERR_INVALID, "null argument");
+    if (!s->store.committed) return fail(QZ_ERR_NOT_COMMITTED, "Scene must be committed before rendering.");
+    QZ_CUDA(cudaSetDevice(s->device));
+    const size_t n = (size_t)camera->image_width * camera->image_height * 3;
+    DevBuf dc, dn, da;
+    QZ_CUDA(dc.alloc(n * 4));
+    if (normal) QZ_CUDA(dn.alloc(n * 4));
+    if (albedo) QZ_CUDA(da.alloc(n * 4));
+    const bool sharded = region && region->strip_rows && region->n_shards > 1;
+    if (sharded) {
+        // rows this call does not own keep the caller's contents
+        QZ_CUDA(cudaMemcpy(dc.p, color, n * 4, cudaMemcpyHostToDevice));
+        if (normal) QZ_CUDA(cudaMemcpy(dn.p, normal, n * 4, cudaMemcpyHostToDevice));
+        if (albedo) QZ_CUDA(cudaMemcpy(da.p, albedo, n * 4, cudaMemcpyHostToDevice));
+    }
+    int rc = render_impl(s, camera, n_samples, max_bounces, region, options, dc.as<float>(), normal ? dn.as<float>() : nullptr,
+                         albedo ? da.as<float>() : nullptr, nullptr, stats);
+    if (rc != QZ_OK) return rc;
+    QZ_CUDA(cudaMemcpy(color, dc.p, n * 4, cudaMemcpyDeviceToHost));
+    if (normal) QZ_CUDA(cudaMemcpy(normal, dn.p, n * 4, cudaMemcpyDeviceToHost));
+    if (albedo) QZ_CUDA(cudaMemcpy(albedo, da.p, n * 4, cudaMemcpyDeviceToHost));
+    return QZ_OK;
+}
+
+// ------------------------------------------------------------------ probes
+int qz_trace_paths(qz_scene s, const qz_camera* camera, uint32_t n_samples, uint32_t max_bounces, uint32_t n,
+                   const int32_t* xys, float* records) {
+    (void)n_samples;
+    if (!s || !camera || (!xys && n) || (!records && n)) return fail(QZ_ERR_INVALID, "null argument");
+    if (!s->store.committed) return fail(QZ_ERR_NOT_COMMITTED, "Scene must be committed before rendering.");
+    QZ_CUDA(cudaSetDevice(s->device));
+    if (!n) return QZ_OK;
+    DevBuf dx, dr, sensor;
+    QZ_CUDA(dx.alloc((size_t)n * 12));
+    QZ_CUDA(dr.alloc((size_t)n * 128));
+    QZ_CUDA(sensor.alloc(3 * 471 * 4));
+    QZ_CUDA(cudaMemcpy(dx.p, xys, (size_t)n * 12, cudaMemcpyHostToDevice));
+    QZ_CUDA(cudaMemcpy(sensor.p, camera->sensor_rgb, 3 * 471 * 4, cudaMemcpyHostToDevice));
+    DCamera cam = make_camera(camera, sensor.as<float>());
+    SamplerParams spar = make_sampler_params((int)cam.width, (int)cam.height);
+    k_trace_paths<<<(n + 63) / 64, 64>>>(s->store.view, cam, spar, max_bounces, n, dx.as<int32_t>(), dr.as<float>());
+    QZ_CUDA(cudaGetLastError());
+    QZ_CUDA(cudaDeviceSynchronize());
+    QZ_CUDA(cudaMemcpy(records, dr.p, (size_t)n * 128, cudaMemcpyDeviceToHost));
+    return QZ_OK;
+}
+
+int qz_sampler_eval(uint32_t n_samples, uint32_t width, uint32_t height, uint32_t n, const int32_t* q, float* out) {
+    (void)n_samples;
+    int rc = ensure_device();
+    if (rc) return rc;
+    if (!n) return QZ_OK;
+    DeviceTables t;
+    rc = device_tables(g_device, t);
+    if (rc) return rc;
+    DevBuf dq, dout;
+    QZ_CUDA(dq.alloc((size_t)n * 16));
+    QZ_CUDA(dout.alloc((size_t)n * 4));
+    QZ_CUDA(cudaMemcpy(dq.p, q, (size_t)n * 16, cudaMemcpyHostToDevice));
+    SamplerParams spar = make_sampler_params((int)width, (int)height);
+    k_sampler_eval<<<(n + 127) / 128, 128>>>(t.sampler, spar, n, dq.as<int32_t>(), dout.as<float>());
+    QZ_CUDA(cudaGetLastError());
+    QZ_CUDA(cudaMemcpy(out, dout.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    return QZ_OK;
+}
+
+int qz_intersect(qz_scene s, uint32_t n, const float* rays, float* out) {
+    if (!s || (!rays && n) || (!out && n)) return fail(QZ_ERR_INVALID, "null argument");
+    if (!s->store.committed) return fail(QZ_ERR_NOT_COMMITTED, "Scene must be committed before rendering.");
+    QZ_CUDA(cudaSetDevice(s->device));
+    if (!n) return QZ_OK;
+    DevBuf dr, dout;
+    QZ_CUDA(dr.alloc((size_t)n * 24));
+    QZ_CUDA(dout.alloc((size_t)n * 32));
+    QZ_CUDA(cudaMemcpy(dr.p, rays, (size_t)n * 24, cudaMemcpyHostToDevice));
+    k_intersect<<<(n + 127) / 128, 128>>>(s->store.view, n, dr.as<float>(), dout.as<float>());
+    QZ_CUDA(cudaGetLastError());
+    QZ_CUDA(cudaMemcpy(out, dout.p, (size_t)n * 32, cudaMemcpyDeviceToHost));
+    return QZ_OK;
+}
+
+int qz_eval_spectrum(qz_scene s, int32_t id, uint32_t n, const float* lambdas, float* out) {
+    if (!s || (!lambdas && n) || (!out && n)) return fail(QZ_ERR_INVALID, "null argument");
+    if (!s->store.committed) return fail(QZ_ERR_NOT_COMMITTED, "Scene must be committed before rendering.");
+    QZ_CUDA(cudaSetDevice(s->device));
+    if (id < 0) id = s->store.view.bg_spectrum;
+    if (id < 0) return fail(QZ_ERR_INVALID, "no such spectrum");
+    if (!n) return QZ_OK;
+    DevBuf dl, dout;
+    QZ_CUDA(dl.alloc((size_t)n * 4));
+    QZ_CUDA(dout.alloc((size_t)n * 4));
+    QZ_CUDA(cudaMemcpy(dl.p, lambdas, (size_t)n * 4, cudaMemcpyHostToDevice));
+    k_eval_spectrum<<<(n + 127) / 128, 128>>>(s->store.view, id, n, dl.as<float>(), dout.as<float>());
+    QZ_CUDA(cudaGetLastError());
+    QZ_CUDA(cudaMemcpy(out, dout.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    return QZ_OK;
+}
+
+int qz_sensor_eval(const qz_camera* camera, uint32_t n, const float* in, float* out) {
+    if (!camera || (!in && n) || (!out && n)) return fail(QZ_ERR_INVALID, "null argument");
+    int rc = ensure_device();
+    if (rc) return rc;
+    if (!n) return QZ_OK;
+    DevBuf din, dout, sensor;
+    QZ_CUDA(din.alloc((size_t)n * 20));
+    QZ_CUDA(dout.alloc((size_t)n * 12));
+    QZ_CUDA(sensor.alloc(3 * 471 * 4));
+    QZ_CUDA(cudaMemcpy(din.p, in, (size_t)n * 20, cudaMemcpyHostToDevice));
+    QZ_CUDA(cudaMemcpy(sensor.p, camera->sensor_rgb, 3 * 471 * 4, cudaMemcpyHostToDevice));
+    DCamera cam = make_camera(camera, sensor.as<float>());
+    k_sensor_eval<<<(n + 127) / 128, 128>>>(cam, n, din.as<float>(), dout.as<float>());
+    QZ_CUDA(cudaGetLastError());
+    QZ_CUDA(cudaMemcpy(out, dout.p, (size_t)n * 12, cudaMemcpyDeviceToHost));
+    return QZ_OK;
+}
+
+}  // extern "C"

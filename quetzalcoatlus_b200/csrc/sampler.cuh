@@ -167,7 +167,6 @@ QZ_HD V2 sample_2d(const SamplerDim* __restrict__ table, Sampler& smp) {
 }
 
 // ---- host-side table construction (runs once per process) ---------------------------
-#if !defined(__CUDA_ARCH__)
 inline void build_sampler_table(SamplerDim* out /* QZ_N_PRIMES entries */) {
     uint32_t count = 0;
     for (uint32_t n = 2; count < QZ_N_PRIMES; n++) {
@@ -213,6 +212,5 @@ inline SamplerParams make_sampler_params(int x_res, int y_res) {
     sp.pad = 0;
     return sp;
 }
-#endif
 
 }  // namespace qz

@@ -1,0 +1,399 @@
+// Wavefront path-tracing pipeline: the reference's per-pixel loop (render.cpp:247-319
+// render_pixels, :91-212 sample_pixel) re-cut into stages connected by SoA queues.
+//
+//   k_generate        camera ray + wavelengths for new pixel-samples (render.cpp:268-273)
+//   k_closest_hit     persistent, warp-scheduled BVH traversal (scene.cpp:61-117 / rtcIntersect1);
+//                     classifies each hit by material family into one queue per family
+//   k_shade<family>   emission + MIS, BSDF construction, depth-0 albedo, light sampling,
+//                     BSDF sampling, throughput update and Russian roulette for ONE family
+//                     (diffuse / conductor / dielectric); a fourth "misc" kernel takes misses,
+//                     emitter pass-throughs and MixedMaterial hits with run-time dispatch
+//   k_shadow          persistent any-hit traversal of the next-event shadow rays
+//                     (scene.cpp:136-143); adds the pending contribution when unoccluded
+//   k_finish          PixelSensor::to_sensor_rgb of finished paths (sensor.cpp:57-70) into the
+//                     per-sample result buffer, then regenerates a new path in the freed slot
+//   k_film            ordered per-pixel sum over the sample index (render.cpp:264-294)
+//
+// Path state lives in structure-of-arrays buffers of 16-byte elements indexed by slot; the
+// queues carry 4-byte slot indices.  Russian roulette stays fused at the end of k_shade: it
+// needs the freshly updated throughput and the next sampler dimension, so a separate kernel
+// would only re-read what is in registers.
+//
+// DETERMINISM: a path's arithmetic depends only on (x, y, s); queue order varies from run to
+// run but no result depends on it.  Every pixel-sample writes its sensor RGB into its own
+// result cell and k_film adds the cells of a pixel in ascending s, exactly the reference's
+// summation order, so the film is bit-stable and independent of the pool size, the pass
+// size and the number of GPUs.
+#pragma once
+
+#include <cooperative_groups.h>
+
+#include "shading.cuh"
+
+namespace qz {
+
+namespace cg = cooperative_groups;
+
+enum ShadeQueue { SQ_MISC = 0, SQ_DIFFUSE = 1, SQ_CONDUCTOR = 2, SQ_DIELECTRIC = 3, SQ_COUNT = 4 };
+
+// counter block layout (uint32 words)
+enum Counter {
+    C_TRACE0 = 0, C_TRACE1 = 1,           // sizes of the double-buffered trace queue
+    C_SHADE0 = 2,                         // .. C_SHADE0 + SQ_COUNT - 1
+    C_SHADOW = 6, C_DONE = 7,
+    C_CURSOR_TRACE = 8, C_CURSOR_SHADOW = 9,
+    C_NEXT_PATH = 10,                     // next path id of the pass to hand out
+    C_WORDS = 16
+};
+// 64-bit statistics block
+enum Stat { S_RAYS_CLOSEST = 0, S_RAYS_SHADOW = 1, S_SHADE = 2, S_NODES = 3, S_PRIMS = 4, S_PATHS_DONE = 5, S_WORDS = 8 };
+
+struct WfBuffers {
+    float4 *ray_o, *ray_d;      // o.xyz | ior_scale ; d.xyz | p_b
+    float4 *hit_a, *hit_b;      // t, u, v, prim ; Ng.xyz, key
+    float4 *weight, *radiance, *lambda, *lpdf;
+    uint4* misc;                // path id, halton index, dim | depth << 16 | flags << 24, rays issued
+    float4 *aov_n, *aov_a;
+    float4 *sh_o, *sh_d, *sh_c;
+    uint32_t* q_trace[2];
+    uint32_t* q_shade[SQ_COUNT];
+    uint32_t *q_shadow, *q_done;
+    uint32_t* counters;
+    unsigned long long* stats;
+    float4 *res_a, *res_b;      // per pixel-sample: (color rgb, normal.x), (albedo rgb, normal.y)
+    float* res_c;               // normal.z
+    uint32_t pool;
+};
+
+struct PassParams {
+    uint32_t n_pix;             // owned pixels
+    uint32_t s_begin, s_count;  // sample indices of this pass
+    uint32_t total;             // n_pix * s_count
+    uint32_t max_bounces;
+    const uint32_t* owned_rows; // film rows owned by this call, ascending
+    uint32_t width, height;
+    SamplerParams spar;
+};
+
+// ------------------------------------------------------------------ SoA helpers
+__device__ __forceinline__ float4 f4(float a, float b, float c, float d) { return make_float4(a, b, c, d); }
+__device__ __forceinline__ float4 f4(const Spec4& s) { return make_float4(s.v[0], s.v[1], s.v[2], s.v[3]); }
+__device__ __forceinline__ Spec4 s4(const float4& f) { return spec4(f.x, f.y, f.z, f.w); }
+
+__device__ __forceinline__ void store_state(const WfBuffers& b, uint32_t slot, const PathState& ps, uint32_t path_id) {
+    b.ray_o[slot] = f4(ps.ray.o.x, ps.ray.o.y, ps.ray.o.z, ps.ior_scale);
+    b.ray_d[slot] = f4(ps.ray.d.x, ps.ray.d.y, ps.ray.d.z, ps.p_b);
+    b.weight[slot] = f4(ps.weight);
+    b.radiance[slot] = f4(ps.L);
+    b.lpdf[slot] = f4(ps.pdf);
+    b.misc[slot] = make_uint4(path_id, ps.smp.index, ps.smp.dim | (ps.depth << 16) | (ps.flags << 24), ps.n_rays);
+}
+
+__device__ __forceinline__ uint32_t load_state(const WfBuffers& b, uint32_t slot, PathState& ps) {
+    const float4 o = b.ray_o[slot], d = b.ray_d[slot];
+    ps.ray.o = v3(o.x, o.y, o.z); ps.ior_scale = o.w;
+    ps.ray.d = v3(d.x, d.y, d.z); ps.p_b = d.w;
+    ps.weight = s4(b.weight[slot]);
+    ps.L = s4(b.radiance[slot]);
+    ps.lambda = s4(b.lambda[slot]);
+    ps.pdf = s4(b.lpdf[slot]);
+    const uint4 m = b.misc[slot];
+    ps.smp.index = m.y;
+    ps.smp.dim = m.z & 0xffffu;
+    ps.depth = (m.z >> 16) & 0xffu;
+    ps.flags = m.z >> 24;
+    ps.n_rays = m.w;
+    return m.x;
+}
+
+// append `slot` to a queue; lanes of the warp that push to the same queue share one atomic
+__device__ __forceinline__ void queue_push(uint32_t* counter, uint32_t* queue, uint32_t slot) {
+    const unsigned peers = __match_any_sync(__activemask(), (unsigned long long)counter);
+    const int leader = __ffs(peers) - 1;
+    const int lane = threadIdx.x & 31;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    queue[base + __popc(peers & ((1u << lane) - 1u))] = slot;
+}
+
+// path id of the pass -> pixel and sample; initialises the slot (render.cpp:261-273)
+__device__ __forceinline__ void init_slot(const DScene& sc, const DCamera& cam, const WfBuffers& b, const PassParams& pp,
+                                          uint32_t slot, uint32_t path_id) {
+    const uint32_t pix = path_id % pp.n_pix;
+    const uint32_t s = pp.s_begin + path_id / pp.n_pix;
+    const uint32_t row = pp.owned_rows[pix / pp.width];
+    const uint32_t x = pix % pp.width;
+    const uint32_t y = pp.height - row - 1;
+    PathState ps;
+    PathAov aov;
+    start_path(sc, cam, pp.spar, x, y, s, ps, aov);
+    store_state(b, slot, ps, path_id);
+    b.lambda[slot] = f4(ps.lambda);
+    b.aov_n[slot] = f4(0.0f, 0.0f, 0.0f, 0.0f);
+    b.aov_a[slot] = f4(0.0f, 0.0f, 0.0f, 0.0f);
+}
+
+// ------------------------------------------------------------------ kernels
+__global__ void __launch_bounds__(256) k_generate(DScene sc, DCamera cam, WfBuffers b, PassParams pp, uint32_t n) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        init_slot(sc, cam, b, pp, i, i);
+        b.q_trace[0][i] = i;
+    }
+}
+
+// family of the surface a closest-hit result lands on (the branch-sorting key)
+__device__ __forceinline__ int classify_hit(const DScene& sc, const Hit& hit, bool unsorted) {
+    if (unsorted || hit.prim == QZ_NO_HIT) return SQ_MISC;
+    const uint32_t geom = __float_as_uint(__ldg(reinterpret_cast<const float4*>(sc.prims + (size_t)hit.prim * 4)).w);
+    const int32_t mat = sc.geoms[geom].material;
+    if (mat < 0) return SQ_MISC;
+    const uint32_t kind = sc.materials[mat].kind;
+    if (kind == QZ_MAT_DIFFUSE) return SQ_DIFFUSE;
+    if (kind == QZ_MAT_CONDUCTOR) return SQ_CONDUCTOR;
+    if (kind == QZ_MAT_DIELECTRIC || kind == QZ_MAT_THIN_DIELECTRIC) return SQ_DIELECTRIC;
+    return SQ_MISC;  // MixedMaterial: the family depends on the bounce's material sample
+}
+
+#define QZ_REFILL_MIN 8   /* idle lanes that trigger a refill from the queue */
+#define QZ_STEPS_PER_ROUND 4
+
+// Persistent closest-hit traversal.  Each warp owns 32 lanes of traversal state; lanes whose
+// ray has finished are refilled from the queue cursor as soon as QZ_REFILL_MIN of them are
+// idle (warp vote), so a warp keeps working at high lane occupancy on incoherent rays.
+template <bool COUNT>
+__global__ void __launch_bounds__(128) k_closest_hit(DScene sc, WfBuffers b, int qsel, uint32_t flags) {
+    const uint32_t count = b.counters[C_TRACE0 + qsel];
+    const uint32_t* queue = b.q_trace[qsel];
+    const int lane = threadIdx.x & 31;
+    const unsigned full = 0xffffffffu;
+    Trav tv;
+    tv.done = true;
+    bool active = false;
+    bool exhausted = false;
+    uint32_t slot = 0;
+    TraversalCounters cnt;
+    cnt.nodes = 0; cnt.prims = 0;
+    for (;;) {
+        const unsigned idle = __ballot_sync(full, !active);
+        if (!exhausted && idle && (__popc(idle) >= QZ_REFILL_MIN || idle == full)) {
+            const int leader = __ffs(idle) - 1;
+            uint32_t base = 0;
+            if (lane == leader) base = atomicAdd(&b.counters[C_CURSOR_TRACE], (uint32_t)__popc(idle));
+            base = __shfl_sync(full, base, leader);
+            if (!active) {
+                const uint32_t idx = base + __popc(idle & ((1u << lane) - 1u));
+                if (idx < count) {
+                    slot = queue[idx];
+                    const float4 o = b.ray_o[slot], d = b.ray_d[slot];
+                    Ray r;
+                    r.o = v3(o.x, o.y, o.z);
+                    r.d = v3(d.x, d.y, d.z);
+                    trav_init(tv, r, INFINITY);
+                    active = true;
+                }
+            }
+            if (base + __popc(idle) >= count) exhausted = true;
+        }
+        if (!__any_sync(full, active)) break;
+#pragma unroll 1
+        for (int k = 0; k < QZ_STEPS_PER_ROUND; k++)
+            if (active && !tv.done) trav_step<false, COUNT>(sc, tv, &cnt);
+        if (active && tv.done) {
+            const Hit& h = tv.best;
+            b.hit_a[slot] = f4(h.t, h.u, h.v, __uint_as_float(h.prim));
+            b.hit_b[slot] = f4(h.ng.x, h.ng.y, h.ng.z, 0.0f);
+            const int fam = classify_hit(sc, h, (flags & QZ_FLAG_UNSORTED_SHADING) != 0);
+            queue_push(&b.counters[C_SHADE0 + fam], b.q_shade[fam], slot);
+            active = false;
+        }
+    }
+    if (COUNT) {
+        atomicAdd(&b.stats[S_NODES], (unsigned long long)cnt.nodes);
+        atomicAdd(&b.stats[S_PRIMS], (unsigned long long)cnt.prims);
+    }
+}
+
+// Persistent any-hit traversal of the shadow queue; resolves next-event estimation.
+template <bool COUNT>
+__global__ void __launch_bounds__(128) k_shadow(DScene sc, WfBuffers b) {
+    const uint32_t count = b.counters[C_SHADOW];
+    const int lane = threadIdx.x & 31;
+    const unsigned full = 0xffffffffu;
+    Trav tv;
+    tv.done = true;
+    bool active = false;
+    bool exhausted = false;
+    uint32_t slot = 0;
+    TraversalCounters cnt;
+    cnt.nodes = 0; cnt.prims = 0;
+    for (;;) {
+        const unsigned idle = __ballot_sync(full, !active);
+        if (!exhausted && idle && (__popc(idle) >= QZ_REFILL_MIN || idle == full)) {
+            const int leader = __ffs(idle) - 1;
+            uint32_t base = 0;
+            if (lane == leader) base = atomicAdd(&b.counters[C_CURSOR_SHADOW], (uint32_t)__popc(idle));
+            base = __shfl_sync(full, base, leader);
+            if (!active) {
+                const uint32_t idx = base + __popc(idle & ((1u << lane) - 1u));
+                if (idx < count) {
+                    slot = b.q_shadow[idx];
+                    const float4 o = b.sh_o[slot], d = b.sh_d[slot];
+                    Ray r;
+                    r.o = v3(o.x, o.y, o.z);
+                    r.d = v3(d.x, d.y, d.z);
+                    trav_init(tv, r, 1.0f);
+                    active = true;
+                }
+            }
+            if (base + __popc(idle) >= count) exhausted = true;
+        }
+        if (!__any_sync(full, active)) break;
+#pragma unroll 1
+        for (int k = 0; k < QZ_STEPS_PER_ROUND; k++)
+            if (active && !tv.done) trav_step<true, COUNT>(sc, tv, &cnt);
+        if (active && tv.done) {
+            if (!tv.occluded) {
+                const float4 L = b.radiance[slot], c = b.sh_c[slot];
+                b.radiance[slot] = f4(L.x + c.x, L.y + c.y, L.z + c.z, L.w + c.w);
+            }
+            active = false;
+        }
+    }
+    if (COUNT) {
+        atomicAdd(&b.stats[S_NODES], (unsigned long long)cnt.nodes);
+        atomicAdd(&b.stats[S_PRIMS], (unsigned long long)cnt.prims);
+    }
+}
+
+// One bounce for every path of one family queue.
+template <int KH>
+__global__ void __launch_bounds__(128) k_shade(DScene sc, WfBuffers b, int fam, int next_sel, uint32_t max_bounces) {
+    const uint32_t count = b.counters[C_SHADE0 + fam];
+    const uint32_t* queue = b.q_shade[fam];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+        const uint32_t slot = queue[i];
+        PathState ps;
+        const uint32_t path_id = load_state(b, slot, ps);
+        ps.n_rays++;  // the closest-hit query that produced this hit
+        const float4 ha = b.hit_a[slot], hb = b.hit_b[slot];
+        Hit hit;
+        hit.t = ha.x; hit.u = ha.y; hit.v = ha.z; hit.prim = __float_as_uint(ha.w);
+        hit.ng = v3(hb.x, hb.y, hb.z);
+        hit.key = 0;
+        PathAov aov;
+        aov.normal = v3(0.0f, 0.0f, 0.0f);
+        aov.albedo = spec4(0.0f);
+        const bool first = ps.depth == 0;
+        ShadowRequest sh;
+        const bool alive = shade_bounce<KH>(sc, ps, aov, hit, max_bounces, sh);
+        if (first) {
+            // depth is still 0 after an emitter pass-through, so these may be written more than
+            // once per path; the last write (the first real surface) wins, as in the reference
+            if (hit.prim != QZ_NO_HIT) b.aov_n[slot] = f4(aov.normal.x, aov.normal.y, aov.normal.z, 0.0f);
+            if (ps.depth != 0 || !alive) b.aov_a[slot] = f4(aov.albedo);
+        }
+        if (ps.flags & QZ_FLAG_HAS_SHADOW) {
+            ps.n_rays++;
+            b.sh_o[slot] = f4(sh.o.x, sh.o.y, sh.o.z, 0.0f);
+            b.sh_d[slot] = f4(sh.d.x, sh.d.y, sh.d.z, 0.0f);
+            b.sh_c[slot] = f4(sh.contrib);
+            queue_push(&b.counters[C_SHADOW], b.q_shadow, slot);
+        }
+        store_state(b, slot, ps, path_id);
+        if (alive) queue_push(&b.counters[C_TRACE0 + next_sel], b.q_trace[next_sel], slot);
+        else queue_push(&b.counters[C_DONE], b.q_done, slot);
+    }
+}
+
+// Finished paths: sensor conversion into the result cells, then a new path in the same slot.
+__global__ void __launch_bounds__(256) k_finish(DScene sc, DCamera cam, WfBuffers b, PassParams pp, int next_sel) {
+    const uint32_t count = b.counters[C_DONE];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+        const uint32_t slot = b.q_done[i];
+        const uint32_t path_id = b.misc[slot].x;
+        const Spec4 L = s4(b.radiance[slot]), lambda = s4(b.lambda[slot]), pdf = s4(b.lpdf[slot]);
+        const float4 n = b.aov_n[slot];
+        const V3 rgb = to_sensor_rgb(cam, L, lambda, pdf);
+        const V3 argb = to_sensor_rgb(cam, s4(b.aov_a[slot]), lambda, pdf);
+        b.res_a[path_id] = f4(rgb.x, rgb.y, rgb.z, n.x);
+        b.res_b[path_id] = f4(argb.x, argb.y, argb.z, n.y);
+        b.res_c[path_id] = n.z;
+        // regenerate
+        const unsigned peers = __activemask();
+        const int lane = threadIdx.x & 31;
+        const int leader = __ffs(peers) - 1;
+        uint32_t base = 0;
+        if (lane == leader) base = atomicAdd(&b.counters[C_NEXT_PATH], (uint32_t)__popc(peers));
+        base = __shfl_sync(peers, base, leader);
+        const uint32_t next_id = base + __popc(peers & ((1u << lane) - 1u));
+        if (next_id < pp.total) {
+            init_slot(sc, cam, b, pp, slot, next_id);
+            queue_push(&b.counters[C_TRACE0 + next_sel], b.q_trace[next_sel], slot);
+        }
+    }
+}
+
+// Between iterations: account the queue sizes, clear the consumed queues and the cursors.
+__global__ void k_next_iteration(WfBuffers b, int cur_sel) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        uint32_t* c = b.counters;
+        unsigned long long shade = 0;
+        for (int k = 0; k < SQ_COUNT; k++) shade += c[C_SHADE0 + k];
+        b.stats[S_RAYS_CLOSEST] += c[C_TRACE0 + cur_sel];
+        b.stats[S_RAYS_SHADOW] += c[C_SHADOW];
+        b.stats[S_SHADE] += shade;
+        b.stats[S_PATHS_DONE] += c[C_DONE];
+        c[C_TRACE0 + cur_sel] = 0;
+        for (int k = 0; k < SQ_COUNT; k++) c[C_SHADE0 + k] = 0;
+        c[C_SHADOW] = 0;
+        c[C_DONE] = 0;
+        c[C_CURSOR_TRACE] = 0;
+        c[C_CURSOR_SHADOW] = 0;
+    }
+}
+
+// Ordered accumulation of one pass into the running per-pixel sums; on the last pass divide
+// by the sample count and write the three film planes (render.cpp:264-294).
+__global__ void __launch_bounds__(256) k_film(WfBuffers b, PassParams pp, float* acc /* 9 floats per owned pixel */,
+                                               bool first_pass, bool last_pass, uint32_t n_samples_total, float* color,
+                                               float* normal, float* albedo) {
+    for (uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x; pix < pp.n_pix; pix += gridDim.x * blockDim.x) {
+        float c[3], a[3], n[3];
+        if (first_pass) {
+            for (int k = 0; k < 3; k++) { c[k] = 0.0f; a[k] = 0.0f; n[k] = 0.0f; }
+        } else {
+            for (int k = 0; k < 3; k++) {
+                c[k] = acc[(size_t)k * pp.n_pix + pix];
+                a[k] = acc[(size_t)(3 + k) * pp.n_pix + pix];
+                n[k] = acc[(size_t)(6 + k) * pp.n_pix + pix];
+            }
+        }
+        for (uint32_t s = 0; s < pp.s_count; s++) {
+            const size_t cell = (size_t)s * pp.n_pix + pix;
+            const float4 ra = b.res_a[cell], rb = b.res_b[cell];
+            const float rc = b.res_c[cell];
+            c[0] += ra.x; c[1] += ra.y; c[2] += ra.z;
+            a[0] += rb.x; a[1] += rb.y; a[2] += rb.z;
+            n[0] += ra.w; n[1] += rb.w; n[2] += rc;
+        }
+        if (!last_pass) {
+            for (int k = 0; k < 3; k++) {
+                acc[(size_t)k * pp.n_pix + pix] = c[k];
+                acc[(size_t)(3 + k) * pp.n_pix + pix] = a[k];
+                acc[(size_t)(6 + k) * pp.n_pix + pix] = n[k];
+            }
+        } else {
+            const float inv = (float)n_samples_total;
+            const uint32_t row = pp.owned_rows[pix / pp.width];
+            const size_t o = ((size_t)row * pp.width + pix % pp.width) * 3;
+            for (int k = 0; k < 3; k++) {
+                color[o + k] = c[k] / inv;
+                if (normal) normal[o + k] = n[k] / inv;
+                if (albedo) albedo[o + k] = a[k] / inv;
+            }
+        }
+    }
+}
+
+}  // namespace qz
