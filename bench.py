@@ -1,0 +1,346 @@
+#!/usr/bin/env python3
+"""Benchmark of the path-tracing hot path (BASELINE.json: Mpaths/s and Mrays/s on the named scenes).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (torchrun launches N ranks)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU renderer (rank 0 only)
+
+A "step" is one full render() of the workload.  Default workload: cornell_box exactly as
+shipped (examples/cornell_box.cpp: 800x800, 64 bounces) at 128 spp PER GPU: with N GPUs the
+render has 128*N samples per pixel and is sharded by interleaved 8-row strips, each rank
+owning every N-th strip and all samples of its pixels (weak scaling: 81.92 M paths per GPU per
+step); the partial films are combined by ONE NCCL sum-reduce.  The film is bit-identical to a
+single-GPU render of the same configuration (ordered per-pixel accumulation, exact zeros
+elsewhere).
+
+`value`  whole-job Mpaths/s, scene and film resident in HBM, device-timed (CUDA events,
+         max over ranks).
+`e2e`    the same metric through the reference-facing call render(camera, scene, spp, bounces)
+         with HOST RenderResult buffers: per step the camera/sensor tables go host->device
+         and the three film planes come back device->host inside the timed region.
+`roofline`     the dominant kernel stage against the measured HBM peak (MEASURED_PEAKS.json).
+`cpu_baseline` the oracle (reference sources over the Embree shim -- NOT real Embree, which is
+               absent) timed on this box's host cores on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+WORKLOADS = {
+    # name: (scene, width, height, spp per GPU, max_bounces)
+    "cornell_box": ("cornell_box", 800, 800, 128, 64),
+    "cornell_4k": ("cornell_box", 3840, 2160, 128, 64),   # x8 GPUs = 1024 spp: BASELINE.json configs[4]
+    "glass_spheres": ("glass_spheres", 800, 800, 512, 64),
+    "textures": ("textures", 800, 800, 36, 32),
+    "opposing_planes": ("opposing_planes", 1920, 1080, 256, 64),
+    "obj_viewer": ("obj_viewer", 800, 600, 24, 32),         # synthetic ~1M-triangle mesh
+}
+STRIP_ROWS = 8
+
+
+def measured_peaks() -> tuple[float, str]:
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        return float(json.loads(p.read_text())["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks and throttle reasons during the timed region."""
+
+    QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([f.strip() for f in out.split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self) -> dict:
+        self._stop_evt.set()
+        self.join(timeout=6)
+        sm = [float(s[0]) for s in self.samples if s and s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for s in self.samples for i in range(4) if len(s) > 2 + i and s[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.samples)}
+
+
+def ensure_mesh(n_tri: int = 1_000_000) -> str:
+    sys.path.insert(0, str(ROOT / "tools"))
+    import gen_mesh
+
+    path = Path(os.environ.get("QZ_MESH_DIR", "/tmp")) / f"qz_knot_{n_tri}.obj"
+    if not path.exists():
+        pos, nrm, tris = gen_mesh.knot_mesh(n_tri)
+        gen_mesh.write_obj(str(path), pos, nrm, tris)
+    return str(path)
+
+
+def build_scene(harness, workload: str, width: int, height: int, mesh_tris: int):
+    scene = WORKLOADS[workload][0]
+    if scene == "obj_viewer":
+        return harness.build_scene(scene, width, height, obj_path=ensure_mesh(mesh_tris), obj_material="alluminum", obj_light="point")
+    return harness.build_scene(scene, width, height)
+
+
+def cpu_baseline(workload: str, width: int, height: int, max_bounces: int, mesh_tris: int, budget_s: float = 15.0) -> dict:
+    """The oracle on this box's host cores, bounded sample: full resolution, reduced spp."""
+    from quetzalcoatlus_b200.harness import Harness
+
+    lib = ROOT / "oracle" / "_ref" / "liboracle_ref.so"
+    if not lib.exists():
+        return {"value": None, "unit": "Mpaths/s", "cores": 0, "kind": "reference", "sample": "oracle/_ref not built"}
+    orc = Harness(lib, "orc_")
+    if WORKLOADS[workload][0] == "obj_viewer":
+        mesh_tris = min(mesh_tris, 20_000)  # the reference's regex OBJ loader needs ~0.8 ms per line
+    with build_scene(orc, workload, width, height, mesh_tris) as sc:
+        probe = sc.render(1, max_bounces)
+        spp = int(max(1, min(WORKLOADS[workload][3], budget_s / max(probe.seconds, 1e-3))))
+        r = sc.render(spp, max_bounces) if spp > 1 else probe
+    paths = width * height * spp
+    return {"value": paths / r.seconds / 1e6, "unit": "Mpaths/s", "cores": r.n_threads, "kind": "reference",
+            "mrays_per_s": r.rays / r.seconds / 1e6,
+            "sample": f"{workload} {width}x{height}, {spp} spp of the workload's samples, {max_bounces} bounces, "
+                      f"{r.seconds:.2f} s; reference integrator over the oracle's Embree shim (not real Embree)"
+                      + (f"; mesh reduced to {mesh_tris} triangles" if WORKLOADS[workload][0] == "obj_viewer" else "")}
+
+
+def run_reference(args) -> None:
+    """The reference arm: the reference's own CPU renderer (oracle/_ref) on rank 0."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    _, w0, h0, spp0, mb = WORKLOADS[args.workload]
+    width, height = args.width or w0, args.height or h0
+    from quetzalcoatlus_b200.harness import Harness
+
+    lib = ROOT / "oracle" / "_ref" / "liboracle_ref.so"
+    if not lib.exists():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/liboracle_ref.so is not built"}))
+        return
+    orc = Harness(lib, "orc_")
+    mesh_tris = min(args.mesh_triangles, 20_000)
+    with build_scene(orc, args.workload, width, height, mesh_tris) as sc:
+        probe = sc.render(1, mb)
+        # each step = a bounded sample of the workload: as many of its spp as fit ~8 s
+        spp = int(max(1, min(spp0 * args.gpus, 8.0 / max(probe.seconds, 1e-3))))
+        for _ in range(min(args.warmup, 1)):
+            sc.render(spp, mb)
+        secs, rays, threads = [], 0, 0
+        for _ in range(args.steps):
+            r = sc.render(spp, mb)
+            secs.append(r.seconds)
+            rays, threads = r.rays, r.n_threads
+    total = sum(secs)
+    paths = width * height * spp
+    value = paths * args.steps / total / 1e6
+    sample = (f"{args.workload} {width}x{height}, {spp} of {spp0 * args.gpus} spp per step, {mb} bounces; reference "
+              f"integrator over the oracle's Embree shim (not real Embree)")
+    print(json.dumps({
+        "impl": "reference", "metric": "Mpaths/s", "value": value, "unit": "Mpaths/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "width": width, "height": height, "spp_per_step": spp, "max_bounces": mb},
+        "mrays_per_s": rays / secs[-1] / 1e6,
+        "cpu_baseline": {"value": value, "unit": "Mpaths/s", "cores": threads, "kind": "reference", "sample": sample},
+        "e2e": {"value": value, "unit": "Mpaths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def run_ours(args) -> None:
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    os.environ["QZ_DEVICE"] = str(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from quetzalcoatlus_b200 import load_harness
+    from quetzalcoatlus_b200.harness import (QZ_FLAG_COUNT_TRAVERSAL, QZ_FLAG_STAGE_TIMING, QzRegion, QzRenderOptions, QzStats)
+
+    qz = load_harness()
+    lib = qz.lib
+    _, w0, h0, spp0, mb = WORKLOADS[args.workload]
+    width, height = args.width or w0, args.height or h0
+    spp = (args.spp or spp0) * world
+    sc = build_scene(qz, args.workload, width, height, args.mesh_triangles)
+    handle, cam = ctypes.c_void_p(sc.c_scene_handle()), sc.c_camera()
+    region = QzRegion(STRIP_ROWS, world, rank)
+    film = torch.zeros((3, height, width, 3), dtype=torch.float32, device="cuda")  # colour, normal, albedo planes
+    stream = torch.cuda.current_stream()
+
+    def step(flags: int = 0) -> dict:
+        """One render into the device-resident film + (N > 1) the single NCCL reduce."""
+        if world > 1:
+            film.zero_()
+        st = QzStats()
+        opts = QzRenderOptions(flags, args.pool, 0, 0)
+        rc = lib.qz_render_device(handle, ctypes.byref(cam), spp, mb, ctypes.byref(region), ctypes.byref(opts),
+                                  ctypes.c_void_p(film[0].data_ptr()), ctypes.c_void_p(film[1].data_ptr()),
+                                  ctypes.c_void_p(film[2].data_ptr()), ctypes.c_void_p(stream.cuda_stream), ctypes.byref(st))
+        if rc != 0:
+            lib.qz_last_error.restype = ctypes.c_char_p
+            raise RuntimeError(f"qz_render_device failed: {lib.qz_last_error().decode()}")
+        if world > 1:
+            dist.reduce(film, dst=0, op=dist.ReduceOp.SUM)
+        return st.as_dict()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    stats = [step() for _ in range(args.steps)]
+    e1.record(stream)
+    barrier()
+    clock_info = clocks.stop()
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    launches = sum(s["kernel_launches"] for s in stats)
+    rays = torch.tensor([float(sum(s["rays_closest"] + s["rays_shadow"] for s in stats)),
+                         float(sum(s["shade_calls"] for s in stats)), float(launches)], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(rays, op=dist.ReduceOp.SUM)
+    total_paths = width * height * spp * args.steps
+    value = total_paths / (ms_total * 1e-3) / 1e6
+
+    # ---- end to end through render() with host buffers (public API of the host library)
+    def e2e_step():
+        color = np.zeros((height, width, 3), np.float32)
+        normal, albedo = np.zeros_like(color), np.zeros_like(color)
+        st = QzStats()
+        opts = QzRenderOptions(0, args.pool, 0, 0)
+        rc = lib.qz_render(handle, ctypes.byref(cam), spp, mb, ctypes.byref(region), ctypes.byref(opts),
+                           color.ctypes.data_as(ctypes.c_void_p), normal.ctypes.data_as(ctypes.c_void_p),
+                           albedo.ctypes.data_as(ctypes.c_void_p), ctypes.byref(st))
+        assert rc == 0
+        if world > 1:
+            t = torch.from_numpy(np.stack([color, normal, albedo])).cuda()
+            dist.reduce(t, dst=0, op=dist.ReduceOp.SUM)
+            t.cpu()
+        return color
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(1, min(args.steps, 3))
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = width * height * spp * e2e_steps / float(e2e_s.item()) / 1e6
+    film_bytes = 3 * height * width * 3 * 4
+    h2d = 3 * 471 * 4 + height * 4 + (film_bytes if world > 1 else 0)
+
+    # ---- roofline of the dominant stage: one instrumented step (stage events + traversal counters), rank 0, untimed
+    roofline, extra = None, {}
+    if rank == 0:
+        inst = step(QZ_FLAG_STAGE_TIMING | QZ_FLAG_COUNT_TRAVERSAL) if world == 1 else None
+        if inst:
+            n_rays = inst["rays_closest"] + inst["rays_shadow"]
+            n_node = inst["node_visits"] / max(n_rays, 1)
+            n_prim = inst["prim_tests"] / max(n_rays, 1)
+            # B_ray = N_node*128 + N_prim*64 + 32 (ray read) + 32 (hit write; 4 for shadow rays)
+            bytes_trav = inst["node_visits"] * 128 + inst["prim_tests"] * 64 + inst["rays_closest"] * 64 + inst["rays_shadow"] * 36
+            bytes_shade = inst["shade_calls"] * 288 + inst["rays_shadow"] * 48
+            stages = {"traversal (k_closest_hit + k_shadow)": (inst["ms_closest"] + inst["ms_shadow"], bytes_trav),
+                      "shading (k_shade<family>)": (inst["ms_shade"], bytes_shade)}
+            dom = max(stages, key=lambda k: stages[k][0])
+            d_ms, d_bytes = stages[dom]
+            peak, how = measured_peaks()
+            achieved = d_bytes / (d_ms * 1e-3) / 1e9 if d_ms > 0 else 0.0
+            roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                        "kernel": dom, "peak_source": how, "stage_ms": {k: v[0] for k, v in stages.items()},
+                        "note": "path-tracing of small analytic scenes is issue-bound (integer sampler), not HBM-bound; see DESIGN.md"}
+            extra = {"n_node_per_ray": n_node, "n_prim_per_ray": n_prim, "bounces_per_path": inst["shade_calls"] / inst["paths"],
+                     "shadow_ray_fraction": inst["rays_shadow"] / max(n_rays, 1), "bvh_nodes": inst["bvh_nodes"],
+                     "whole_pipeline_algorithmic_gbs": (bytes_trav + bytes_shade) / (inst["ms_total"] * 1e-3) / 1e9}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(args.workload, width, height, mb, args.mesh_triangles)
+
+    if rank == 0:
+        print(json.dumps({
+            "metric": "Mpaths/s", "value": value, "unit": "Mpaths/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "scene": WORKLOADS[args.workload][0], "width": width, "height": height,
+                       "spp": spp, "spp_per_gpu": spp // world, "max_bounces": mb,
+                       "parallelism": f"interleaved {STRIP_ROWS}-row strips over {world} GPU(s), one NCCL sum-reduce of the film",
+                       "l2": "per-step working set (path pool + result cells, > 3 GB) exceeds L2"},
+            "mrays_per_s": float(rays[0].item()) / (ms_total * 1e-3) / 1e6,
+            "gpu_launches": int(rays[2].item()),
+            "e2e": {"value": e2e_value, "unit": "Mpaths/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": film_bytes},
+            "roofline": roofline, "cpu_baseline": cpu, "clocks": clock_info, **extra,
+        }))
+    sc.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="cornell_box")
+    ap.add_argument("--width", type=int, default=0)
+    ap.add_argument("--height", type=int, default=0)
+    ap.add_argument("--spp", type=int, default=0, help="samples per pixel PER GPU (default: the workload's)")
+    ap.add_argument("--pool", type=int, default=0, help="paths in flight (0 = library default)")
+    ap.add_argument("--mesh-triangles", type=int, default=1_000_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,127 @@
+"""CPU-only checks of the boundary: the C-ABI library loads without a GPU and exports every
+symbol include/qz_b200.h declares; without a device it fails LOUDLY (no CPU fallback); the
+reference's own example programs and colour test compile UNCHANGED against the host headers."""
+import ctypes
+import re
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+PKG = ROOT / "quetzalcoatlus_b200"
+HEADER = ROOT / "include" / "qz_b200.h"
+CUDA_LIB = PKG / "_lib" / "libqz_b200.so"
+HARNESS_LIB = PKG / "_lib" / "libqz_harness.so"
+REFERENCE = Path("/root/reference")
+
+
+def declared_symbols():
+    text = re.sub(r"/\*.*?\*/", "", HEADER.read_text(), flags=re.S)
+    return sorted(set(re.findall(r"\b(qz_[a-z_0-9]+)\s*\(", text)))
+
+
+def has_gpu() -> bool:
+    try:
+        import torch
+
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def test_header_declares_the_expected_entry_points():
+    syms = declared_symbols()
+    for must in ["qz_init", "qz_scene_create", "qz_scene_commit", "qz_scene_destroy", "qz_render", "qz_render_device",
+                 "qz_trace_paths", "qz_sampler_eval", "qz_intersect", "qz_last_error"]:
+        assert must in syms
+
+
+def test_cuda_library_exports_every_declared_symbol():
+    if not CUDA_LIB.exists():
+        pytest.fail(f"{CUDA_LIB} missing: run __graft_entry__.build()")
+    lib = ctypes.CDLL(str(CUDA_LIB))
+    for name in declared_symbols():
+        assert hasattr(lib, name), f"libqz_b200.so does not export {name}"
+    assert lib.qz_abi_version() == 1
+
+
+def test_pod_struct_sizes_match_the_python_bindings():
+    from quetzalcoatlus_b200.harness import QzCamera, QzRegion, QzRenderOptions, QzStats
+
+    src = '#include <stdio.h>\n#include "qz_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",' \
+          "sizeof(qz_spectrum),sizeof(qz_texture),sizeof(qz_material),sizeof(qz_light),sizeof(qz_geometry),sizeof(qz_prim)," \
+          "sizeof(qz_camera),sizeof(qz_region),sizeof(qz_render_options),sizeof(qz_stats));return 0;}"
+    exe = Path("/tmp/qz_sizes")
+    subprocess.run(["gcc", "-x", "c", "-", f"-I{ROOT / 'include'}", "-o", str(exe)], input=src, text=True, check=True)
+    sizes = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    assert sizes[:6] == [32, 32, 32, 80, 32, 64]
+    assert sizes[6:] == [ctypes.sizeof(QzCamera), ctypes.sizeof(QzRegion), ctypes.sizeof(QzRenderOptions), ctypes.sizeof(QzStats)]
+
+
+@pytest.mark.skipif(has_gpu(), reason="checks the no-GPU failure mode")
+def test_no_gpu_means_loud_failure_not_a_cpu_fallback():
+    lib = ctypes.CDLL(str(CUDA_LIB))
+    lib.qz_last_error.restype = ctypes.c_char_p
+    assert lib.qz_init(0) == 1  # QZ_ERR_NO_DEVICE
+    assert b"no CPU fallback" in lib.qz_last_error()
+    scene = ctypes.c_void_p()
+    assert lib.qz_scene_create(ctypes.byref(scene)) == 1
+    out = np.zeros(4, np.float32)
+    q = np.zeros(4, np.int32)
+    assert lib.qz_sampler_eval(1, 8, 8, 1, q.ctypes.data_as(ctypes.c_void_p), out.ctypes.data_as(ctypes.c_void_p)) == 1
+    # the host library reports it the way the reference reports a failed device and leaves the scene not ready
+    from quetzalcoatlus_b200 import load_harness
+
+    qz = load_harness()
+    with pytest.raises(RuntimeError):
+        qz.build_scene("cornell_box", 8, 8)
+
+
+def test_product_libraries_do_not_link_the_oracle_or_the_emulation():
+    for lib in (CUDA_LIB, HARNESS_LIB):
+        out = subprocess.run(["ldd", str(lib)], capture_output=True, text=True).stdout
+        assert "oracle" not in out and "emu" not in out, out
+    for py in list(PKG.glob("*.py")) + [ROOT / "quetzalcoatlus_b200" / "Makefile"]:
+        text = py.read_text()
+        assert "liboracle_ref" not in text and "libqz_emu" not in text, py
+
+
+@pytest.mark.skipif(not REFERENCE.exists(), reason="/root/reference not present")
+@pytest.mark.parametrize("example", ["cornell_box", "glass_spheres", "textures", "opposing_planes", "mandelbrot"])
+def test_reference_examples_compile_unchanged_against_the_host_headers(example, tmp_path):
+    """Drop-in at the source level: the reference's example mains, untouched, against our headers."""
+    src = REFERENCE / "examples" / f"{example}.cpp"
+    cmd = ["g++", "-std=c++20", "-O0", "-w", "-fsyntax-only", f"-I{PKG / 'host'}", f"-I{ROOT / 'include'}", str(src)]
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    assert proc.returncode == 0, proc.stderr[-3000:]
+
+
+@pytest.mark.skipif(not REFERENCE.exists(), reason="/root/reference not present")
+def test_reference_color_test_against_the_host_library(tmp_path):
+    """The reference's colour smoke test, compiled unchanged against the host colour classes, prints
+    the values the reference prints."""
+    exe = tmp_path / "color_test_host"
+    # compile a byte-identical copy placed outside the reference tree, so that its quoted
+    # #include "color.hpp" resolves to OUR headers instead of the file's own directory
+    src = tmp_path / "color_test.cpp"
+    src.write_bytes((REFERENCE / "src" / "color" / "color_test.cpp").read_bytes())
+    cmd = ["g++", "-std=c++20", "-O2", "-ffp-contract=off", "-w", f"-I{PKG / 'host'}", f"-I{PKG / 'host' / 'color'}",
+           f"-I{ROOT / 'include'}", str(src), str(PKG / "host" / "src" / "color.cpp"),
+           "-ldl", "-o", str(exe)]
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    assert proc.returncode == 0, proc.stderr[-3000:]
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True, env={"QZ_DATA_DIR": str(PKG / "data")}).stdout
+    for want in ["whitepoint: 0.3367 0.357918", "0.333314 0.333288", "0.771653 0.470475 0.980432", "0.769878 0.544533 0.671843",
+                 "0.446457 0.594196 0.175637", "0.758855 0.589091 1.49932", "0.656894 0.511026 0.176181", "0.609913 0.599273 1.37064"]:
+        assert want in out, (want, out)
+
+
+def test_obj_loader_semantics(emu, tmp_path):
+    """Face forms, triangle-as-degenerate-quad, comments, extra corners, bad lines."""
+    p = tmp_path / "t.obj"
+    p.write_text("# comment\nv 0 0 -5\nv 1 0 -5\nv 1 1 -5 1.0\nv 0 1 -5\nvn 0 0 1\nvt 0 0\n\ng grp\n"
+                 "f 1 2 3\nf 1/1 2/1 3/1 4/1\nf 1//1 2//1 3//1\nf 1/1/1 2/1/1 3/1/1 4/1/1 1/1/1\nf 1 2\nx junk\n")
+    with emu.build_scene("obj_viewer", 16, 12, obj_path=str(p), obj_material="diffuse", obj_light="point") as sc:
+        assert sc.width == 16
