@@ -24,7 +24,7 @@ def load_cuda_library() -> ctypes.CDLL:
     if not path.exists():
         raise RuntimeError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` (needs nvcc); "
                            "there is no CPU fallback")
-    return ctypes.CDLL(str(path), mode=ctypes.RTLD_GLOBAL)
+    return ctypes.CDLL(str(path))
 
 
 def load_harness():

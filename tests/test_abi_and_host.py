@@ -118,10 +118,22 @@ def test_reference_color_test_against_the_host_library(tmp_path):
         assert want in out, (want, out)
 
 
-def test_obj_loader_semantics(emu, tmp_path):
-    """Face forms, triangle-as-degenerate-quad, comments, extra corners, bad lines."""
-    p = tmp_path / "t.obj"
-    p.write_text("# comment\nv 0 0 -5\nv 1 0 -5\nv 1 1 -5 1.0\nv 0 1 -5\nvn 0 0 1\nvt 0 0\n\ng grp\n"
-                 "f 1 2 3\nf 1/1 2/1 3/1 4/1\nf 1//1 2//1 3//1\nf 1/1/1 2/1/1 3/1/1 4/1/1 1/1/1\nf 1 2\nx junk\n")
-    with emu.build_scene("obj_viewer", 16, 12, obj_path=str(p), obj_material="diffuse", obj_light="point") as sc:
-        assert sc.width == 16
+def test_obj_loader_semantics(emu, oracle, tmp_path):
+    """Face forms, triangle-as-degenerate-quad, comments, extra corners, bad lines: same paths as
+    the reference's regex loader produces."""
+    import sys
+
+    sys.path.insert(0, str(ROOT / "tests"))
+    from common import bits_equal, pixel_samples
+
+    verts = "v -1 0.2 -0.5\nv 1 0.2 -0.5\nv 1 2.2 -0.8 1.0\nv -1 2.2 -0.8\nv 0 3.0 -1\n"
+    plain = tmp_path / "plain.obj"
+    plain.write_text("# comment\n" + verts + "vt 0 0\n\ng grp\nf 1 2 3\nf 1/1 3/1 4/1\nf 4 3 5 5 1\nf 1 2\nx junk\n")
+    smooth = tmp_path / "smooth.obj"
+    smooth.write_text(verts + "vn 0 0 1\nvn 0.1 0 1\nvn 0 0.1 1\n"
+                      "f 1//1 2//2 3//3\nf 1/1/1 3/1/3 4/1/2\nf 4//1 3//2 5//3 5//3\n")
+    for path in (plain, smooth):
+        kw = dict(obj_path=str(path), obj_material="diffuse", obj_light="point")
+        with emu.build_scene("obj_viewer", 32, 24, **kw) as se, oracle.build_scene("obj_viewer", 32, 24, **kw) as so:
+            xys = pixel_samples(so, 600, seed=2)
+            assert bits_equal(se.trace_paths(xys), so.trace_paths(xys)).all(), path.name
