@@ -175,6 +175,7 @@ typedef struct qz_region {
 
 #define QZ_FLAG_UNSORTED_SHADING 1u /* one uber shading kernel over the unsorted queue (evidence runs only) */
 #define QZ_FLAG_COUNT_TRAVERSAL 2u  /* count wide-node visits and primitive tests (slower; for B_ray)        */
+#define QZ_FLAG_FORCE_BVH 8u        /* use the BVH traversal kernels even for scenes small enough for the flat kernel */
 #define QZ_FLAG_STAGE_TIMING 4u     /* CUDA events around every stage (serialises the pipeline; for profiles) */
 
 typedef struct qz_render_options {

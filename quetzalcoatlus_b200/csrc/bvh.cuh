@@ -398,6 +398,7 @@ QZ_HD void trav_init(Trav& tv, const Ray& ray, float tmax_any) {
     tv.tmax_any = tmax_any;
     tv.best.t = INFINITY; tv.best.u = 0.0f; tv.best.v = 0.0f; tv.best.prim = QZ_NO_HIT; tv.best.key = 0xffffffffu;
     tv.best.ng = v3(0.0f, 0.0f, 0.0f);
+    tv.best.geom_id = QZ_NO_HIT; tv.best.prim_id = 0;
     tv.sp = 0;
     tv.cur = 0;
     tv.cur_dist = 0.0f;

@@ -13,9 +13,11 @@ namespace qz {
 
 struct Hit {
     float t, u, v;
-    uint32_t prim;  // slot in the (leaf-ordered) primitive array; 0xffffffff = miss
-    V3 ng;          // unnormalised geometric normal as Embree reports it
-    uint32_t key;   // tie-break key: primitive index in (geomID, primID, cell) order
+    uint32_t prim;     // slot in the (leaf-ordered) primitive array; 0xffffffff = miss
+    V3 ng;             // unnormalised geometric normal as Embree reports it
+    uint32_t key;      // tie-break key: primitive index in (geomID, primID, cell) order
+    uint32_t geom_id;  // RTCHit::geomID
+    uint32_t prim_id;  // RTCHit::primID
 };
 
 #define QZ_NO_HIT 0xffffffffu
@@ -97,9 +99,8 @@ QZ_HD uint32_t prim_key(uint32_t w2) { return w2 >> 2; }
 
 // Tests primitive slot `slot`; updates `best` under the (t, key) order.  tfar is the ray's
 // own far limit (infinity for path rays): validity never depends on the running best.
-QZ_HD void prim_test(const DScene& sc, uint32_t slot, V3 O, V3 D, float tnear, float tfar, Hit& best) {
-    const F4* rec = sc.prims + (size_t)slot * 4;
-    const F4 a = load_f4(rec), b = load_f4(rec + 1), c = load_f4(rec + 2), d = load_f4(rec + 3);
+QZ_HD void prim_test_rec(const DScene& sc, const F4& a, const F4& b, const F4& c, const F4& d, uint32_t slot, V3 O, V3 D,
+                         float tnear, float tfar, Hit& best) {
     const uint32_t w2 = float_as_u32(c.w);
     const uint32_t kind = prim_kind(w2);
     PrimHit h;
@@ -125,7 +126,14 @@ QZ_HD void prim_test(const DScene& sc, uint32_t slot, V3 O, V3 D, float tnear, f
     const uint32_t key = prim_key(w2);
     if (h.t < best.t || (h.t == best.t && key < best.key)) {
         best.t = h.t; best.u = h.u; best.v = h.v; best.ng = h.ng; best.prim = slot; best.key = key;
+        best.geom_id = float_as_u32(a.w); best.prim_id = float_as_u32(b.w);
     }
+}
+
+QZ_HD void prim_test(const DScene& sc, uint32_t slot, V3 O, V3 D, float tnear, float tfar, Hit& best) {
+    const F4* rec = sc.prims + (size_t)slot * 4;
+    const F4 a = load_f4(rec), b = load_f4(rec + 1), c = load_f4(rec + 2), d = load_f4(rec + 3);
+    prim_test_rec(sc, a, b, c, d, slot, O, D, tnear, tfar, best);
 }
 
 }  // namespace qz

@@ -194,17 +194,40 @@ __global__ void k_sensor_eval(DCamera cam, uint32_t n, const float* in, float* o
 // RAII device buffer
 struct DevBuf {
     void* p = nullptr;
+    size_t bytes = 0;
     ~DevBuf() { if (p) cudaFree(p); }
-    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+    cudaError_t alloc(size_t n) {
+        if (p) { cudaFree(p); p = nullptr; }
+        bytes = n ? n : 1;
+        return cudaMalloc(&p, bytes);
+    }
+    // grow-only variant for buffers that live across calls
+    cudaError_t reserve(size_t n) { return (p && bytes >= n) ? cudaSuccess : alloc(n); }
     template <class T> T* as() { return static_cast<T*>(p); }
 };
 
 }  // namespace
 
+// Working memory of render(): allocated on first use, kept with the scene and re-used by later
+// calls of the same or a smaller size (cudaMalloc/cudaFree of gigabytes per call would otherwise
+// dominate the end-to-end time of short renders).
+struct WorkMem {
+    DevBuf f4bufs[14], qbufs[12], counters, statsb, res_a, res_b, res_c, rowsb, sensor, acc;
+    uint32_t pool = 0;
+    uint64_t cells = 0, acc_pix = 0, rows = 0;
+    uint32_t* h_counters = nullptr;  // pinned
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_a = nullptr, ev_b = nullptr;
+    ~WorkMem() {
+        if (h_counters) cudaFreeHost(h_counters);
+        for (cudaEvent_t e : {ev_begin, ev_end, ev_a, ev_b}) if (e) cudaEventDestroy(e);
+    }
+};
+
 struct qz_scene_t {
     SceneStore<CudaExec> store;
     int device = 0;
     DeviceTables tables;
+    WorkMem work;
 };
 
 extern "C" {
@@ -316,19 +339,23 @@ static int render_impl(qz_scene s, const qz_camera* camera, uint32_t n_samples, 
     pool = (uint32_t)std::min<uint64_t>(pool, cells);
     pool = std::max(pool, 1u);
 
-    // ---- allocations
-    DevBuf f4bufs[14], qbufs[8], counters, statsb, res_a, res_b, res_c, rowsb, sensor, acc;
-    for (auto& b : f4bufs) QZ_CUDA(b.alloc((size_t)pool * 16));
-    for (auto& b : qbufs) QZ_CUDA(b.alloc((size_t)pool * 4));
-    QZ_CUDA(counters.alloc(C_WORDS * 4));
-    QZ_CUDA(statsb.alloc(S_WORDS * 8));
-    QZ_CUDA(res_a.alloc(cells * 16));
-    QZ_CUDA(res_b.alloc(cells * 16));
-    QZ_CUDA(res_c.alloc(cells * 4));
-    QZ_CUDA(rowsb.alloc(rows.size() * 4));
-    QZ_CUDA(sensor.alloc(3 * 471 * 4));
+    // ---- working memory (cached in the scene handle)
+    WorkMem& wm = s->work;
+    DevBuf(&f4bufs)[14] = wm.f4bufs;
+    DevBuf(&qbufs)[12] = wm.qbufs;
+    DevBuf &counters = wm.counters, &statsb = wm.statsb, &res_a = wm.res_a, &res_b = wm.res_b, &res_c = wm.res_c,
+           &rowsb = wm.rowsb, &sensor = wm.sensor, &acc = wm.acc;
+    for (auto& buf : f4bufs) QZ_CUDA(buf.reserve((size_t)pool * 16));
+    for (auto& buf : qbufs) QZ_CUDA(buf.reserve((size_t)pool * 4));
+    QZ_CUDA(counters.reserve(C_WORDS * 4));
+    QZ_CUDA(statsb.reserve(S_WORDS * 8));
+    QZ_CUDA(res_a.reserve(cells * 16));
+    QZ_CUDA(res_b.reserve(cells * 16));
+    QZ_CUDA(res_c.reserve(cells * 4));
+    QZ_CUDA(rowsb.reserve(rows.size() * 4));
+    QZ_CUDA(sensor.reserve(3 * 471 * 4));
     const bool multi_pass = s_pass < n_samples;
-    if (multi_pass) QZ_CUDA(acc.alloc((size_t)n_pix * 9 * 4));
+    if (multi_pass) QZ_CUDA(acc.reserve((size_t)n_pix * 9 * 4));
     QZ_CUDA(cudaMemcpyAsync(rowsb.p, rows.data(), rows.size() * 4, cudaMemcpyHostToDevice, stream));
     QZ_CUDA(cudaMemcpyAsync(sensor.p, camera->sensor_rgb, 3 * 471 * 4, cudaMemcpyHostToDevice, stream));
     QZ_CUDA(cudaMemsetAsync(statsb.p, 0, S_WORDS * 8, stream));
@@ -343,7 +370,7 @@ static int render_impl(qz_scene s, const qz_camera* camera, uint32_t n_samples, 
     b.sh_o = f4bufs[11].as<float4>(); b.sh_d = f4bufs[12].as<float4>(); b.sh_c = f4bufs[13].as<float4>();
     b.q_trace[0] = qbufs[0].as<uint32_t>(); b.q_trace[1] = qbufs[1].as<uint32_t>();
     for (int k = 0; k < SQ_COUNT; k++) b.q_shade[k] = qbufs[2 + k].as<uint32_t>();
-    b.q_shadow = qbufs[6].as<uint32_t>(); b.q_done = qbufs[7].as<uint32_t>();
+    b.q_shadow = qbufs[10].as<uint32_t>(); b.q_done = qbufs[11].as<uint32_t>();
     b.counters = counters.as<uint32_t>();
     b.stats = statsb.as<unsigned long long>();
     b.res_a = res_a.as<float4>(); b.res_b = res_b.as<float4>(); b.res_c = res_c.as<float>();
@@ -351,19 +378,23 @@ static int render_impl(qz_scene s, const qz_camera* camera, uint32_t n_samples, 
 
     DCamera cam = make_camera(camera, sensor.as<float>());
     const bool count_trav = (flags & QZ_FLAG_COUNT_TRAVERSAL) != 0;
-    const bool stage_timing = (flags & 4u) != 0;
+    const bool stage_timing = (flags & QZ_FLAG_STAGE_TIMING) != 0;
+    // tiny scenes skip the BVH (k_closest_flat); counting runs and QZ_FLAG_FORCE_BVH keep the traversal kernels
+    const bool flat = sc.n_prims <= QZ_FLAT_MAX_PRIMS && sc.n_prims > 0 && !count_trav && !(flags & QZ_FLAG_FORCE_BVH);
 
     int n_sm = 148;
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, s->device);
     const int trav_blocks = n_sm * 8;   // persistent: 8 CTAs of 4 warps per SM
     const int shade_blocks = n_sm * 8;
 
-    cudaEvent_t ev_begin, ev_end, ev_a, ev_b;
-    QZ_CUDA(cudaEventCreate(&ev_begin)); QZ_CUDA(cudaEventCreate(&ev_end));
-    QZ_CUDA(cudaEventCreate(&ev_a)); QZ_CUDA(cudaEventCreate(&ev_b));
+    if (!wm.ev_begin) {
+        QZ_CUDA(cudaEventCreate(&wm.ev_begin)); QZ_CUDA(cudaEventCreate(&wm.ev_end));
+        QZ_CUDA(cudaEventCreate(&wm.ev_a)); QZ_CUDA(cudaEventCreate(&wm.ev_b));
+        QZ_CUDA(cudaMallocHost(&wm.h_counters, C_WORDS * 4));
+    }
+    cudaEvent_t ev_begin = wm.ev_begin, ev_end = wm.ev_end, ev_a = wm.ev_a, ev_b = wm.ev_b;
+    uint32_t* h_counters = wm.h_counters;
     QZ_CUDA(cudaEventRecord(ev_begin, stream));
-    uint32_t* h_counters = nullptr;
-    QZ_CUDA(cudaMallocHost(&h_counters, C_WORDS * 4));
 
     auto timed = [&](float& acc_ms, auto&& launch) -> cudaError_t {
         if (!stage_timing) { launch(); return cudaGetLastError(); }
@@ -403,26 +434,34 @@ static int render_impl(qz_scene s, const qz_camera* camera, uint32_t n_samples, 
         for (;;) {
             const int nxt = cur ^ 1;
             QZ_CUDA(timed(st.ms_closest, [&] {
-                if (count_trav) k_closest_hit<true><<<trav_blocks, 128, 0, stream>>>(sc, b, cur, flags);
+                if (flat) k_closest_flat<<<shade_blocks, 256, 0, stream>>>(sc, b, cur, flags);
+                else if (count_trav) k_closest_hit<true><<<trav_blocks, 128, 0, stream>>>(sc, b, cur, flags);
                 else k_closest_hit<false><<<trav_blocks, 128, 0, stream>>>(sc, b, cur, flags);
             }));
             QZ_CUDA(timed(st.ms_shade, [&] {
-                k_shade<KH_ANY><<<shade_blocks, 128, 0, stream>>>(sc, b, SQ_MISC, nxt, max_bounces);
-                if (!(flags & QZ_FLAG_UNSORTED_SHADING)) {
-                    k_shade<KH_DIFFUSE><<<shade_blocks, 128, 0, stream>>>(sc, b, SQ_DIFFUSE, nxt, max_bounces);
-                    k_shade<KH_CONDUCTOR><<<shade_blocks, 128, 0, stream>>>(sc, b, SQ_CONDUCTOR, nxt, max_bounces);
-                    k_shade<KH_DIELECTRIC><<<shade_blocks, 128, 0, stream>>>(sc, b, SQ_DIELECTRIC, nxt, max_bounces);
+                if (flags & QZ_FLAG_UNSORTED_SHADING) {
+                    k_shade<KH_ANY, -1><<<shade_blocks, 128, 0, stream>>>(sc, b, SQ_MISC, nxt, max_bounces);
+                } else {
+                    k_shade<KH_ANY, 1><<<shade_blocks, 128, 0, stream>>>(sc, b, SQ_FAMILIES + SQ_MISC, nxt, max_bounces);
+                    k_shade<KH_DIFFUSE, 1><<<shade_blocks, 128, 0, stream>>>(sc, b, SQ_FAMILIES + SQ_DIFFUSE, nxt, max_bounces);
+                    k_shade<KH_CONDUCTOR, 1><<<shade_blocks, 128, 0, stream>>>(sc, b, SQ_FAMILIES + SQ_CONDUCTOR, nxt, max_bounces);
+                    k_shade<KH_DIELECTRIC, 1><<<shade_blocks, 128, 0, stream>>>(sc, b, SQ_FAMILIES + SQ_DIELECTRIC, nxt, max_bounces);
+                    k_shade<KH_ANY, 0><<<shade_blocks, 128, 0, stream>>>(sc, b, SQ_MISC, nxt, max_bounces);
+                    k_shade<KH_DIFFUSE, 0><<<shade_blocks, 128, 0, stream>>>(sc, b, SQ_DIFFUSE, nxt, max_bounces);
+                    k_shade<KH_CONDUCTOR, 0><<<shade_blocks, 128, 0, stream>>>(sc, b, SQ_CONDUCTOR, nxt, max_bounces);
+                    k_shade<KH_DIELECTRIC, 0><<<shade_blocks, 128, 0, stream>>>(sc, b, SQ_DIELECTRIC, nxt, max_bounces);
                 }
             }));
             QZ_CUDA(timed(st.ms_shadow, [&] {
-                if (count_trav) k_shadow<true><<<trav_blocks, 128, 0, stream>>>(sc, b);
+                if (flat) k_shadow_flat<<<shade_blocks, 256, 0, stream>>>(sc, b);
+                else if (count_trav) k_shadow<true><<<trav_blocks, 128, 0, stream>>>(sc, b);
                 else k_shadow<false><<<trav_blocks, 128, 0, stream>>>(sc, b);
             }));
             QZ_CUDA(timed(st.ms_other, [&] {
                 k_finish<<<shade_blocks, 256, 0, stream>>>(sc, cam, b, pp, nxt);
                 k_next_iteration<<<1, 32, 0, stream>>>(b, cur);
             }));
-            st.kernel_launches += (flags & QZ_FLAG_UNSORTED_SHADING) ? 5 : 8;
+            st.kernel_launches += (flags & QZ_FLAG_UNSORTED_SHADING) ? 5 : 12;
             st.iterations++;
             it++;
             cur = nxt;
@@ -451,8 +490,6 @@ static int render_impl(qz_scene s, const qz_camera* camera, uint32_t n_samples, 
     st.shade_calls = h_stats[S_SHADE];
     st.node_visits = h_stats[S_NODES];
     st.prim_tests = h_stats[S_PRIMS];
-    cudaFreeHost(h_counters);
-    cudaEventDestroy(ev_begin); cudaEventDestroy(ev_end); cudaEventDestroy(ev_a); cudaEventDestroy(ev_b);
     if (rc == QZ_OK && h_stats[S_PATHS_DONE] != st.paths) rc = fail(QZ_ERR_CUDA, "internal error: finished path count does not match");
     if (stats_out) *stats_out = st;
     return rc;

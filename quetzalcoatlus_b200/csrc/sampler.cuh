@@ -152,18 +152,78 @@ QZ_HD float sample_dimension(const SamplerDim* __restrict__ table, const Sampler
     return owen_scrambled_radical_inv(rec, smp.index);
 }
 
-// Sampler::sample_1d / sample_2d (sampler.cpp:433-447): dimensions wrap to 2 past the table
-QZ_HD float sample_1d(const SamplerDim* __restrict__ table, Sampler& smp) {
-    if (smp.dim >= QZ_N_PRIMES) smp.dim = 2;
-    return sample_dimension(table, smp, smp.dim++);
+// two independent dimensions evaluated in one loop: the digit chains of the two dimensions do
+// not depend on each other, so interleaving them doubles the instruction-level parallelism of
+// what is otherwise one long dependent integer chain per digit
+QZ_HD V2 owen_scrambled_radical_inv_pair(const SamplerDim r0, const SamplerDim r1, uint32_t a) {
+    const uint32_t b0 = r0.base_nd & 0xffffu, b1 = r1.base_nd & 0xffffu;
+    const uint32_t n0 = r0.base_nd >> 16, n1 = r1.base_nd >> 16;
+    uint32_t w0 = b0 - 1, w1 = b1 - 1;
+    w0 |= w0 >> 1; w0 |= w0 >> 2; w0 |= w0 >> 4; w0 |= w0 >> 8; w0 |= w0 >> 16;
+    w1 |= w1 >> 1; w1 |= w1 >> 2; w1 |= w1 >> 4; w1 |= w1 >> 8; w1 |= w1 >> 16;
+    uint64_t rev0 = 0, rev1 = 0;
+    uint32_t a0 = a, a1 = a;
+    const uint32_t nmin = n0 < n1 ? n0 : n1;
+    uint32_t k = 0;
+    for (; k < nmin; k++) {
+        uint32_t d0, d1;
+        a0 = div_magic(a0, b0, r0.magic, d0);
+        a1 = div_magic(a1, b1, r1.magic, d1);
+        uint32_t h0 = (uint32_t)mix_bits((uint64_t)r0.hash ^ rev0);
+        uint32_t h1 = (uint32_t)mix_bits((uint64_t)r1.hash ^ rev1);
+        d0 = permutation_element(d0, b0, r0.magic, w0, h0);
+        d1 = permutation_element(d1, b1, r1.magic, w1, h1);
+        rev0 = rev0 * b0 + d0;
+        rev1 = rev1 * b1 + d1;
+    }
+    for (uint32_t j = k; j < n0; j++) {
+        uint32_t d0;
+        a0 = div_magic(a0, b0, r0.magic, d0);
+        d0 = permutation_element(d0, b0, r0.magic, w0, (uint32_t)mix_bits((uint64_t)r0.hash ^ rev0));
+        rev0 = rev0 * b0 + d0;
+    }
+    for (uint32_t j = k; j < n1; j++) {
+        uint32_t d1;
+        a1 = div_magic(a1, b1, r1.magic, d1);
+        d1 = permutation_element(d1, b1, r1.magic, w1, (uint32_t)mix_bits((uint64_t)r1.hash ^ rev1));
+        rev1 = rev1 * b1 + d1;
+    }
+    return v2(std_min(u32_as_float(r0.scale) * (float)rev0, QZ_ONE_MINUS_EPS),
+              std_min(u32_as_float(r1.scale) * (float)rev1, QZ_ONE_MINUS_EPS));
 }
-QZ_HD V2 sample_2d(const SamplerDim* __restrict__ table, Sampler& smp) {
+
+QZ_HD SamplerDim load_dim(const SamplerDim* __restrict__ table, uint32_t dim) {
+#if defined(__CUDA_ARCH__)
+    const uint4 raw = __ldg(reinterpret_cast<const uint4*>(table) + dim);
+    SamplerDim rec; rec.base_nd = raw.x; rec.magic = raw.y; rec.hash = raw.z; rec.scale = raw.w;
+    return rec;
+#else
+    return table[dim];
+#endif
+}
+
+// Sampler::sample_1d / sample_2d (sampler.cpp:433-447): dimensions wrap to 2 past the table.
+// The *_skip variants advance the dimension counter exactly like the real calls but do not
+// evaluate the value: the reference draws several samples whose value it never reads (the
+// material-select sample of non-mixed materials, the light pick with a single light, the 2-D
+// sample of point lights and specular BxDFs, the 1-D sample of non-dielectric BxDFs, the
+// roulette sample when roulette does not apply); skipping the arithmetic is exact.
+QZ_HD uint32_t sample_1d_skip(Sampler& smp) {
+    if (smp.dim >= QZ_N_PRIMES) smp.dim = 2;
+    return smp.dim++;
+}
+QZ_HD uint32_t sample_2d_skip(Sampler& smp) {
     if (smp.dim + 1 >= QZ_N_PRIMES) smp.dim = 2;
     uint32_t d = smp.dim;
     smp.dim += 2;
-    float a = sample_dimension(table, smp, d);
-    float b = sample_dimension(table, smp, d + 1);
-    return v2(a, b);
+    return d;
+}
+QZ_HD float sample_1d(const SamplerDim* __restrict__ table, Sampler& smp) {
+    return sample_dimension(table, smp, sample_1d_skip(smp));
+}
+QZ_HD V2 sample_2d(const SamplerDim* __restrict__ table, Sampler& smp) {
+    const uint32_t d = sample_2d_skip(smp);
+    return owen_scrambled_radical_inv_pair(load_dim(table, d), load_dim(table, d + 1), smp.index);
 }
 
 // ---- host-side table construction (runs once per process) ---------------------------

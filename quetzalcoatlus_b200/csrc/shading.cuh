@@ -100,10 +100,8 @@ struct SurfacePoint {
 // Scene::ray_intersect after the Embree call (scene.cpp:72-116)
 QZ_HD SurfacePoint make_surface_point(const DScene& sc, const Ray& ray, const Hit& hit) {
     SurfacePoint sp;
-    const F4* rec = sc.prims + (size_t)hit.prim * 4;
-    const uint32_t geom_id = float_as_u32(load_f4(rec).w);
-    const uint32_t prim_id = float_as_u32(load_f4(rec + 1).w);
-    const qz_geometry g = sc.geoms[geom_id];
+    const uint32_t prim_id = hit.prim_id;
+    const qz_geometry g = sc.geoms[hit.geom_id];
     sp.uv = v2(hit.u, hit.v);
     if (g.normal_offset >= 0 && g.shape == QZ_SHAPE_OBJ) {
         const int32_t* fi = sc.nidx + 4 * ((size_t)g.nindex_offset + prim_id);
@@ -169,15 +167,20 @@ QZ_HD void sample_lights(const DScene& sc, const SurfacePoint& sp, const Bsdf& f
     int32_t li = -1;
     float proba = 0.0f;
     if (sc.n_lights != 0) {
-        float u = sample_1d(tab, smp);
-        li = (int32_t)(uint32_t)(u * (float)sc.n_lights);
+        // with a single light the pick is index 0 whatever the sample says: draw without evaluating
+        if (sc.n_lights == 1) { sample_1d_skip(smp); li = 0; }
+        else li = (int32_t)(uint32_t)(sample_1d(tab, smp) * (float)sc.n_lights);
         proba = 1.0f / (float)sc.n_lights;
     }
-    V2 u2 = sample_2d(tab, smp);
     if (li < 0) {
-        sample_2d(tab, smp);  // keeps the dimension count even (render.cpp:62-66)
+        sample_2d_skip(smp);
+        sample_2d_skip(smp);  // keeps the dimension count even (render.cpp:62-66)
         return;
     }
+    // point lights never read their 2-D sample (light.cpp:8-17)
+    V2 u2 = v2(0.0f, 0.0f);
+    if (sc.lights[li].kind == QZ_LIGHT_POINT) sample_2d_skip(smp);
+    else u2 = sample_2d(tab, smp);
     const qz_light l = sc.lights[li];
     const V3 lp = v3(l.p[0], l.p[1], l.p[2]);
     Spec4 spec;
@@ -222,9 +225,13 @@ QZ_HD void sample_lights(const DScene& sc, const SurfacePoint& sp, const Bsdf& f
 
 // One iteration of the while loop of sample_pixel() AFTER the closest-hit query.
 // Returns true when the path continues (ps.ray holds the next ray).
-template <int KH>
+// FIRST: 1 = the path is known to be at depth 0, 0 = known to be deeper, -1 = decide at run time.
+// The wavefront sorts first hits into their own queues: only they pay for the 16-sample albedo
+// estimate, and the kernels for deeper bounces do not even contain that code.
+template <int KH, int FIRST>
 QZ_HD bool shade_bounce(const DScene& sc, PathState& ps, PathAov& aov, const Hit& hit, uint32_t max_bounces,
                         ShadowRequest& shadow) {
+    const bool first = FIRST < 0 ? ps.depth == 0 : FIRST != 0;
     ps.flags &= ~QZ_FLAG_HAS_SHADOW;
     const SamplerDim* tab = sc.sampler_table;
     if (hit.prim == QZ_NO_HIT) {
@@ -232,13 +239,13 @@ QZ_HD bool shade_bounce(const DScene& sc, PathState& ps, PathAov& aov, const Hit
         return false;
     }
     SurfacePoint sp = make_surface_point(sc, ps.ray, hit);
-    if (ps.depth == 0) aov.normal = sp.normal;
+    if (first) aov.normal = sp.normal;
 
     if (sp.light >= 0) {
         const qz_light l = sc.lights[sp.light];
         Spec4 emitted = light_emission(sc, l, sp.normal, -ps.ray.d, ps.lambda);
         if (!is_zero(emitted)) {
-            if (ps.depth == 0 || (ps.flags & QZ_FLAG_SPECULAR_BOUNCE)) {
+            if (first || (ps.flags & QZ_FLAG_SPECULAR_BOUNCE)) {
                 ps.L = ps.L + ps.weight * emitted;
             } else {
                 // light_sample_pmf * light->pdf: uniform light pick, area-measure pdf (scene.cpp:132-134, light.cpp:44-46)
@@ -250,17 +257,20 @@ QZ_HD bool shade_bounce(const DScene& sc, PathState& ps, PathAov& aov, const Hit
     }
     if (ps.depth == max_bounces) return false;
 
-    float mat_sample = sample_1d(tab, ps.smp);
+    // the material-select sample is only read by MixedMaterial (material.hpp:94-97)
+    const uint32_t mat_dim = sample_1d_skip(ps.smp);
     if (sp.material < 0) {
         // emitter geometry has no material: pass straight through, depth unchanged (render.cpp:142-148)
         ps.flags |= QZ_FLAG_SPECULAR_BOUNCE;
         ps.ray.o = sp.point;
         return !is_zero(ps.weight);
     }
+    float mat_sample = 0.0f;
+    if (KH == KH_ANY && sc.materials[sp.material].kind == QZ_MAT_MIXED) mat_sample = sample_dimension(tab, ps.smp, mat_dim);
     const int32_t mat = KH == KH_ANY ? resolve_material(sc, sp.material, mat_sample) : sp.material;
     Bsdf f = make_bsdf<KH>(sc, mat, sp, ps.lambda, ps.pdf);
 
-    if (ps.depth == 0) aov.albedo = bsdf_rho_hd<KH>(sc, f, sp.wo);
+    if (first) aov.albedo = bsdf_rho_hd<KH>(sc, f, sp.wo);
 
     if (!bsdf_is_specular<KH>(f)) {
         bool has_shadow;
@@ -276,9 +286,14 @@ QZ_HD bool shade_bounce(const DScene& sc, PathState& ps, PathAov& aov, const Hit
     }
 
     // g++ evaluates the arguments of bsdf->sample(wo, sample_1d(), sample_2d()) right to left:
-    // the 2-D sample takes the next two dimensions, the 1-D sample the one after (render.cpp:177)
-    V2 u2 = sample_2d(tab, ps.smp);
-    float u1 = sample_1d(tab, ps.smp);
+    // the 2-D sample takes the next two dimensions, the 1-D sample the one after (render.cpp:177).
+    // Only diffuse and rough-conductor BxDFs read the 2-D sample, only the dielectrics the 1-D one.
+    const bool needs_u2 = is_kind<KH>(f, BX_DIFFUSE) || (is_kind<KH>(f, BX_CONDUCTOR) && !tr_is_smooth(f.rough));
+    const bool needs_u1 = is_kind<KH>(f, BX_DIELECTRIC) || is_kind<KH>(f, BX_THIN);
+    V2 u2 = v2(0.0f, 0.0f);
+    if (needs_u2) u2 = sample_2d(tab, ps.smp); else sample_2d_skip(ps.smp);
+    float u1 = 0.0f;
+    if (needs_u1) u1 = sample_1d(tab, ps.smp); else sample_1d_skip(ps.smp);
     BsdfSample bs = bsdf_sample<KH>(f, sp.wo, u1, u2);
     if (!bs.valid) return false;
 
@@ -290,10 +305,12 @@ QZ_HD bool shade_bounce(const DScene& sc, PathState& ps, PathAov& aov, const Hit
     ps.ray.d = bs.wi;
     ps.depth++;
 
-    float roulette = sample_1d(tab, ps.smp);
+    // the roulette sample is drawn every bounce but only read when roulette applies (render.cpp:200-208)
+    const uint32_t rr_dim = sample_1d_skip(ps.smp);
     Spec4 rr = ps.weight * ps.ior_scale;
     if (max_component(rr) < 1.f && ps.depth > 1) {
         float q = std_max(0.0f, 1.0f - max_component(rr));
+        float roulette = sample_dimension(tab, ps.smp, rr_dim);
         if (roulette < q) return false;
         ps.weight = ps.weight / (1.0f - q);
     }
@@ -334,7 +351,7 @@ QZ_HD void run_path(const DScene& sc, const DCamera& cam, const SamplerParams& s
         closest_hit<COUNT>(sc, ps.ray, hit, cnt);
         ps.n_rays++;
         ShadowRequest sh;
-        bool alive = shade_bounce<KH_ANY>(sc, ps, aov, hit, max_bounces, sh);
+        bool alive = shade_bounce<KH_ANY, -1>(sc, ps, aov, hit, max_bounces, sh);
         if (ps.flags & QZ_FLAG_HAS_SHADOW) {
             Ray sr;
             sr.o = sh.o; sr.d = sh.d;

@@ -34,15 +34,20 @@ namespace qz {
 
 namespace cg = cooperative_groups;
 
-enum ShadeQueue { SQ_MISC = 0, SQ_DIFFUSE = 1, SQ_CONDUCTOR = 2, SQ_DIELECTRIC = 3, SQ_COUNT = 4 };
+// shade queues: material family x {later bounce, first hit}
+enum ShadeQueue { SQ_MISC = 0, SQ_DIFFUSE = 1, SQ_CONDUCTOR = 2, SQ_DIELECTRIC = 3, SQ_FAMILIES = 4, SQ_COUNT = 8 };
+
+// trace-queue entries carry the slot in the low 31 bits and "this path is at depth 0" in bit 31
+#define QZ_ENTRY_FIRST 0x80000000u
+#define QZ_FLAT_MAX_PRIMS 96  /* scenes this small are intersected without a BVH (k_closest_flat) */
 
 // counter block layout (uint32 words)
 enum Counter {
     C_TRACE0 = 0, C_TRACE1 = 1,           // sizes of the double-buffered trace queue
     C_SHADE0 = 2,                         // .. C_SHADE0 + SQ_COUNT - 1
-    C_SHADOW = 6, C_DONE = 7,
-    C_CURSOR_TRACE = 8, C_CURSOR_SHADOW = 9,
-    C_NEXT_PATH = 10,                     // next path id of the pass to hand out
+    C_SHADOW = 10, C_DONE = 11,
+    C_CURSOR_TRACE = 12, C_CURSOR_SHADOW = 13,
+    C_NEXT_PATH = 14,                     // next path id of the pass to hand out
     C_WORDS = 16
 };
 // 64-bit statistics block
@@ -50,7 +55,7 @@ enum Stat { S_RAYS_CLOSEST = 0, S_RAYS_SHADOW = 1, S_SHADE = 2, S_NODES = 3, S_P
 
 struct WfBuffers {
     float4 *ray_o, *ray_d;      // o.xyz | ior_scale ; d.xyz | p_b
-    float4 *hit_a, *hit_b;      // t, u, v, prim ; Ng.xyz, key
+    float4 *hit_a, *hit_b;      // t, u, v, primID ; Ng.xyz, geomID (0xffffffff = miss)
     float4 *weight, *radiance, *lambda, *lpdf;
     uint4* misc;                // path id, halton index, dim | depth << 16 | flags << 24, rays issued
     float4 *aov_n, *aov_a;
@@ -138,15 +143,14 @@ __device__ __forceinline__ void init_slot(const DScene& sc, const DCamera& cam, 
 __global__ void __launch_bounds__(256) k_generate(DScene sc, DCamera cam, WfBuffers b, PassParams pp, uint32_t n) {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         init_slot(sc, cam, b, pp, i, i);
-        b.q_trace[0][i] = i;
+        b.q_trace[0][i] = i | QZ_ENTRY_FIRST;
     }
 }
 
 // family of the surface a closest-hit result lands on (the branch-sorting key)
 __device__ __forceinline__ int classify_hit(const DScene& sc, const Hit& hit, bool unsorted) {
-    if (unsorted || hit.prim == QZ_NO_HIT) return SQ_MISC;
-    const uint32_t geom = __float_as_uint(__ldg(reinterpret_cast<const float4*>(sc.prims + (size_t)hit.prim * 4)).w);
-    const int32_t mat = sc.geoms[geom].material;
+    if (unsorted || hit.geom_id == QZ_NO_HIT) return SQ_MISC;
+    const int32_t mat = sc.geoms[hit.geom_id].material;
     if (mat < 0) return SQ_MISC;
     const uint32_t kind = sc.materials[mat].kind;
     if (kind == QZ_MAT_DIFFUSE) return SQ_DIFFUSE;
@@ -154,6 +158,23 @@ __device__ __forceinline__ int classify_hit(const DScene& sc, const Hit& hit, bo
     if (kind == QZ_MAT_DIELECTRIC || kind == QZ_MAT_THIN_DIELECTRIC) return SQ_DIELECTRIC;
     return SQ_MISC;  // MixedMaterial: the family depends on the bounce's material sample
 }
+
+// closest-hit epilogue shared by the BVH and the flat kernel: write the hit record, sort the path
+__device__ __forceinline__ void finish_closest(const DScene& sc, const WfBuffers& b, uint32_t entry, const Hit& h, uint32_t flags) {
+    const uint32_t slot = entry & ~QZ_ENTRY_FIRST;
+    b.hit_a[slot] = f4(h.t, h.u, h.v, __uint_as_float(h.prim_id));
+    b.hit_b[slot] = f4(h.ng.x, h.ng.y, h.ng.z, __uint_as_float(h.geom_id));
+    const int fam = classify_hit(sc, h, (flags & QZ_FLAG_UNSORTED_SHADING) != 0);
+    const int q = fam + ((entry & QZ_ENTRY_FIRST) && !(flags & QZ_FLAG_UNSORTED_SHADING) ? SQ_FAMILIES : 0);
+    queue_push(&b.counters[C_SHADE0 + q], b.q_shade[q], slot);
+}
+
+#ifndef QZ_SHADE_MIN_BLOCKS_LIGHT
+#define QZ_SHADE_MIN_BLOCKS_LIGHT 5   /* diffuse / dielectric shade kernels: 96 registers */
+#endif
+#ifndef QZ_SHADE_MIN_BLOCKS_HEAVY
+#define QZ_SHADE_MIN_BLOCKS_HEAVY 3   /* conductor / run-time-dispatch shade kernels */
+#endif
 
 #define QZ_REFILL_MIN 8   /* idle lanes that trigger a refill from the queue */
 #define QZ_STEPS_PER_ROUND 4
@@ -184,8 +205,8 @@ __global__ void __launch_bounds__(128) k_closest_hit(DScene sc, WfBuffers b, int
             if (!active) {
                 const uint32_t idx = base + __popc(idle & ((1u << lane) - 1u));
                 if (idx < count) {
-                    slot = queue[idx];
-                    const float4 o = b.ray_o[slot], d = b.ray_d[slot];
+                    slot = queue[idx];  // entry: slot | first-hit flag
+                    const float4 o = b.ray_o[slot & ~QZ_ENTRY_FIRST], d = b.ray_d[slot & ~QZ_ENTRY_FIRST];
                     Ray r;
                     r.o = v3(o.x, o.y, o.z);
                     r.d = v3(d.x, d.y, d.z);
@@ -200,17 +221,64 @@ __global__ void __launch_bounds__(128) k_closest_hit(DScene sc, WfBuffers b, int
         for (int k = 0; k < QZ_STEPS_PER_ROUND; k++)
             if (active && !tv.done) trav_step<false, COUNT>(sc, tv, &cnt);
         if (active && tv.done) {
-            const Hit& h = tv.best;
-            b.hit_a[slot] = f4(h.t, h.u, h.v, __uint_as_float(h.prim));
-            b.hit_b[slot] = f4(h.ng.x, h.ng.y, h.ng.z, 0.0f);
-            const int fam = classify_hit(sc, h, (flags & QZ_FLAG_UNSORTED_SHADING) != 0);
-            queue_push(&b.counters[C_SHADE0 + fam], b.q_shade[fam], slot);
+            finish_closest(sc, b, slot, tv.best, flags);
             active = false;
         }
     }
     if (COUNT) {
         atomicAdd(&b.stats[S_NODES], (unsigned long long)cnt.nodes);
         atomicAdd(&b.stats[S_PRIMS], (unsigned long long)cnt.prims);
+    }
+}
+
+// Tiny scenes (<= QZ_FLAT_MAX_PRIMS primitives: every shipped analytic scene): no BVH at all.
+// The primitive records are staged once per CTA in shared memory and every lane walks the
+// same list in lockstep -- no stack, no divergence between lanes, broadcast shared-memory
+// reads.  The result is the brute-force minimum under the (t, key) order, i.e. exactly what the
+// BVH traversal is defined to return.
+__global__ void __launch_bounds__(256) k_closest_flat(DScene sc, WfBuffers b, int qsel, uint32_t flags) {
+    __shared__ F4 s_prims[QZ_FLAT_MAX_PRIMS * 4];
+    const uint32_t n_prims = sc.n_prims;
+    for (uint32_t i = threadIdx.x; i < n_prims * 4; i += blockDim.x) s_prims[i] = sc.prims[i];
+    __syncthreads();
+    const uint32_t count = b.counters[C_TRACE0 + qsel];
+    const uint32_t* queue = b.q_trace[qsel];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+        const uint32_t entry = queue[i];
+        const uint32_t slot = entry & ~QZ_ENTRY_FIRST;
+        const float4 o = b.ray_o[slot], d = b.ray_d[slot];
+        const V3 O = v3(o.x, o.y, o.z), D = v3(d.x, d.y, d.z);
+        Hit best;
+        best.t = INFINITY; best.u = 0.0f; best.v = 0.0f; best.prim = QZ_NO_HIT; best.key = 0xffffffffu;
+        best.ng = v3(0.0f, 0.0f, 0.0f); best.geom_id = QZ_NO_HIT; best.prim_id = 0;
+#pragma unroll 1
+        for (uint32_t p = 0; p < n_prims; p++)
+            prim_test_rec(sc, s_prims[4 * p], s_prims[4 * p + 1], s_prims[4 * p + 2], s_prims[4 * p + 3], p, O, D, QZ_TNEAR, INFINITY, best);
+        finish_closest(sc, b, entry, best, flags);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_shadow_flat(DScene sc, WfBuffers b) {
+    __shared__ F4 s_prims[QZ_FLAT_MAX_PRIMS * 4];
+    const uint32_t n_prims = sc.n_prims;
+    for (uint32_t i = threadIdx.x; i < n_prims * 4; i += blockDim.x) s_prims[i] = sc.prims[i];
+    __syncthreads();
+    const uint32_t count = b.counters[C_SHADOW];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+        const uint32_t slot = b.q_shadow[i];
+        const float4 o = b.sh_o[slot], d = b.sh_d[slot];
+        const V3 O = v3(o.x, o.y, o.z), D = v3(d.x, d.y, d.z);
+        Hit best;
+        best.t = INFINITY; best.u = 0.0f; best.v = 0.0f; best.prim = QZ_NO_HIT; best.key = 0xffffffffu;
+        best.ng = v3(0.0f, 0.0f, 0.0f); best.geom_id = QZ_NO_HIT; best.prim_id = 0;
+        // occluded iff the closest hit has t <= 1 (scene.cpp:136-143)
+#pragma unroll 1
+        for (uint32_t p = 0; p < n_prims; p++)
+            prim_test_rec(sc, s_prims[4 * p], s_prims[4 * p + 1], s_prims[4 * p + 2], s_prims[4 * p + 3], p, O, D, QZ_TNEAR, INFINITY, best);
+        if (!(best.prim != QZ_NO_HIT && best.t <= 1.0f)) {
+            const float4 L = b.radiance[slot], c = b.sh_c[slot];
+            b.radiance[slot] = f4(L.x + c.x, L.y + c.y, L.z + c.z, L.w + c.w);
+        }
     }
 }
 
@@ -266,11 +334,12 @@ __global__ void __launch_bounds__(128) k_shadow(DScene sc, WfBuffers b) {
     }
 }
 
-// One bounce for every path of one family queue.
-template <int KH>
-__global__ void __launch_bounds__(128) k_shade(DScene sc, WfBuffers b, int fam, int next_sel, uint32_t max_bounces) {
-    const uint32_t count = b.counters[C_SHADE0 + fam];
-    const uint32_t* queue = b.q_shade[fam];
+// One bounce for every path of one (family, first-hit?) queue.
+template <int KH, int FIRST>
+__global__ void __launch_bounds__(128, (KH == KH_DIFFUSE || KH == KH_DIELECTRIC) ? QZ_SHADE_MIN_BLOCKS_LIGHT : QZ_SHADE_MIN_BLOCKS_HEAVY)
+k_shade(DScene sc, WfBuffers b, int queue_id, int next_sel, uint32_t max_bounces) {
+    const uint32_t count = b.counters[C_SHADE0 + queue_id];
+    const uint32_t* queue = b.q_shade[queue_id];
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
         const uint32_t slot = queue[i];
         PathState ps;
@@ -278,15 +347,17 @@ __global__ void __launch_bounds__(128) k_shade(DScene sc, WfBuffers b, int fam, 
         ps.n_rays++;  // the closest-hit query that produced this hit
         const float4 ha = b.hit_a[slot], hb = b.hit_b[slot];
         Hit hit;
-        hit.t = ha.x; hit.u = ha.y; hit.v = ha.z; hit.prim = __float_as_uint(ha.w);
+        hit.t = ha.x; hit.u = ha.y; hit.v = ha.z; hit.prim_id = __float_as_uint(ha.w);
         hit.ng = v3(hb.x, hb.y, hb.z);
+        hit.geom_id = __float_as_uint(hb.w);
+        hit.prim = hit.geom_id;  // only compared against QZ_NO_HIT from here on
         hit.key = 0;
         PathAov aov;
         aov.normal = v3(0.0f, 0.0f, 0.0f);
         aov.albedo = spec4(0.0f);
-        const bool first = ps.depth == 0;
+        const bool first = FIRST < 0 ? ps.depth == 0 : FIRST != 0;
         ShadowRequest sh;
-        const bool alive = shade_bounce<KH>(sc, ps, aov, hit, max_bounces, sh);
+        const bool alive = shade_bounce<KH, FIRST>(sc, ps, aov, hit, max_bounces, sh);
         if (first) {
             // depth is still 0 after an emitter pass-through, so these may be written more than
             // once per path; the last write (the first real surface) wins, as in the reference
@@ -301,7 +372,7 @@ __global__ void __launch_bounds__(128) k_shade(DScene sc, WfBuffers b, int fam, 
             queue_push(&b.counters[C_SHADOW], b.q_shadow, slot);
         }
         store_state(b, slot, ps, path_id);
-        if (alive) queue_push(&b.counters[C_TRACE0 + next_sel], b.q_trace[next_sel], slot);
+        if (alive) queue_push(&b.counters[C_TRACE0 + next_sel], b.q_trace[next_sel], slot | (ps.depth == 0 ? QZ_ENTRY_FIRST : 0u));
         else queue_push(&b.counters[C_DONE], b.q_done, slot);
     }
 }
@@ -329,7 +400,7 @@ __global__ void __launch_bounds__(256) k_finish(DScene sc, DCamera cam, WfBuffer
         const uint32_t next_id = base + __popc(peers & ((1u << lane) - 1u));
         if (next_id < pp.total) {
             init_slot(sc, cam, b, pp, slot, next_id);
-            queue_push(&b.counters[C_TRACE0 + next_sel], b.q_trace[next_sel], slot);
+            queue_push(&b.counters[C_TRACE0 + next_sel], b.q_trace[next_sel], slot | QZ_ENTRY_FIRST);
         }
     }
 }

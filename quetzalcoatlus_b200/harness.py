@@ -82,6 +82,7 @@ class QzRenderOptions(ctypes.Structure):
 QZ_FLAG_UNSORTED_SHADING = 1
 QZ_FLAG_COUNT_TRAVERSAL = 2
 QZ_FLAG_STAGE_TIMING = 4
+QZ_FLAG_FORCE_BVH = 8
 
 
 @dataclass

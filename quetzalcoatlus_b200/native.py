@@ -11,8 +11,11 @@ from __future__ import annotations
 import ctypes
 from pathlib import Path
 
+import os
+
 PKG_DIR = Path(__file__).resolve().parent
-LIB_DIR = PKG_DIR / "_lib"
+# QZ_LIB_DIR selects another in-tree build of the same sources (tuning variants, profiles/)
+LIB_DIR = Path(os.environ["QZ_LIB_DIR"]).resolve() if os.environ.get("QZ_LIB_DIR") else PKG_DIR / "_lib"
 
 
 def native_paths() -> dict:
