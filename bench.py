@@ -206,7 +206,7 @@ def run_ours(args) -> None:
         if world > 1:
             film.zero_()
         st = QzStats()
-        opts = QzRenderOptions(flags, args.pool, 0, 0)
+        opts = QzRenderOptions(flags | args.flags, args.pool, 0, 0)
         rc = lib.qz_render_device(handle, ctypes.byref(cam), spp, mb, ctypes.byref(region), ctypes.byref(opts),
                                   ctypes.c_void_p(film[0].data_ptr()), ctypes.c_void_p(film[1].data_ptr()),
                                   ctypes.c_void_p(film[2].data_ptr()), ctypes.c_void_p(stream.cuda_stream), ctypes.byref(st))
@@ -250,7 +250,7 @@ def run_ours(args) -> None:
         color = np.zeros((height, width, 3), np.float32)
         normal, albedo = np.zeros_like(color), np.zeros_like(color)
         st = QzStats()
-        opts = QzRenderOptions(0, args.pool, 0, 0)
+        opts = QzRenderOptions(args.flags, args.pool, 0, 0)
         rc = lib.qz_render(handle, ctypes.byref(cam), spp, mb, ctypes.byref(region), ctypes.byref(opts),
                            color.ctypes.data_as(ctypes.c_void_p), normal.ctypes.data_as(ctypes.c_void_p),
                            albedo.ctypes.data_as(ctypes.c_void_p), ctypes.byref(st))
@@ -333,6 +333,7 @@ def main() -> None:
     ap.add_argument("--height", type=int, default=0)
     ap.add_argument("--spp", type=int, default=0, help="samples per pixel PER GPU (default: the workload's)")
     ap.add_argument("--pool", type=int, default=0, help="paths in flight (0 = library default)")
+    ap.add_argument("--flags", type=int, default=0, help="extra QZ_FLAG_* bits for the timed steps (1 unsorted shading, 8 force BVH)")
     ap.add_argument("--mesh-triangles", type=int, default=1_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
