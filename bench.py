@@ -278,8 +278,11 @@ def run_ours(args) -> None:
     # ---- roofline of the dominant stage: one instrumented step (stage events + traversal counters), rank 0, untimed
     roofline, extra = None, {}
     if rank == 0:
-        inst = step(QZ_FLAG_STAGE_TIMING | QZ_FLAG_COUNT_TRAVERSAL) if world == 1 else None
+        inst = step(QZ_FLAG_COUNT_TRAVERSAL) if world == 1 else None   # traversal counters (BVH kernels)
+        timing = step(QZ_FLAG_STAGE_TIMING) if world == 1 else None    # per-stage device time of the real kernels
         if inst:
+            for k in ("ms_closest", "ms_shadow", "ms_shade", "ms_other", "ms_total", "ms_sample"):
+                inst[k] = timing[k]
             n_rays = inst["rays_closest"] + inst["rays_shadow"]
             n_node = inst["node_visits"] / max(n_rays, 1)
             n_prim = inst["prim_tests"] / max(n_rays, 1)
@@ -293,7 +296,9 @@ def run_ours(args) -> None:
             peak, how = measured_peaks()
             achieved = d_bytes / (d_ms * 1e-3) / 1e9 if d_ms > 0 else 0.0
             roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                        "kernel": dom, "peak_source": how, "stage_ms": {k: v[0] for k, v in stages.items()},
+                        "kernel": dom, "peak_source": how,
+                        "stage_ms": {**{k: v[0] for k, v in stages.items()}, "sampler (k_sample)": inst["ms_sample"],
+                                     "finish + regenerate": inst["ms_other"], "step": inst["ms_total"]},
                         "note": "path-tracing of small analytic scenes is issue-bound (integer sampler), not HBM-bound; see DESIGN.md"}
             extra = {"n_node_per_ray": n_node, "n_prim_per_ray": n_prim, "bounces_per_path": inst["shade_calls"] / inst["paths"],
                      "shadow_ray_fraction": inst["rays_shadow"] / max(n_rays, 1), "bvh_nodes": inst["bvh_nodes"],

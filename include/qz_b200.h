@@ -194,8 +194,10 @@ typedef struct qz_stats {
     uint64_t kernel_launches;
     uint64_t node_visits, prim_tests; /* only with QZ_FLAG_COUNT_TRAVERSAL */
     float ms_total;         /* device time of the whole call (CUDA events)                       */
-    float ms_closest, ms_shadow, ms_shade, ms_other; /* per-stage device time (events per stage)  */
+    float ms_closest, ms_shadow, ms_shade, ms_other; /* per-stage device time (QZ_FLAG_STAGE_TIMING) */
     uint32_t bvh_nodes, bvh_bytes;
+    float ms_sample;        /* the sampler stage (k_sample)                                      */
+    uint32_t reserved;
 } qz_stats;
 
 typedef struct qz_scene_t* qz_scene;

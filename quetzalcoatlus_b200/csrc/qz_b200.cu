@@ -212,14 +212,16 @@ struct DevBuf {
 // calls of the same or a smaller size (cudaMalloc/cudaFree of gigabytes per call would otherwise
 // dominate the end-to-end time of short renders).
 struct WorkMem {
-    DevBuf f4bufs[14], qbufs[12], counters, statsb, res_a, res_b, res_c, rowsb, sensor, acc;
+    DevBuf f4bufs[14], qbufs[12], samples, counters, statsb, res_a, res_b, res_c, rowsb, sensor, acc;
     uint32_t pool = 0;
     uint64_t cells = 0, acc_pix = 0, rows = 0;
     uint32_t* h_counters = nullptr;  // pinned
+    std::vector<cudaEvent_t> stage_events;
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_a = nullptr, ev_b = nullptr;
     ~WorkMem() {
         if (h_counters) cudaFreeHost(h_counters);
         for (cudaEvent_t e : {ev_begin, ev_end, ev_a, ev_b}) if (e) cudaEventDestroy(e);
+        for (cudaEvent_t e : stage_events) cudaEventDestroy(e);
     }
 };
 
@@ -347,6 +349,7 @@ static int render_impl(qz_scene s, const qz_camera* camera, uint32_t n_samples, 
            &rowsb = wm.rowsb, &sensor = wm.sensor, &acc = wm.acc;
     for (auto& buf : f4bufs) QZ_CUDA(buf.reserve((size_t)pool * 16));
     for (auto& buf : qbufs) QZ_CUDA(buf.reserve((size_t)pool * 4));
+    QZ_CUDA(wm.samples.reserve((size_t)pool * R_COUNT * 4));
     QZ_CUDA(counters.reserve(C_WORDS * 4));
     QZ_CUDA(statsb.reserve(S_WORDS * 8));
     QZ_CUDA(res_a.reserve(cells * 16));
@@ -368,6 +371,7 @@ static int render_impl(qz_scene s, const qz_camera* camera, uint32_t n_samples, 
     b.misc = f4bufs[8].as<uint4>();
     b.aov_n = f4bufs[9].as<float4>(); b.aov_a = f4bufs[10].as<float4>();
     b.sh_o = f4bufs[11].as<float4>(); b.sh_d = f4bufs[12].as<float4>(); b.sh_c = f4bufs[13].as<float4>();
+    b.samples = wm.samples.as<float>();
     b.q_trace[0] = qbufs[0].as<uint32_t>(); b.q_trace[1] = qbufs[1].as<uint32_t>();
     for (int k = 0; k < SQ_COUNT; k++) b.q_shade[k] = qbufs[2 + k].as<uint32_t>();
     b.q_shadow = qbufs[10].as<uint32_t>(); b.q_done = qbufs[11].as<uint32_t>();
@@ -396,15 +400,38 @@ static int render_impl(qz_scene s, const qz_camera* camera, uint32_t n_samples, 
     uint32_t* h_counters = wm.h_counters;
     QZ_CUDA(cudaEventRecord(ev_begin, stream));
 
+    // Stage timing: events are recorded asynchronously between the stages (no host sync inside
+    // the pipeline) and read back once per pass, so the figures are device time per stage of the
+    // very run that is being timed.
+    std::vector<cudaEvent_t>& evpool = wm.stage_events;
+    std::vector<float*> ev_target;
+    size_t ev_used = 0;
+    auto next_event = [&]() -> cudaEvent_t {
+        if (ev_used == evpool.size()) {
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            evpool.push_back(e);
+        }
+        return evpool[ev_used++];
+    };
+    auto flush_events = [&]() {
+        cudaStreamSynchronize(stream);
+        for (size_t i = 0; i + 1 < ev_used; i += 2) {
+            float ms = 0.0f;
+            cudaEventElapsedTime(&ms, evpool[i], evpool[i + 1]);
+            *ev_target[i / 2] += ms;
+        }
+        ev_used = 0;
+        ev_target.clear();
+    };
     auto timed = [&](float& acc_ms, auto&& launch) -> cudaError_t {
         if (!stage_timing) { launch(); return cudaGetLastError(); }
-        cudaEventRecord(ev_a, stream);
+        cudaEvent_t a = next_event(), c = next_event();
+        cudaEventRecord(a, stream);
         launch();
-        cudaEventRecord(ev_b, stream);
-        cudaEventSynchronize(ev_b);
-        float ms = 0.0f;
-        cudaEventElapsedTime(&ms, ev_a, ev_b);
-        acc_ms += ms;
+        cudaEventRecord(c, stream);
+        ev_target.push_back(&acc_ms);
+        if (ev_used >= 8192) flush_events();
         return cudaGetLastError();
     };
 
@@ -438,6 +465,9 @@ static int render_impl(qz_scene s, const qz_camera* camera, uint32_t n_samples, 
                 else if (count_trav) k_closest_hit<true><<<trav_blocks, 128, 0, stream>>>(sc, b, cur, flags);
                 else k_closest_hit<false><<<trav_blocks, 128, 0, stream>>>(sc, b, cur, flags);
             }));
+            if (!(flags & QZ_FLAG_UNSORTED_SHADING)) {
+                QZ_CUDA(timed(st.ms_sample, [&] { k_sample<<<shade_blocks * 2, 256, 0, stream>>>(sc, b); }));
+            }
             QZ_CUDA(timed(st.ms_shade, [&] {
                 if (flags & QZ_FLAG_UNSORTED_SHADING) {
                     k_shade<KH_ANY, -1><<<shade_blocks, 128, 0, stream>>>(sc, b, SQ_MISC, nxt, max_bounces);
@@ -461,7 +491,7 @@ static int render_impl(qz_scene s, const qz_camera* camera, uint32_t n_samples, 
                 k_finish<<<shade_blocks, 256, 0, stream>>>(sc, cam, b, pp, nxt);
                 k_next_iteration<<<1, 32, 0, stream>>>(b, cur);
             }));
-            st.kernel_launches += (flags & QZ_FLAG_UNSORTED_SHADING) ? 5 : 12;
+            st.kernel_launches += (flags & QZ_FLAG_UNSORTED_SHADING) ? 5 : 13;
             st.iterations++;
             it++;
             cur = nxt;
@@ -481,6 +511,7 @@ static int render_impl(qz_scene s, const qz_camera* camera, uint32_t n_samples, 
     }
     QZ_CUDA(cudaEventRecord(ev_end, stream));
     QZ_CUDA(cudaEventSynchronize(ev_end));
+    if (stage_timing) flush_events();
     QZ_CUDA(cudaEventElapsedTime(&st.ms_total, ev_begin, ev_end));
     unsigned long long h_stats[S_WORDS];
     QZ_CUDA(cudaMemcpy(h_stats, b.stats, sizeof(h_stats), cudaMemcpyDeviceToHost));

@@ -156,20 +156,64 @@ QZ_HD Spec4 light_emission(const DScene& sc, const qz_light& l, V3 n, V3 w, cons
     return from_spectrum(sc, l.spectrum, lambda) * l.scale;
 }
 
+// ------------------------------------------------------------------ where a bounce's samples come from
+// The draws of one bounce, in the order the reference makes them (render.cpp:141-200):
+//   material select (1), [light pick (1), light uv (2)] if the BSDF is not specular, BSDF uv (2),
+//   BSDF u1 (1), roulette (1).  shade_bounce() does the dimension bookkeeping itself and asks a
+//   SOURCE for the value of a role at a dimension:
+//   * SamplesOnTheFly evaluates the Owen-scrambled dimension right there (per-path replay, the
+//     run-time-dispatch kernels, the host emulation);
+//   * SamplesPrecomputed returns what k_sample (wavefront.cuh) computed for this bounce in a
+//     separate, fully convergent, high-occupancy integer kernel.
+enum SampleRole { R_MAT = 0, R_PICK = 1, R_LIGHT = 2 /* and 3 */, R_BSDF = 4 /* and 5 */, R_U1 = 6, R_RR = 7, R_COUNT = 8 };
+
+struct SamplesOnTheFly {
+    const SamplerDim* tab;
+    uint32_t index;
+    QZ_HD float one(int, uint32_t dim) const {
+        Sampler s; s.index = index; s.dim = 0;
+        return sample_dimension(tab, s, dim);
+    }
+    QZ_HD V2 two(int, uint32_t dim) const { return owen_scrambled_radical_inv_pair(load_dim(tab, dim), load_dim(tab, dim + 1), index); }
+};
+
+struct SamplesPrecomputed {
+    float v[R_COUNT];
+    QZ_HD float one(int role, uint32_t) const { return v[role]; }
+    QZ_HD V2 two(int role, uint32_t) const { return v2(v[role], v[role + 1]); }
+};
+
+// dimensions of every role of a bounce that starts at dimension d0 (same skip calls as shade_bounce)
+QZ_HD void bounce_dims(uint32_t d0, bool nee, bool has_lights, uint32_t dims[R_COUNT]) {
+    Sampler t; t.index = 0; t.dim = d0;
+    for (int k = 0; k < R_COUNT; k++) dims[k] = 2;
+    dims[R_MAT] = sample_1d_skip(t);
+    if (nee) {
+        if (has_lights) dims[R_PICK] = sample_1d_skip(t);
+        const uint32_t dl = sample_2d_skip(t);
+        dims[R_LIGHT] = dl; dims[R_LIGHT + 1] = dl + 1;
+        if (!has_lights) sample_2d_skip(t);
+    }
+    const uint32_t db = sample_2d_skip(t);
+    dims[R_BSDF] = db; dims[R_BSDF + 1] = db + 1;
+    dims[R_U1] = sample_1d_skip(t);
+    dims[R_RR] = sample_1d_skip(t);
+}
+
 // sample_lights (render.cpp:54-87) without the occlusion test: returns the contribution for a
 // visible light and the shadow segment to test; `has_shadow` false means the term is zero
-template <int KH>
+template <int KH, class SRC>
 QZ_HD void sample_lights(const DScene& sc, const SurfacePoint& sp, const Bsdf& f, const Spec4& lambda, Sampler& smp,
-                         bool& has_shadow, V3& p_light_out, Spec4& result) {
+                         const SRC& src, bool& has_shadow, V3& p_light_out, Spec4& result) {
     has_shadow = false;
     result = spec4(0.0f);
-    const SamplerDim* tab = sc.sampler_table;
     int32_t li = -1;
     float proba = 0.0f;
     if (sc.n_lights != 0) {
         // with a single light the pick is index 0 whatever the sample says: draw without evaluating
-        if (sc.n_lights == 1) { sample_1d_skip(smp); li = 0; }
-        else li = (int32_t)(uint32_t)(sample_1d(tab, smp) * (float)sc.n_lights);
+        const uint32_t dp = sample_1d_skip(smp);
+        if (sc.n_lights == 1) li = 0;
+        else li = (int32_t)(uint32_t)(src.one(R_PICK, dp) * (float)sc.n_lights);
         proba = 1.0f / (float)sc.n_lights;
     }
     if (li < 0) {
@@ -179,8 +223,8 @@ QZ_HD void sample_lights(const DScene& sc, const SurfacePoint& sp, const Bsdf& f
     }
     // point lights never read their 2-D sample (light.cpp:8-17)
     V2 u2 = v2(0.0f, 0.0f);
-    if (sc.lights[li].kind == QZ_LIGHT_POINT) sample_2d_skip(smp);
-    else u2 = sample_2d(tab, smp);
+    const uint32_t dl = sample_2d_skip(smp);
+    if (sc.lights[li].kind != QZ_LIGHT_POINT) u2 = src.two(R_LIGHT, dl);
     const qz_light l = sc.lights[li];
     const V3 lp = v3(l.p[0], l.p[1], l.p[2]);
     Spec4 spec;
@@ -228,12 +272,11 @@ QZ_HD void sample_lights(const DScene& sc, const SurfacePoint& sp, const Bsdf& f
 // FIRST: 1 = the path is known to be at depth 0, 0 = known to be deeper, -1 = decide at run time.
 // The wavefront sorts first hits into their own queues: only they pay for the 16-sample albedo
 // estimate, and the kernels for deeper bounces do not even contain that code.
-template <int KH, int FIRST>
+template <int KH, int FIRST, class SRC>
 QZ_HD bool shade_bounce(const DScene& sc, PathState& ps, PathAov& aov, const Hit& hit, uint32_t max_bounces,
-                        ShadowRequest& shadow) {
+                        ShadowRequest& shadow, const SRC& src) {
     const bool first = FIRST < 0 ? ps.depth == 0 : FIRST != 0;
     ps.flags &= ~QZ_FLAG_HAS_SHADOW;
-    const SamplerDim* tab = sc.sampler_table;
     if (hit.prim == QZ_NO_HIT) {
         if (sc.bg_spectrum >= 0) ps.L = ps.L + ps.weight * from_spectrum(sc, sc.bg_spectrum, ps.lambda) * sc.bg_scale;
         return false;
@@ -266,7 +309,7 @@ QZ_HD bool shade_bounce(const DScene& sc, PathState& ps, PathAov& aov, const Hit
         return !is_zero(ps.weight);
     }
     float mat_sample = 0.0f;
-    if (KH == KH_ANY && sc.materials[sp.material].kind == QZ_MAT_MIXED) mat_sample = sample_dimension(tab, ps.smp, mat_dim);
+    if (KH == KH_ANY && sc.materials[sp.material].kind == QZ_MAT_MIXED) mat_sample = src.one(R_MAT, mat_dim);
     const int32_t mat = KH == KH_ANY ? resolve_material(sc, sp.material, mat_sample) : sp.material;
     Bsdf f = make_bsdf<KH>(sc, mat, sp, ps.lambda, ps.pdf);
 
@@ -276,7 +319,7 @@ QZ_HD bool shade_bounce(const DScene& sc, PathState& ps, PathAov& aov, const Hit
         bool has_shadow;
         V3 p_light;
         Spec4 direct;
-        sample_lights<KH>(sc, sp, f, ps.lambda, ps.smp, has_shadow, p_light, direct);
+        sample_lights<KH>(sc, sp, f, ps.lambda, ps.smp, src, has_shadow, p_light, direct);
         if (has_shadow) {
             shadow.o = sp.point;
             shadow.d = p_light - sp.point;
@@ -291,9 +334,11 @@ QZ_HD bool shade_bounce(const DScene& sc, PathState& ps, PathAov& aov, const Hit
     const bool needs_u2 = is_kind<KH>(f, BX_DIFFUSE) || (is_kind<KH>(f, BX_CONDUCTOR) && !tr_is_smooth(f.rough));
     const bool needs_u1 = is_kind<KH>(f, BX_DIELECTRIC) || is_kind<KH>(f, BX_THIN);
     V2 u2 = v2(0.0f, 0.0f);
-    if (needs_u2) u2 = sample_2d(tab, ps.smp); else sample_2d_skip(ps.smp);
+    const uint32_t db = sample_2d_skip(ps.smp);
+    if (needs_u2) u2 = src.two(R_BSDF, db);
     float u1 = 0.0f;
-    if (needs_u1) u1 = sample_1d(tab, ps.smp); else sample_1d_skip(ps.smp);
+    const uint32_t du = sample_1d_skip(ps.smp);
+    if (needs_u1) u1 = src.one(R_U1, du);
     BsdfSample bs = bsdf_sample<KH>(f, sp.wo, u1, u2);
     if (!bs.valid) return false;
 
@@ -310,7 +355,7 @@ QZ_HD bool shade_bounce(const DScene& sc, PathState& ps, PathAov& aov, const Hit
     Spec4 rr = ps.weight * ps.ior_scale;
     if (max_component(rr) < 1.f && ps.depth > 1) {
         float q = std_max(0.0f, 1.0f - max_component(rr));
-        float roulette = sample_dimension(tab, ps.smp, rr_dim);
+        float roulette = src.one(R_RR, rr_dim);
         if (roulette < q) return false;
         ps.weight = ps.weight / (1.0f - q);
     }
@@ -351,7 +396,9 @@ QZ_HD void run_path(const DScene& sc, const DCamera& cam, const SamplerParams& s
         closest_hit<COUNT>(sc, ps.ray, hit, cnt);
         ps.n_rays++;
         ShadowRequest sh;
-        bool alive = shade_bounce<KH_ANY, -1>(sc, ps, aov, hit, max_bounces, sh);
+        SamplesOnTheFly src;
+        src.tab = sc.sampler_table; src.index = ps.smp.index;
+        bool alive = shade_bounce<KH_ANY, -1>(sc, ps, aov, hit, max_bounces, sh, src);
         if (ps.flags & QZ_FLAG_HAS_SHADOW) {
             Ray sr;
             sr.o = sh.o; sr.d = sh.d;

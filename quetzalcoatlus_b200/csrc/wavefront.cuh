@@ -60,6 +60,7 @@ struct WfBuffers {
     uint4* misc;                // path id, halton index, dim | depth << 16 | flags << 24, rays issued
     float4 *aov_n, *aov_a;
     float4 *sh_o, *sh_d, *sh_c;
+    float* samples;             // R_COUNT floats per slot: this bounce's draws, written by k_sample
     uint32_t* q_trace[2];
     uint32_t* q_shade[SQ_COUNT];
     uint32_t *q_shadow, *q_done;
@@ -334,6 +335,67 @@ __global__ void __launch_bounds__(128) k_shadow(DScene sc, WfBuffers b) {
     }
 }
 
+// roles (bit mask over SampleRole) a queue's paths will read this bounce
+__device__ __forceinline__ uint32_t queue_roles(int queue_id, uint32_t n_lights) {
+    const int fam = queue_id % SQ_FAMILIES;
+    const bool first = queue_id >= SQ_FAMILIES;
+    if (fam == SQ_MISC) return 0u;  // run-time dispatch: evaluated on the fly inside k_shade<KH_ANY>
+    uint32_t m = 0;
+    if (fam == SQ_DIFFUSE || fam == SQ_CONDUCTOR) {
+        m |= (3u << R_LIGHT) | (3u << R_BSDF);
+        if (n_lights > 1) m |= 1u << R_PICK;
+    } else {
+        m |= 1u << R_U1;
+    }
+    if (!first) m |= 1u << R_RR;  // roulette cannot apply at depth 1 (render.cpp:202)
+    return m;
+}
+
+// The sampler as its own wavefront stage.  The Owen-scrambled Halton evaluation is a long,
+// purely integer, dependent chain per digit (~75 instructions); inside the shading kernels it
+// runs at low occupancy next to float-heavy code and diverges with every lane's bounce depth.
+// Here one THREAD evaluates ONE dimension of one path: 32 registers, full occupancy, lanes of a
+// warp work on neighbouring dimensions of the same few paths, nothing else in the kernel.
+// k_shade then reads eight floats per path instead of running the sampler.
+__global__ void __launch_bounds__(256) k_sample(DScene sc, WfBuffers b) {
+    // prefix sums of (entries x roles) over the six sampled queues
+    uint32_t start[SQ_COUNT + 1];
+    uint32_t roles[SQ_COUNT], nrole[SQ_COUNT];
+    start[0] = 0;
+#pragma unroll
+    for (int q = 0; q < SQ_COUNT; q++) {
+        roles[q] = queue_roles(q, sc.n_lights);
+        nrole[q] = __popc(roles[q]);
+        start[q + 1] = start[q] + b.counters[C_SHADE0 + q] * nrole[q];
+    }
+    const uint32_t total = start[SQ_COUNT];
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+        int q = 0;
+#pragma unroll
+        for (int k = 1; k < SQ_COUNT; k++) q += (t >= start[k]) ? 1 : 0;
+        const uint32_t local = t - start[q];
+        const uint32_t entry = local / nrole[q], r = local % nrole[q];
+        // r-th set bit of the role mask
+        uint32_t m = roles[q];
+        for (uint32_t k = 0; k < r; k++) m &= m - 1;
+        const int role = __ffs(m) - 1;
+        const uint32_t slot = b.q_shade[q][entry];
+        const uint4 misc = b.misc[slot];
+        const int fam = q % SQ_FAMILIES;
+        bool nee = fam == SQ_DIFFUSE;
+        if (fam == SQ_CONDUCTOR) {
+            const uint32_t geom = __float_as_uint(b.hit_b[slot].w);
+            const qz_material mat = sc.materials[sc.geoms[geom].material];
+            nee = !(mat.alpha_x < 1e-3f && mat.alpha_y < 1e-3f);
+        }
+        uint32_t dims[R_COUNT];
+        bounce_dims(misc.z & 0xffffu, nee, sc.n_lights != 0, dims);
+        Sampler smp;
+        smp.index = misc.y; smp.dim = 0;
+        b.samples[(size_t)slot * R_COUNT + role] = sample_dimension(sc.sampler_table, smp, dims[role]);
+    }
+}
+
 // One bounce for every path of one (family, first-hit?) queue.
 template <int KH, int FIRST>
 __global__ void __launch_bounds__(128, (KH == KH_DIFFUSE || KH == KH_DIELECTRIC) ? QZ_SHADE_MIN_BLOCKS_LIGHT : QZ_SHADE_MIN_BLOCKS_HEAVY)
@@ -357,7 +419,19 @@ k_shade(DScene sc, WfBuffers b, int queue_id, int next_sel, uint32_t max_bounces
         aov.albedo = spec4(0.0f);
         const bool first = FIRST < 0 ? ps.depth == 0 : FIRST != 0;
         ShadowRequest sh;
-        const bool alive = shade_bounce<KH, FIRST>(sc, ps, aov, hit, max_bounces, sh);
+        bool alive;
+        if (KH == KH_ANY) {
+            SamplesOnTheFly src;
+            src.tab = sc.sampler_table; src.index = ps.smp.index;
+            alive = shade_bounce<KH, FIRST>(sc, ps, aov, hit, max_bounces, sh, src);
+        } else {
+            const float4* sv = reinterpret_cast<const float4*>(b.samples + (size_t)slot * R_COUNT);
+            const float4 s0 = sv[0], s1 = sv[1];
+            SamplesPrecomputed src;
+            src.v[0] = s0.x; src.v[1] = s0.y; src.v[2] = s0.z; src.v[3] = s0.w;
+            src.v[4] = s1.x; src.v[5] = s1.y; src.v[6] = s1.z; src.v[7] = s1.w;
+            alive = shade_bounce<KH, FIRST>(sc, ps, aov, hit, max_bounces, sh, src);
+        }
         if (first) {
             // depth is still 0 after an emitter pass-through, so these may be written more than
             // once per path; the last write (the first real surface) wins, as in the reference

@@ -45,6 +45,8 @@ class QzStats(ctypes.Structure):
         ("ms_other", ctypes.c_float),
         ("bvh_nodes", ctypes.c_uint32),
         ("bvh_bytes", ctypes.c_uint32),
+        ("ms_sample", ctypes.c_float),
+        ("reserved", ctypes.c_uint32),
     ]
 
     def as_dict(self) -> dict:
