@@ -212,7 +212,7 @@ struct DevBuf {
 // calls of the same or a smaller size (cudaMalloc/cudaFree of gigabytes per call would otherwise
 // dominate the end-to-end time of short renders).
 struct WorkMem {
-    DevBuf f4bufs[14], qbufs[12], samples, counters, statsb, res_a, res_b, res_c, rowsb, sensor, acc;
+    DevBuf f4bufs[14], qbufs[10], tags[3], samples, counters, statsb, res_a, res_b, res_c, rowsb, sensor, acc;
     uint32_t pool = 0;
     uint64_t cells = 0, acc_pix = 0, rows = 0;
     uint32_t* h_counters = nullptr;  // pinned
@@ -344,12 +344,13 @@ static int render_impl(qz_scene s, const qz_camera* camera, uint32_t n_samples, 
     // ---- working memory (cached in the scene handle)
     WorkMem& wm = s->work;
     DevBuf(&f4bufs)[14] = wm.f4bufs;
-    DevBuf(&qbufs)[12] = wm.qbufs;
+    DevBuf(&qbufs)[10] = wm.qbufs;
     DevBuf &counters = wm.counters, &statsb = wm.statsb, &res_a = wm.res_a, &res_b = wm.res_b, &res_c = wm.res_c,
            &rowsb = wm.rowsb, &sensor = wm.sensor, &acc = wm.acc;
     for (auto& buf : f4bufs) QZ_CUDA(buf.reserve((size_t)pool * 16));
     for (auto& buf : qbufs) QZ_CUDA(buf.reserve((size_t)pool * 4));
     QZ_CUDA(wm.samples.reserve((size_t)pool * R_COUNT * 4));
+    for (auto& buf : wm.tags) QZ_CUDA(buf.reserve((size_t)pool + 16));
     QZ_CUDA(counters.reserve(C_WORDS * 4));
     QZ_CUDA(statsb.reserve(S_WORDS * 8));
     QZ_CUDA(res_a.reserve(cells * 16));
@@ -372,9 +373,9 @@ static int render_impl(qz_scene s, const qz_camera* camera, uint32_t n_samples, 
     b.aov_n = f4bufs[9].as<float4>(); b.aov_a = f4bufs[10].as<float4>();
     b.sh_o = f4bufs[11].as<float4>(); b.sh_d = f4bufs[12].as<float4>(); b.sh_c = f4bufs[13].as<float4>();
     b.samples = wm.samples.as<float>();
-    b.q_trace[0] = qbufs[0].as<uint32_t>(); b.q_trace[1] = qbufs[1].as<uint32_t>();
-    for (int k = 0; k < SQ_COUNT; k++) b.q_shade[k] = qbufs[2 + k].as<uint32_t>();
-    b.q_shadow = qbufs[10].as<uint32_t>(); b.q_done = qbufs[11].as<uint32_t>();
+    b.stage = wm.tags[0].as<uint8_t>(); b.fam = wm.tags[1].as<uint8_t>(); b.post = wm.tags[2].as<uint8_t>();
+    for (int k = 0; k < SQ_COUNT; k++) b.q_shade[k] = qbufs[k].as<uint32_t>();
+    b.q_shadow = qbufs[8].as<uint32_t>(); b.q_done = qbufs[9].as<uint32_t>();
     b.counters = counters.as<uint32_t>();
     b.stats = statsb.as<unsigned long long>();
     b.res_a = res_a.as<float4>(); b.res_b = res_b.as<float4>(); b.res_c = res_c.as<float>();
@@ -449,38 +450,42 @@ static int render_impl(qz_scene s, const qz_camera* camera, uint32_t n_samples, 
 
         const uint32_t first = std::min<uint32_t>(pool, pp.total);
         uint32_t init[C_WORDS] = {0};
-        init[C_TRACE0] = first;
         init[C_NEXT_PATH] = first;
         QZ_CUDA(cudaMemcpyAsync(b.counters, init, sizeof(init), cudaMemcpyHostToDevice, stream));
         k_generate<<<shade_blocks, 256, 0, stream>>>(sc, cam, b, pp, first);
         st.kernel_launches++;
         QZ_CUDA(cudaGetLastError());
 
-        int cur = 0;
         uint64_t it = 0;
+        const int bin_blocks = (int)std::min<uint32_t>((pool + 2047u) / 2048u, (uint32_t)n_sm * 8u);
         for (;;) {
-            const int nxt = cur ^ 1;
             QZ_CUDA(timed(st.ms_closest, [&] {
-                if (flat) k_closest_flat<<<shade_blocks, 256, 0, stream>>>(sc, b, cur, flags);
-                else if (count_trav) k_closest_hit<true><<<trav_blocks, 128, 0, stream>>>(sc, b, cur, flags);
-                else k_closest_hit<false><<<trav_blocks, 128, 0, stream>>>(sc, b, cur, flags);
+                if (flat) k_closest_flat<<<shade_blocks, 256, 0, stream>>>(sc, b, flags);
+                else if (count_trav) k_closest_hit<true><<<trav_blocks, 128, 0, stream>>>(sc, b, flags);
+                else k_closest_hit<false><<<trav_blocks, 128, 0, stream>>>(sc, b, flags);
+            }));
+            QZ_CUDA(timed(st.ms_other, [&] {
+                k_bin<SQ_COUNT, true><<<bin_blocks, 256, 0, stream>>>(b.fam, nullptr, pool, b.counters + C_SHADE0, b, 0);
             }));
             if (!(flags & QZ_FLAG_UNSORTED_SHADING)) {
                 QZ_CUDA(timed(st.ms_sample, [&] { k_sample<<<shade_blocks * 2, 256, 0, stream>>>(sc, b); }));
             }
             QZ_CUDA(timed(st.ms_shade, [&] {
                 if (flags & QZ_FLAG_UNSORTED_SHADING) {
-                    k_shade<KH_ANY, -1><<<shade_blocks, 128, 0, stream>>>(sc, b, SQ_MISC, nxt, max_bounces);
+                    k_shade<KH_ANY, -1><<<shade_blocks, 128, 0, stream>>>(sc, b, SQ_MISC, max_bounces);
                 } else {
-                    k_shade<KH_ANY, 1><<<shade_blocks, 128, 0, stream>>>(sc, b, SQ_FAMILIES + SQ_MISC, nxt, max_bounces);
-                    k_shade<KH_DIFFUSE, 1><<<shade_blocks, 128, 0, stream>>>(sc, b, SQ_FAMILIES + SQ_DIFFUSE, nxt, max_bounces);
-                    k_shade<KH_CONDUCTOR, 1><<<shade_blocks, 128, 0, stream>>>(sc, b, SQ_FAMILIES + SQ_CONDUCTOR, nxt, max_bounces);
-                    k_shade<KH_DIELECTRIC, 1><<<shade_blocks, 128, 0, stream>>>(sc, b, SQ_FAMILIES + SQ_DIELECTRIC, nxt, max_bounces);
-                    k_shade<KH_ANY, 0><<<shade_blocks, 128, 0, stream>>>(sc, b, SQ_MISC, nxt, max_bounces);
-                    k_shade<KH_DIFFUSE, 0><<<shade_blocks, 128, 0, stream>>>(sc, b, SQ_DIFFUSE, nxt, max_bounces);
-                    k_shade<KH_CONDUCTOR, 0><<<shade_blocks, 128, 0, stream>>>(sc, b, SQ_CONDUCTOR, nxt, max_bounces);
-                    k_shade<KH_DIELECTRIC, 0><<<shade_blocks, 128, 0, stream>>>(sc, b, SQ_DIELECTRIC, nxt, max_bounces);
+                    k_shade<KH_ANY, 1><<<shade_blocks, 128, 0, stream>>>(sc, b, SQ_FAMILIES + SQ_MISC, max_bounces);
+                    k_shade<KH_DIFFUSE, 1><<<shade_blocks, 128, 0, stream>>>(sc, b, SQ_FAMILIES + SQ_DIFFUSE, max_bounces);
+                    k_shade<KH_CONDUCTOR, 1><<<shade_blocks, 128, 0, stream>>>(sc, b, SQ_FAMILIES + SQ_CONDUCTOR, max_bounces);
+                    k_shade<KH_DIELECTRIC, 1><<<shade_blocks, 128, 0, stream>>>(sc, b, SQ_FAMILIES + SQ_DIELECTRIC, max_bounces);
+                    k_shade<KH_ANY, 0><<<shade_blocks, 128, 0, stream>>>(sc, b, SQ_MISC, max_bounces);
+                    k_shade<KH_DIFFUSE, 0><<<shade_blocks, 128, 0, stream>>>(sc, b, SQ_DIFFUSE, max_bounces);
+                    k_shade<KH_CONDUCTOR, 0><<<shade_blocks, 128, 0, stream>>>(sc, b, SQ_CONDUCTOR, max_bounces);
+                    k_shade<KH_DIELECTRIC, 0><<<shade_blocks, 128, 0, stream>>>(sc, b, SQ_DIELECTRIC, max_bounces);
                 }
+            }));
+            QZ_CUDA(timed(st.ms_other, [&] {
+                k_bin<2, false><<<bin_blocks, 256, 0, stream>>>(b.post, b.fam, pool, b.counters + C_SHADOW, b, 1);
             }));
             QZ_CUDA(timed(st.ms_shadow, [&] {
                 if (flat) k_shadow_flat<<<shade_blocks, 256, 0, stream>>>(sc, b);
@@ -488,18 +493,17 @@ static int render_impl(qz_scene s, const qz_camera* camera, uint32_t n_samples, 
                 else k_shadow<false><<<trav_blocks, 128, 0, stream>>>(sc, b);
             }));
             QZ_CUDA(timed(st.ms_other, [&] {
-                k_finish<<<shade_blocks, 256, 0, stream>>>(sc, cam, b, pp, nxt);
-                k_next_iteration<<<1, 32, 0, stream>>>(b, cur);
+                k_finish<<<shade_blocks, 256, 0, stream>>>(sc, cam, b, pp);
+                k_next_iteration<<<1, 32, 0, stream>>>(b);
             }));
-            st.kernel_launches += (flags & QZ_FLAG_UNSORTED_SHADING) ? 5 : 13;
+            st.kernel_launches += (flags & QZ_FLAG_UNSORTED_SHADING) ? 7 : 15;
             st.iterations++;
             it++;
-            cur = nxt;
             // the active count is read back every 4th iteration (every iteration would serialise host and device)
             if ((it & 3u) == 0) {
                 QZ_CUDA(cudaMemcpyAsync(h_counters, b.counters, C_WORDS * 4, cudaMemcpyDeviceToHost, stream));
                 QZ_CUDA(cudaStreamSynchronize(stream));
-                if (h_counters[C_TRACE0 + cur] == 0) break;
+                if (h_counters[C_ACTIVE] == 0) break;
             }
             if (it > 1000000ull) { rc = fail(QZ_ERR_CUDA, "wavefront did not terminate"); break; }
         }

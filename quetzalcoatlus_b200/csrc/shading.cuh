@@ -272,13 +272,17 @@ QZ_HD void sample_lights(const DScene& sc, const SurfacePoint& sp, const Bsdf& f
 // FIRST: 1 = the path is known to be at depth 0, 0 = known to be deeper, -1 = decide at run time.
 // The wavefront sorts first hits into their own queues: only they pay for the 16-sample albedo
 // estimate, and the kernels for deeper bounces do not even contain that code.
+// Radiance picked up AT the hit (emitter or background) is returned in `gain` (has_gain) rather
+// than added to ps.L: a bounce adds at most one such term, and the wavefront kernels only touch
+// the radiance buffer when there is one.  ps.L is neither read nor written here.
 template <int KH, int FIRST, class SRC>
 QZ_HD bool shade_bounce(const DScene& sc, PathState& ps, PathAov& aov, const Hit& hit, uint32_t max_bounces,
-                        ShadowRequest& shadow, const SRC& src) {
+                        ShadowRequest& shadow, const SRC& src, Spec4& gain, bool& has_gain) {
     const bool first = FIRST < 0 ? ps.depth == 0 : FIRST != 0;
     ps.flags &= ~QZ_FLAG_HAS_SHADOW;
+    has_gain = false;
     if (hit.prim == QZ_NO_HIT) {
-        if (sc.bg_spectrum >= 0) ps.L = ps.L + ps.weight * from_spectrum(sc, sc.bg_spectrum, ps.lambda) * sc.bg_scale;
+        if (sc.bg_spectrum >= 0) { gain = ps.weight * from_spectrum(sc, sc.bg_spectrum, ps.lambda) * sc.bg_scale; has_gain = true; }
         return false;
     }
     SurfacePoint sp = make_surface_point(sc, ps.ray, hit);
@@ -288,13 +292,14 @@ QZ_HD bool shade_bounce(const DScene& sc, PathState& ps, PathAov& aov, const Hit
         const qz_light l = sc.lights[sp.light];
         Spec4 emitted = light_emission(sc, l, sp.normal, -ps.ray.d, ps.lambda);
         if (!is_zero(emitted)) {
+            has_gain = true;
             if (first || (ps.flags & QZ_FLAG_SPECULAR_BOUNCE)) {
-                ps.L = ps.L + ps.weight * emitted;
+                gain = ps.weight * emitted;
             } else {
                 // light_sample_pmf * light->pdf: uniform light pick, area-measure pdf (scene.cpp:132-134, light.cpp:44-46)
                 float light_proba = (1.0f / (float)sc.n_lights) * l.inv_area;
                 float light_weight = power_heuristic(ps.p_b, light_proba);
-                ps.L = ps.L + emitted * (ps.weight * light_weight);
+                gain = emitted * (ps.weight * light_weight);
             }
         }
     }
@@ -398,7 +403,10 @@ QZ_HD void run_path(const DScene& sc, const DCamera& cam, const SamplerParams& s
         ShadowRequest sh;
         SamplesOnTheFly src;
         src.tab = sc.sampler_table; src.index = ps.smp.index;
-        bool alive = shade_bounce<KH_ANY, -1>(sc, ps, aov, hit, max_bounces, sh, src);
+        Spec4 gain;
+        bool has_gain;
+        bool alive = shade_bounce<KH_ANY, -1>(sc, ps, aov, hit, max_bounces, sh, src, gain, has_gain);
+        if (has_gain) ps.L = ps.L + gain;
         if (ps.flags & QZ_FLAG_HAS_SHADOW) {
             Ray sr;
             sr.o = sh.o; sr.d = sh.d;

@@ -3,7 +3,10 @@
 //
 //   k_generate        camera ray + wavelengths for new pixel-samples (render.cpp:268-273)
 //   k_closest_hit     persistent, warp-scheduled BVH traversal (scene.cpp:61-117 / rtcIntersect1);
-//                     classifies each hit by material family into one queue per family
+//                     tags each hit with its material family (k_closest_flat: BVH-less variant for
+//                     scenes of <= 96 primitives)
+//   k_bin             ordered compaction of the tags into one queue per family x {first hit, later}
+//   k_sample          this bounce's Owen-scrambled Halton draws, one thread per dimension
 //   k_shade<family>   emission + MIS, BSDF construction, depth-0 albedo, light sampling,
 //                     BSDF sampling, throughput update and Russian roulette for ONE family
 //                     (diffuse / conductor / dielectric); a fourth "misc" kernel takes misses,
@@ -15,7 +18,13 @@
 //   k_film            ordered per-pixel sum over the sample index (render.cpp:264-294)
 //
 // Path state lives in structure-of-arrays buffers of 16-byte elements indexed by slot; the
-// queues carry 4-byte slot indices.  Russian roulette stays fused at the end of k_shade: it
+// queues carry 4-byte slot indices.  QUEUES ARE BUILT IN SLOT ORDER: the stages do not append to
+// queues with atomics (which scatters neighbouring slots across a queue and turns every 16-byte
+// state access into its own 64-byte DRAM burst); they write a one-byte tag per slot, and k_bin
+// -- an ordered compaction, one block per 2048 consecutive slots, one atomic per block and queue
+// -- turns the tags into queues whose entries ascend within each 2048-slot chunk.  Consecutive
+// lanes of the shading kernels then touch neighbouring slots, and the closest-hit stage simply
+// walks the slots densely.  Russian roulette stays fused at the end of k_shade: it
 // needs the freshly updated throughput and the next sampler dimension, so a separate kernel
 // would only re-read what is in registers.
 //
@@ -37,15 +46,19 @@ namespace cg = cooperative_groups;
 // shade queues: material family x {later bounce, first hit}
 enum ShadeQueue { SQ_MISC = 0, SQ_DIFFUSE = 1, SQ_CONDUCTOR = 2, SQ_DIELECTRIC = 3, SQ_FAMILIES = 4, SQ_COUNT = 8 };
 
-// trace-queue entries carry the slot in the low 31 bits and "this path is at depth 0" in bit 31
-#define QZ_ENTRY_FIRST 0x80000000u
+// per-slot stage tag (what the next closest-hit stage does with the slot)
+enum StageTag : uint8_t { ST_EMPTY = 0, ST_TRACE = 1, ST_TRACE_FIRST = 2 };
+#define QZ_FAM_NONE 0xffu   /* family tag of a slot that was not traced this iteration */
+// post-shade tag bits
+#define QZ_POST_SHADOW 1u
+#define QZ_POST_DONE 2u
 #define QZ_FLAT_MAX_PRIMS 96  /* scenes this small are intersected without a BVH (k_closest_flat) */
 
 // counter block layout (uint32 words)
 enum Counter {
-    C_TRACE0 = 0, C_TRACE1 = 1,           // sizes of the double-buffered trace queue
+    C_ACTIVE = 0,                         // paths shaded in the last completed iteration (termination test)
     C_SHADE0 = 2,                         // .. C_SHADE0 + SQ_COUNT - 1
-    C_SHADOW = 10, C_DONE = 11,
+    C_SHADOW = 10, C_DONE = 11,           // (adjacent: k_bin<2, true> fills both)
     C_CURSOR_TRACE = 12, C_CURSOR_SHADOW = 13,
     C_NEXT_PATH = 14,                     // next path id of the pass to hand out
     C_WORDS = 16
@@ -61,9 +74,9 @@ struct WfBuffers {
     float4 *aov_n, *aov_a;
     float4 *sh_o, *sh_d, *sh_c;
     float* samples;             // R_COUNT floats per slot: this bounce's draws, written by k_sample
-    uint32_t* q_trace[2];
+    uint8_t *stage, *fam, *post;  // per-slot tags (StageTag, family queue id or QZ_FAM_NONE, QZ_POST_* bits)
     uint32_t* q_shade[SQ_COUNT];
-    uint32_t *q_shadow, *q_done;
+    uint32_t *q_shadow, *q_done;  // (adjacent in memory order is not required)
     uint32_t* counters;
     unsigned long long* stats;
     float4 *res_a, *res_b;      // per pixel-sample: (color rgb, normal.x), (albedo rgb, normal.y)
@@ -142,9 +155,10 @@ __device__ __forceinline__ void init_slot(const DScene& sc, const DCamera& cam, 
 
 // ------------------------------------------------------------------ kernels
 __global__ void __launch_bounds__(256) k_generate(DScene sc, DCamera cam, WfBuffers b, PassParams pp, uint32_t n) {
+    for (uint32_t i = n + blockIdx.x * blockDim.x + threadIdx.x; i < b.pool; i += gridDim.x * blockDim.x) b.stage[i] = ST_EMPTY;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         init_slot(sc, cam, b, pp, i, i);
-        b.q_trace[0][i] = i | QZ_ENTRY_FIRST;
+        b.stage[i] = ST_TRACE_FIRST;
     }
 }
 
@@ -160,14 +174,95 @@ __device__ __forceinline__ int classify_hit(const DScene& sc, const Hit& hit, bo
     return SQ_MISC;  // MixedMaterial: the family depends on the bounce's material sample
 }
 
-// closest-hit epilogue shared by the BVH and the flat kernel: write the hit record, sort the path
-__device__ __forceinline__ void finish_closest(const DScene& sc, const WfBuffers& b, uint32_t entry, const Hit& h, uint32_t flags) {
-    const uint32_t slot = entry & ~QZ_ENTRY_FIRST;
+// closest-hit epilogue shared by the BVH and the flat kernel: write the hit record and the tag
+// of the shade queue the path belongs to (k_bin builds the queues from the tags)
+__device__ __forceinline__ void finish_closest(const DScene& sc, const WfBuffers& b, uint32_t slot, bool first, const Hit& h, uint32_t flags) {
     b.hit_a[slot] = f4(h.t, h.u, h.v, __uint_as_float(h.prim_id));
     b.hit_b[slot] = f4(h.ng.x, h.ng.y, h.ng.z, __uint_as_float(h.geom_id));
-    const int fam = classify_hit(sc, h, (flags & QZ_FLAG_UNSORTED_SHADING) != 0);
-    const int q = fam + ((entry & QZ_ENTRY_FIRST) && !(flags & QZ_FLAG_UNSORTED_SHADING) ? SQ_FAMILIES : 0);
-    queue_push(&b.counters[C_SHADE0 + q], b.q_shade[q], slot);
+    const bool unsorted = (flags & QZ_FLAG_UNSORTED_SHADING) != 0;
+    const int fam = classify_hit(sc, h, unsorted);
+    b.fam[slot] = (uint8_t)(fam + (first && !unsorted ? SQ_FAMILIES : 0));
+}
+
+// Ordered compaction of per-slot tags into queues.  EXCLUSIVE: tag == q selects queue q (shade
+// families); otherwise bit q of the tag selects queue q (shadow / done: a slot can be in both).
+// A block owns 2048 consecutive slots, each thread 8 consecutive ones, so a queue's entries
+// ascend within every block's share; one atomicAdd per block and queue reserves the share.
+template <int NQ, bool EXCLUSIVE>
+__global__ void __launch_bounds__(256) k_bin(const uint8_t* __restrict__ tags, const uint8_t* __restrict__ traced,
+                                             uint32_t n_slots, uint32_t* counters, WfBuffers b, int which) {
+    __shared__ uint32_t s_warp[8][NQ];
+    __shared__ uint32_t s_base[NQ];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint32_t tile = blockIdx.x * 2048u; tile < n_slots; tile += gridDim.x * 2048u) {
+        const uint32_t first_slot = tile + threadIdx.x * 8u;
+        // this thread's 8 tags; a slot takes part only if it exists and (when `traced` is given) was
+        // traced this iteration
+        uint32_t tg[8];
+        bool ok[8];
+        if (first_slot + 8u <= n_slots) {
+            const uint2 raw = *reinterpret_cast<const uint2*>(tags + first_slot);
+            uint2 tr = make_uint2(0u, 0u);
+            if (traced) tr = *reinterpret_cast<const uint2*>(traced + first_slot);
+#pragma unroll
+            for (uint32_t k = 0; k < 8; k++) {
+                tg[k] = ((k < 4 ? raw.x : raw.y) >> (8 * (k & 3))) & 0xffu;
+                ok[k] = (((k < 4 ? tr.x : tr.y) >> (8 * (k & 3))) & 0xffu) != QZ_FAM_NONE;
+            }
+        } else {
+#pragma unroll
+            for (uint32_t k = 0; k < 8; k++) {
+                const bool in_range = first_slot + k < n_slots;
+                tg[k] = in_range ? tags[first_slot + k] : QZ_FAM_NONE;
+                ok[k] = in_range && (!traced || traced[first_slot + k] != QZ_FAM_NONE);
+            }
+        }
+        // membership masks (bit k = this thread's k-th slot) and per-thread counts
+        uint32_t member[NQ], cnt[NQ];
+#pragma unroll
+        for (int q = 0; q < NQ; q++) {
+            uint32_t m = 0;
+#pragma unroll
+            for (uint32_t k = 0; k < 8; k++) {
+                const bool in = ok[k] && (EXCLUSIVE ? tg[k] == (uint32_t)q : ((tg[k] >> q) & 1u) != 0u);
+                m |= (in ? 1u : 0u) << k;
+            }
+            member[q] = m;
+            cnt[q] = __popc(m);
+        }
+        // exclusive scan of the counts over the block, per queue
+        uint32_t excl[NQ];
+#pragma unroll
+        for (int q = 0; q < NQ; q++) {
+            uint32_t x = cnt[q];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+                if (lane >= d) x += y;
+            }
+            excl[q] = x - cnt[q];
+            if (lane == 31) s_warp[warp][q] = x;
+        }
+        __syncthreads();
+        if (threadIdx.x < NQ) {
+            uint32_t total = 0;
+            for (int w = 0; w < 8; w++) { const uint32_t c = s_warp[w][threadIdx.x]; s_warp[w][threadIdx.x] = total; total += c; }
+            s_base[threadIdx.x] = total ? atomicAdd(&counters[threadIdx.x], total) : 0u;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < NQ; q++) {
+            uint32_t* queue = which == 0 ? b.q_shade[q] : (q == 0 ? b.q_shadow : b.q_done);
+            uint32_t pos = s_base[q] + s_warp[warp][q] + excl[q];
+            uint32_t m = member[q];
+            while (m) {
+                const int k = __ffs(m) - 1;
+                m &= m - 1;
+                queue[pos++] = first_slot + (uint32_t)k;
+            }
+        }
+        __syncthreads();
+    }
 }
 
 #ifndef QZ_SHADE_MIN_BLOCKS_LIGHT
@@ -184,14 +279,14 @@ __device__ __forceinline__ void finish_closest(const DScene& sc, const WfBuffers
 // ray has finished are refilled from the queue cursor as soon as QZ_REFILL_MIN of them are
 // idle (warp vote), so a warp keeps working at high lane occupancy on incoherent rays.
 template <bool COUNT>
-__global__ void __launch_bounds__(128) k_closest_hit(DScene sc, WfBuffers b, int qsel, uint32_t flags) {
-    const uint32_t count = b.counters[C_TRACE0 + qsel];
-    const uint32_t* queue = b.q_trace[qsel];
+__global__ void __launch_bounds__(128) k_closest_hit(DScene sc, WfBuffers b, uint32_t flags) {
+    const uint32_t count = b.pool;  // the slots are walked densely; the stage tag says which are live
     const int lane = threadIdx.x & 31;
     const unsigned full = 0xffffffffu;
     Trav tv;
     tv.done = true;
     bool active = false;
+    bool first = false;
     bool exhausted = false;
     uint32_t slot = 0;
     TraversalCounters cnt;
@@ -206,23 +301,29 @@ __global__ void __launch_bounds__(128) k_closest_hit(DScene sc, WfBuffers b, int
             if (!active) {
                 const uint32_t idx = base + __popc(idle & ((1u << lane) - 1u));
                 if (idx < count) {
-                    slot = queue[idx];  // entry: slot | first-hit flag
-                    const float4 o = b.ray_o[slot & ~QZ_ENTRY_FIRST], d = b.ray_d[slot & ~QZ_ENTRY_FIRST];
-                    Ray r;
-                    r.o = v3(o.x, o.y, o.z);
-                    r.d = v3(d.x, d.y, d.z);
-                    trav_init(tv, r, INFINITY);
-                    active = true;
+                    const uint8_t st = b.stage[idx];
+                    if (st == ST_EMPTY) {
+                        b.fam[idx] = QZ_FAM_NONE;
+                    } else {
+                        slot = idx;
+                        first = st == ST_TRACE_FIRST;
+                        const float4 o = b.ray_o[slot], d = b.ray_d[slot];
+                        Ray r;
+                        r.o = v3(o.x, o.y, o.z);
+                        r.d = v3(d.x, d.y, d.z);
+                        trav_init(tv, r, INFINITY);
+                        active = true;
+                    }
                 }
             }
             if (base + __popc(idle) >= count) exhausted = true;
         }
-        if (!__any_sync(full, active)) break;
+        if (!__any_sync(full, active)) { if (exhausted) break; else continue; }
 #pragma unroll 1
         for (int k = 0; k < QZ_STEPS_PER_ROUND; k++)
             if (active && !tv.done) trav_step<false, COUNT>(sc, tv, &cnt);
         if (active && tv.done) {
-            finish_closest(sc, b, slot, tv.best, flags);
+            finish_closest(sc, b, slot, first, tv.best, flags);
             active = false;
         }
     }
@@ -237,16 +338,14 @@ __global__ void __launch_bounds__(128) k_closest_hit(DScene sc, WfBuffers b, int
 // same list in lockstep -- no stack, no divergence between lanes, broadcast shared-memory
 // reads.  The result is the brute-force minimum under the (t, key) order, i.e. exactly what the
 // BVH traversal is defined to return.
-__global__ void __launch_bounds__(256) k_closest_flat(DScene sc, WfBuffers b, int qsel, uint32_t flags) {
+__global__ void __launch_bounds__(256) k_closest_flat(DScene sc, WfBuffers b, uint32_t flags) {
     __shared__ F4 s_prims[QZ_FLAT_MAX_PRIMS * 4];
     const uint32_t n_prims = sc.n_prims;
     for (uint32_t i = threadIdx.x; i < n_prims * 4; i += blockDim.x) s_prims[i] = sc.prims[i];
     __syncthreads();
-    const uint32_t count = b.counters[C_TRACE0 + qsel];
-    const uint32_t* queue = b.q_trace[qsel];
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
-        const uint32_t entry = queue[i];
-        const uint32_t slot = entry & ~QZ_ENTRY_FIRST;
+    for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < b.pool; slot += gridDim.x * blockDim.x) {
+        const uint8_t st = b.stage[slot];
+        if (st == ST_EMPTY) { b.fam[slot] = QZ_FAM_NONE; continue; }
         const float4 o = b.ray_o[slot], d = b.ray_d[slot];
         const V3 O = v3(o.x, o.y, o.z), D = v3(d.x, d.y, d.z);
         Hit best;
@@ -255,7 +354,7 @@ __global__ void __launch_bounds__(256) k_closest_flat(DScene sc, WfBuffers b, in
 #pragma unroll 1
         for (uint32_t p = 0; p < n_prims; p++)
             prim_test_rec(sc, s_prims[4 * p], s_prims[4 * p + 1], s_prims[4 * p + 2], s_prims[4 * p + 3], p, O, D, QZ_TNEAR, INFINITY, best);
-        finish_closest(sc, b, entry, best, flags);
+        finish_closest(sc, b, slot, st == ST_TRACE_FIRST, best, flags);
     }
 }
 
@@ -396,17 +495,32 @@ __global__ void __launch_bounds__(256) k_sample(DScene sc, WfBuffers b) {
     }
 }
 
-// One bounce for every path of one (family, first-hit?) queue.
+// One bounce for every path of one (family, first-hit?) queue.  Only what the family can change
+// is loaded and stored: the radiance buffer is touched only when the hit itself adds radiance
+// (emitters and misses live in the run-time-dispatch queue), the wavelength pdf only by the
+// dielectric and run-time-dispatch kernels (dispersion), the AOVs only by first-hit kernels.
 template <int KH, int FIRST>
 __global__ void __launch_bounds__(128, (KH == KH_DIFFUSE || KH == KH_DIELECTRIC) ? QZ_SHADE_MIN_BLOCKS_LIGHT : QZ_SHADE_MIN_BLOCKS_HEAVY)
-k_shade(DScene sc, WfBuffers b, int queue_id, int next_sel, uint32_t max_bounces) {
+k_shade(DScene sc, WfBuffers b, int queue_id, uint32_t max_bounces) {
     const uint32_t count = b.counters[C_SHADE0 + queue_id];
     const uint32_t* queue = b.q_shade[queue_id];
+    constexpr bool kPdf = KH == KH_DIELECTRIC || KH == KH_ANY;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
         const uint32_t slot = queue[i];
         PathState ps;
-        const uint32_t path_id = load_state(b, slot, ps);
-        ps.n_rays++;  // the closest-hit query that produced this hit
+        const float4 o = b.ray_o[slot], d = b.ray_d[slot];
+        ps.ray.o = v3(o.x, o.y, o.z); ps.ior_scale = o.w;
+        ps.ray.d = v3(d.x, d.y, d.z); ps.p_b = d.w;
+        ps.weight = s4(b.weight[slot]);
+        ps.lambda = s4(b.lambda[slot]);
+        ps.pdf = kPdf ? s4(b.lpdf[slot]) : spec4(0.0f);
+        ps.L = spec4(0.0f);
+        const uint4 m = b.misc[slot];
+        ps.smp.index = m.y;
+        ps.smp.dim = m.z & 0xffffu;
+        ps.depth = (m.z >> 16) & 0xffu;
+        ps.flags = m.z >> 24;
+        ps.n_rays = m.w + 1;  // + the closest-hit query that produced this hit
         const float4 ha = b.hit_a[slot], hb = b.hit_b[slot];
         Hit hit;
         hit.t = ha.x; hit.u = ha.y; hit.v = ha.z; hit.prim_id = __float_as_uint(ha.w);
@@ -419,40 +533,49 @@ k_shade(DScene sc, WfBuffers b, int queue_id, int next_sel, uint32_t max_bounces
         aov.albedo = spec4(0.0f);
         const bool first = FIRST < 0 ? ps.depth == 0 : FIRST != 0;
         ShadowRequest sh;
-        bool alive;
+        Spec4 gain;
+        bool has_gain, alive;
         if (KH == KH_ANY) {
             SamplesOnTheFly src;
             src.tab = sc.sampler_table; src.index = ps.smp.index;
-            alive = shade_bounce<KH, FIRST>(sc, ps, aov, hit, max_bounces, sh, src);
+            alive = shade_bounce<KH, FIRST>(sc, ps, aov, hit, max_bounces, sh, src, gain, has_gain);
         } else {
             const float4* sv = reinterpret_cast<const float4*>(b.samples + (size_t)slot * R_COUNT);
             const float4 s0 = sv[0], s1 = sv[1];
             SamplesPrecomputed src;
             src.v[0] = s0.x; src.v[1] = s0.y; src.v[2] = s0.z; src.v[3] = s0.w;
             src.v[4] = s1.x; src.v[5] = s1.y; src.v[6] = s1.z; src.v[7] = s1.w;
-            alive = shade_bounce<KH, FIRST>(sc, ps, aov, hit, max_bounces, sh, src);
+            alive = shade_bounce<KH, FIRST>(sc, ps, aov, hit, max_bounces, sh, src, gain, has_gain);
         }
+        if (has_gain) b.radiance[slot] = f4(s4(b.radiance[slot]) + gain);
         if (first) {
             // depth is still 0 after an emitter pass-through, so these may be written more than
             // once per path; the last write (the first real surface) wins, as in the reference
             if (hit.prim != QZ_NO_HIT) b.aov_n[slot] = f4(aov.normal.x, aov.normal.y, aov.normal.z, 0.0f);
             if (ps.depth != 0 || !alive) b.aov_a[slot] = f4(aov.albedo);
         }
+        uint32_t post = alive ? 0u : QZ_POST_DONE;
         if (ps.flags & QZ_FLAG_HAS_SHADOW) {
             ps.n_rays++;
             b.sh_o[slot] = f4(sh.o.x, sh.o.y, sh.o.z, 0.0f);
             b.sh_d[slot] = f4(sh.d.x, sh.d.y, sh.d.z, 0.0f);
             b.sh_c[slot] = f4(sh.contrib);
-            queue_push(&b.counters[C_SHADOW], b.q_shadow, slot);
+            post |= QZ_POST_SHADOW;
         }
-        store_state(b, slot, ps, path_id);
-        if (alive) queue_push(&b.counters[C_TRACE0 + next_sel], b.q_trace[next_sel], slot | (ps.depth == 0 ? QZ_ENTRY_FIRST : 0u));
-        else queue_push(&b.counters[C_DONE], b.q_done, slot);
+        if (alive) {
+            b.ray_o[slot] = f4(ps.ray.o.x, ps.ray.o.y, ps.ray.o.z, ps.ior_scale);
+            b.ray_d[slot] = f4(ps.ray.d.x, ps.ray.d.y, ps.ray.d.z, ps.p_b);
+            b.weight[slot] = f4(ps.weight);
+        }
+        if (kPdf) b.lpdf[slot] = f4(ps.pdf);
+        b.misc[slot] = make_uint4(m.x, ps.smp.index, ps.smp.dim | (ps.depth << 16) | (ps.flags << 24), ps.n_rays);
+        b.post[slot] = (uint8_t)post;
+        b.stage[slot] = alive ? (ps.depth == 0 ? ST_TRACE_FIRST : ST_TRACE) : ST_EMPTY;
     }
 }
 
 // Finished paths: sensor conversion into the result cells, then a new path in the same slot.
-__global__ void __launch_bounds__(256) k_finish(DScene sc, DCamera cam, WfBuffers b, PassParams pp, int next_sel) {
+__global__ void __launch_bounds__(256) k_finish(DScene sc, DCamera cam, WfBuffers b, PassParams pp) {
     const uint32_t count = b.counters[C_DONE];
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
         const uint32_t slot = b.q_done[i];
@@ -474,22 +597,22 @@ __global__ void __launch_bounds__(256) k_finish(DScene sc, DCamera cam, WfBuffer
         const uint32_t next_id = base + __popc(peers & ((1u << lane) - 1u));
         if (next_id < pp.total) {
             init_slot(sc, cam, b, pp, slot, next_id);
-            queue_push(&b.counters[C_TRACE0 + next_sel], b.q_trace[next_sel], slot | QZ_ENTRY_FIRST);
+            b.stage[slot] = ST_TRACE_FIRST;
         }
     }
 }
 
 // Between iterations: account the queue sizes, clear the consumed queues and the cursors.
-__global__ void k_next_iteration(WfBuffers b, int cur_sel) {
+__global__ void k_next_iteration(WfBuffers b) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         uint32_t* c = b.counters;
         unsigned long long shade = 0;
         for (int k = 0; k < SQ_COUNT; k++) shade += c[C_SHADE0 + k];
-        b.stats[S_RAYS_CLOSEST] += c[C_TRACE0 + cur_sel];
+        b.stats[S_RAYS_CLOSEST] += shade;  // every traced slot lands in exactly one shade queue
         b.stats[S_RAYS_SHADOW] += c[C_SHADOW];
         b.stats[S_SHADE] += shade;
         b.stats[S_PATHS_DONE] += c[C_DONE];
-        c[C_TRACE0 + cur_sel] = 0;
+        c[C_ACTIVE] = (uint32_t)shade;
         for (int k = 0; k < SQ_COUNT; k++) c[C_SHADE0 + k] = 0;
         c[C_SHADOW] = 0;
         c[C_DONE] = 0;
