@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(256) k_bin(const uint8_t* __restrict__ tags, c
 #define QZ_SHADE_MIN_BLOCKS_LIGHT 5   /* diffuse / dielectric shade kernels: 96 registers */
 #endif
 #ifndef QZ_SHADE_MIN_BLOCKS_HEAVY
-#define QZ_SHADE_MIN_BLOCKS_HEAVY 3   /* conductor / run-time-dispatch shade kernels */
+#define QZ_SHADE_MIN_BLOCKS_HEAVY 4   /* conductor / run-time-dispatch shade kernels */
 #endif
 
 #define QZ_REFILL_MIN 8   /* idle lanes that trigger a refill from the queue */
