@@ -277,32 +277,35 @@ def run_ours(args) -> None:
 
     # ---- roofline of the dominant stage: one instrumented step (stage events + traversal counters), rank 0, untimed
     roofline, extra = None, {}
+    # every rank runs the instrumented steps (they contain the collective); rank 0 reports its own stages
+    inst = step(QZ_FLAG_COUNT_TRAVERSAL)   # traversal counters (BVH kernels)
+    timing = step(QZ_FLAG_STAGE_TIMING)    # per-stage device time of the real kernels
     if rank == 0:
-        inst = step(QZ_FLAG_COUNT_TRAVERSAL) if world == 1 else None   # traversal counters (BVH kernels)
-        timing = step(QZ_FLAG_STAGE_TIMING) if world == 1 else None    # per-stage device time of the real kernels
-        if inst:
-            for k in ("ms_closest", "ms_shadow", "ms_shade", "ms_other", "ms_total", "ms_sample"):
-                inst[k] = timing[k]
-            n_rays = inst["rays_closest"] + inst["rays_shadow"]
-            n_node = inst["node_visits"] / max(n_rays, 1)
-            n_prim = inst["prim_tests"] / max(n_rays, 1)
-            # B_ray = N_node*128 + N_prim*64 + 32 (ray read) + 32 (hit write; 4 for shadow rays)
-            bytes_trav = inst["node_visits"] * 128 + inst["prim_tests"] * 64 + inst["rays_closest"] * 64 + inst["rays_shadow"] * 36
-            bytes_shade = inst["shade_calls"] * 288 + inst["rays_shadow"] * 48
-            stages = {"traversal (k_closest_hit + k_shadow)": (inst["ms_closest"] + inst["ms_shadow"], bytes_trav),
-                      "shading (k_shade<family>)": (inst["ms_shade"], bytes_shade)}
-            dom = max(stages, key=lambda k: stages[k][0])
-            d_ms, d_bytes = stages[dom]
-            peak, how = measured_peaks()
-            achieved = d_bytes / (d_ms * 1e-3) / 1e9 if d_ms > 0 else 0.0
-            roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                        "kernel": dom, "peak_source": how,
-                        "stage_ms": {**{k: v[0] for k, v in stages.items()}, "sampler (k_sample)": inst["ms_sample"],
-                                     "finish + regenerate": inst["ms_other"], "step": inst["ms_total"]},
-                        "note": "path-tracing of small analytic scenes is issue-bound (integer sampler), not HBM-bound; see DESIGN.md"}
-            extra = {"n_node_per_ray": n_node, "n_prim_per_ray": n_prim, "bounces_per_path": inst["shade_calls"] / inst["paths"],
-                     "shadow_ray_fraction": inst["rays_shadow"] / max(n_rays, 1), "bvh_nodes": inst["bvh_nodes"],
-                     "whole_pipeline_algorithmic_gbs": (bytes_trav + bytes_shade) / (inst["ms_total"] * 1e-3) / 1e9}
+        for k in ("ms_closest", "ms_shadow", "ms_shade", "ms_other", "ms_total", "ms_sample"):
+            inst[k] = timing[k]
+        n_rays = inst["rays_closest"] + inst["rays_shadow"]
+        n_node = inst["node_visits"] / max(n_rays, 1)
+        n_prim = inst["prim_tests"] / max(n_rays, 1)
+        # B_ray = N_node*128 + N_prim*64 + 32 (ray read) + 32 (hit write; 4 for shadow rays)
+        bytes_trav = inst["node_visits"] * 128 + inst["prim_tests"] * 64 + inst["rays_closest"] * 64 + inst["rays_shadow"] * 36
+        # per shaded bounce: the path record is read and written once (288 B) and the sampler stage adds 32 B each way
+        bytes_shade = inst["shade_calls"] * 288 + inst["rays_shadow"] * 48
+        bytes_sample = inst["shade_calls"] * 64
+        stages = {"traversal (k_closest_* + k_shadow_*)": (inst["ms_closest"] + inst["ms_shadow"], bytes_trav),
+                  "shading (k_shade<family, first>)": (inst["ms_shade"], bytes_shade),
+                  "sampler (k_sample)": (inst["ms_sample"], bytes_sample)}
+        dom = max(stages, key=lambda k: stages[k][0])
+        d_ms, d_bytes = stages[dom]
+        peak, how = measured_peaks()
+        achieved = d_bytes / (d_ms * 1e-3) / 1e9 if d_ms > 0 else 0.0
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                    "kernel": dom, "peak_source": how,
+                    "stage_ms": {**{k: v[0] for k, v in stages.items()}, "finish + regenerate + bin": inst["ms_other"], "step": inst["ms_total"]},
+                    "note": "algorithmic bytes (SURVEY.md 8.d) over the stage's device time; analytic scenes are SM-issue-bound "
+                            "(integer sampler, IEEE float), so the HBM fraction is low by nature; see DESIGN.md section 6"}
+        extra = {"n_node_per_ray": n_node, "n_prim_per_ray": n_prim, "bounces_per_path": inst["shade_calls"] / max(inst["paths"], 1),
+                 "shadow_ray_fraction": inst["rays_shadow"] / max(n_rays, 1), "bvh_nodes": inst["bvh_nodes"],
+                 "whole_pipeline_algorithmic_gbs": (bytes_trav + bytes_shade + bytes_sample) / (inst["ms_total"] * 1e-3) / 1e9}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
