@@ -176,6 +176,8 @@ typedef struct qz_region {
 #define QZ_FLAG_UNSORTED_SHADING 1u /* one uber shading kernel over the unsorted queue (evidence runs only) */
 #define QZ_FLAG_COUNT_TRAVERSAL 2u  /* count wide-node visits and primitive tests (slower; for B_ray)        */
 #define QZ_FLAG_FORCE_BVH 8u        /* use the BVH traversal kernels even for scenes small enough for the flat kernel */
+#define QZ_FLAG_LANE_TRAVERSAL 16u  /* first-generation one-ray-per-lane BVH kernels (evidence runs only) */
+#define QZ_FLAG_OCTET_TRAVERSAL 32u /* eight-lanes-per-ray BVH kernels (evidence runs only) */
 #define QZ_FLAG_STAGE_TIMING 4u     /* CUDA events around every stage (serialises the pipeline; for profiles) */
 
 typedef struct qz_render_options {
@@ -197,7 +199,7 @@ typedef struct qz_stats {
     float ms_closest, ms_shadow, ms_shade, ms_other; /* per-stage device time (QZ_FLAG_STAGE_TIMING) */
     uint32_t bvh_nodes, bvh_bytes;
     float ms_sample;        /* the sampler stage (k_sample)                                      */
-    uint32_t reserved;
+    uint32_t stack_overflows; /* warps that ran out of traversal stack (render fails if non-zero) */
 } qz_stats;
 
 typedef struct qz_scene_t* qz_scene;

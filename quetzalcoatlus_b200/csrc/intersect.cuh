@@ -112,7 +112,11 @@ QZ_HD void prim_test_rec(const DScene& sc, const F4& a, const F4& b, const F4& c
     } else {
         PrimHit ha, hb;
         bool fa = tri_test(O, D, tnear, tfar, xyz(a), xyz(b), xyz(d), false, ha);
-        bool fb = tri_test(O, D, tnear, tfar, xyz(c), xyz(d), xyz(b), true, hb);
+        // OBJ triangles arrive as quads with the last vertex repeated (obj.cpp:41-115): the second
+        // triangle (c, d, b) then has a zero edge, hence a zero normal and den == 0 -- rejected by
+        // tri_test for every ray, so it is skipped without changing any result
+        const bool degenerate = c.x == d.x && c.y == d.y && c.z == d.z;
+        bool fb = !degenerate && tri_test(O, D, tnear, tfar, xyz(c), xyz(d), xyz(b), true, hb);
         if (fa && (!fb || ha.t <= hb.t)) { h = ha; found = true; }
         else if (fb) { h = hb; found = true; }
         if (found && kind == QZ_PRIM_GRIDCELL) {

@@ -216,10 +216,14 @@ struct WorkMem {
     uint32_t pool = 0;
     uint64_t cells = 0, acc_pix = 0, rows = 0;
     uint32_t* h_counters = nullptr;  // pinned
+    DevBuf film[3];                  // device film planes of the host-buffer entry (qz_render)
+    float* h_film = nullptr;         // pinned staging for pageable caller buffers
+    size_t h_film_bytes = 0;
     std::vector<cudaEvent_t> stage_events;
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_a = nullptr, ev_b = nullptr;
     ~WorkMem() {
         if (h_counters) cudaFreeHost(h_counters);
+        if (h_film) cudaFreeHost(h_film);
         for (cudaEvent_t e : {ev_begin, ev_end, ev_a, ev_b}) if (e) cudaEventDestroy(e);
         for (cudaEvent_t e : stage_events) cudaEventDestroy(e);
     }
@@ -384,6 +388,8 @@ static int render_impl(qz_scene s, const qz_camera* camera, uint32_t n_samples, 
     DCamera cam = make_camera(camera, sensor.as<float>());
     const bool count_trav = (flags & QZ_FLAG_COUNT_TRAVERSAL) != 0;
     const bool stage_timing = (flags & QZ_FLAG_STAGE_TIMING) != 0;
+    const bool lane_trav = (flags & QZ_FLAG_LANE_TRAVERSAL) != 0;  // first-generation per-lane kernels (evidence arm)
+    const bool oct_trav = (flags & QZ_FLAG_OCTET_TRAVERSAL) != 0;  // eight lanes per ray (evidence arm); default: phase-scheduled
     // tiny scenes skip the BVH (k_closest_flat); counting runs and QZ_FLAG_FORCE_BVH keep the traversal kernels
     const bool flat = sc.n_prims <= QZ_FLAT_MAX_PRIMS && sc.n_prims > 0 && !count_trav && !(flags & QZ_FLAG_FORCE_BVH);
 
@@ -461,8 +467,12 @@ static int render_impl(qz_scene s, const qz_camera* camera, uint32_t n_samples, 
         for (;;) {
             QZ_CUDA(timed(st.ms_closest, [&] {
                 if (flat) k_closest_flat<<<shade_blocks, 256, 0, stream>>>(sc, b, flags);
-                else if (count_trav) k_closest_hit<true><<<trav_blocks, 128, 0, stream>>>(sc, b, flags);
-                else k_closest_hit<false><<<trav_blocks, 128, 0, stream>>>(sc, b, flags);
+                else if (lane_trav && count_trav) k_closest_hit<true><<<trav_blocks, 128, 0, stream>>>(sc, b, flags);
+                else if (lane_trav) k_closest_hit<false><<<trav_blocks, 128, 0, stream>>>(sc, b, flags);
+                else if (oct_trav && count_trav) k_trace_oct<false, true><<<trav_blocks, 128, 0, stream>>>(sc, b, flags);
+                else if (oct_trav) k_trace_oct<false, false><<<trav_blocks, 128, 0, stream>>>(sc, b, flags);
+                else if (count_trav) k_trace_lane<false, true><<<trav_blocks, 128, 0, stream>>>(sc, b, flags);
+                else k_trace_lane<false, false><<<trav_blocks, 128, 0, stream>>>(sc, b, flags);
             }));
             QZ_CUDA(timed(st.ms_other, [&] {
                 k_bin<SQ_COUNT, true><<<bin_blocks, 256, 0, stream>>>(b.fam, nullptr, pool, b.counters + C_SHADE0, b, 0);
@@ -489,8 +499,12 @@ static int render_impl(qz_scene s, const qz_camera* camera, uint32_t n_samples, 
             }));
             QZ_CUDA(timed(st.ms_shadow, [&] {
                 if (flat) k_shadow_flat<<<shade_blocks, 256, 0, stream>>>(sc, b);
-                else if (count_trav) k_shadow<true><<<trav_blocks, 128, 0, stream>>>(sc, b);
-                else k_shadow<false><<<trav_blocks, 128, 0, stream>>>(sc, b);
+                else if (lane_trav && count_trav) k_shadow<true><<<trav_blocks, 128, 0, stream>>>(sc, b);
+                else if (lane_trav) k_shadow<false><<<trav_blocks, 128, 0, stream>>>(sc, b);
+                else if (oct_trav && count_trav) k_trace_oct<true, true><<<trav_blocks, 128, 0, stream>>>(sc, b, flags);
+                else if (oct_trav) k_trace_oct<true, false><<<trav_blocks, 128, 0, stream>>>(sc, b, flags);
+                else if (count_trav) k_trace_lane<true, true><<<trav_blocks, 128, 0, stream>>>(sc, b, flags);
+                else k_trace_lane<true, false><<<trav_blocks, 128, 0, stream>>>(sc, b, flags);
             }));
             QZ_CUDA(timed(st.ms_other, [&] {
                 k_finish<<<shade_blocks, 256, 0, stream>>>(sc, cam, b, pp);
@@ -525,6 +539,9 @@ static int render_impl(qz_scene s, const qz_camera* camera, uint32_t n_samples, 
     st.shade_calls = h_stats[S_SHADE];
     st.node_visits = h_stats[S_NODES];
     st.prim_tests = h_stats[S_PRIMS];
+    st.stack_overflows = (uint32_t)std::min<unsigned long long>(h_stats[S_OVERFLOW], 0xffffffffull);
+    if (rc == QZ_OK && st.stack_overflows)
+        rc = fail(QZ_ERR_CUDA, "BVH traversal stack overflow: the tree is deeper than the shared-memory stack (QZ_OCT_STACK)");
     if (rc == QZ_OK && h_stats[S_PATHS_DONE] != st.paths) rc = fail(QZ_ERR_CUDA, "internal error: finished path count does not match");
     if (stats_out) *stats_out = st;
     return rc;
@@ -546,23 +563,51 @@ int qz_render(qz_scene s, const qz_camera* camera, uint32_t n_samples, uint32_t 
     if (!s->store.committed) return fail(QZ_ERR_NOT_COMMITTED, "Scene must be committed before rendering.");
     QZ_CUDA(cudaSetDevice(s->device));
     const size_t n = (size_t)camera->image_width * camera->image_height * 3;
-    DevBuf dc, dn, da;
-    QZ_CUDA(dc.alloc(n * 4));
-    if (normal) QZ_CUDA(dn.alloc(n * 4));
-    if (albedo) QZ_CUDA(da.alloc(n * 4));
+    // device planes and the pinned staging area live with the scene handle: a render() per frame
+    // must not pay cudaMalloc / cudaFree / first-touch of tens of megabytes every call
+    WorkMem& wm = s->work;
+    DevBuf &dc = wm.film[0], &dn = wm.film[1], &da = wm.film[2];
+    QZ_CUDA(dc.reserve(n * 4));
+    if (normal) QZ_CUDA(dn.reserve(n * 4));
+    if (albedo) QZ_CUDA(da.reserve(n * 4));
+    float* host[3] = {color, normal, albedo};
+    DevBuf* dev[3] = {&dc, &dn, &da};
+    // caller buffers that are already page-locked (cudaHostAlloc / cudaHostRegister / torch pinned
+    // memory) are copied to directly; pageable ones go through the pinned staging area
+    bool pinned[3] = {false, false, false};
+    bool need_staging = false;
+    for (int k = 0; k < 3; k++) {
+        if (!host[k]) continue;
+        cudaPointerAttributes attr{};
+        if (cudaPointerGetAttributes(&attr, host[k]) == cudaSuccess && attr.type == cudaMemoryTypeHost) pinned[k] = true;
+        else { cudaGetLastError(); need_staging = true; }
+    }
+    if (need_staging && wm.h_film_bytes < n * 4) {
+        if (wm.h_film) cudaFreeHost(wm.h_film);
+        wm.h_film = nullptr; wm.h_film_bytes = 0;
+        QZ_CUDA(cudaMallocHost(&wm.h_film, n * 4));
+        wm.h_film_bytes = n * 4;
+    }
     const bool sharded = region && region->strip_rows && region->n_shards > 1;
     if (sharded) {
         // rows this call does not own keep the caller's contents
-        QZ_CUDA(cudaMemcpy(dc.p, color, n * 4, cudaMemcpyHostToDevice));
-        if (normal) QZ_CUDA(cudaMemcpy(dn.p, normal, n * 4, cudaMemcpyHostToDevice));
-        if (albedo) QZ_CUDA(cudaMemcpy(da.p, albedo, n * 4, cudaMemcpyHostToDevice));
+        for (int k = 0; k < 3; k++)
+            if (host[k]) QZ_CUDA(cudaMemcpy(dev[k]->p, host[k], n * 4, cudaMemcpyHostToDevice));
     }
     int rc = render_impl(s, camera, n_samples, max_bounces, region, options, dc.as<float>(), normal ? dn.as<float>() : nullptr,
                          albedo ? da.as<float>() : nullptr, nullptr, stats);
     if (rc != QZ_OK) return rc;
-    QZ_CUDA(cudaMemcpy(color, dc.p, n * 4, cudaMemcpyDeviceToHost));
-    if (normal) QZ_CUDA(cudaMemcpy(normal, dn.p, n * 4, cudaMemcpyDeviceToHost));
-    if (albedo) QZ_CUDA(cudaMemcpy(albedo, da.p, n * 4, cudaMemcpyDeviceToHost));
+    for (int k = 0; k < 3; k++) {
+        if (!host[k]) continue;
+        if (pinned[k]) {
+            QZ_CUDA(cudaMemcpyAsync(host[k], dev[k]->p, n * 4, cudaMemcpyDeviceToHost, nullptr));
+        } else {
+            QZ_CUDA(cudaMemcpyAsync(wm.h_film, dev[k]->p, n * 4, cudaMemcpyDeviceToHost, nullptr));
+            QZ_CUDA(cudaStreamSynchronize(nullptr));
+            std::memcpy(host[k], wm.h_film, n * 4);
+        }
+    }
+    QZ_CUDA(cudaStreamSynchronize(nullptr));
     return QZ_OK;
 }
 

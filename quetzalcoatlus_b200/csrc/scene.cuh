@@ -10,6 +10,8 @@ namespace qz {
 
 struct BvhNode;
 
+#define QZ_PW_BUCKETS 472 /* thresholds 360 .. 831 nm */
+
 struct F4 {
     float x, y, z, w;
 };
@@ -23,6 +25,7 @@ struct DScene {
     const qz_geometry* geoms;
     const F4* prims;            // 4 x F4 per primitive
     const float* pool;
+    const uint8_t* pw_accel;    // 1-nm bucket tables of the piecewise-linear spectra (scene_store.cuh)
     const float* normals;       // float3 packed
     const int32_t* nidx;        // int4 per OBJ face
     const uint32_t* grid_dims;

@@ -116,7 +116,33 @@ struct SceneStore {
     bool commit(Exec& ex, const qz_scene_tables& t, const SamplerDim* d_sampler_table, const float* d_rho_tab) {
         release(ex);
         view = DScene();
-        view.spectra = put(ex, t.spectra, t.n_spectra);
+        // Piecewise-linear spectra get a 1-nm bucket table over [360, 831]: bucket b holds
+        // lower_bound(knots, 360 + b), so a lookup starts at the right knot instead of bisecting
+        // (spectra.cuh).  The table is only built where a forward scan from it provably lands on
+        // std::lower_bound's answer: the knots must be partitioned for every integer threshold
+        // (sorted tables are; so are the reference's tables with their "..., 916, 831" tails).
+        std::vector<qz_spectrum> spectra(t.spectra, t.spectra + t.n_spectra);
+        std::vector<uint8_t> accel;
+        for (qz_spectrum& sp : spectra) {
+            if (sp.kind != QZ_SPEC_PIECEWISE) continue;
+            sp.aux = -1;
+            if (sp.count == 0 || sp.count > 255) continue;
+            const float* l = t.pool + sp.offset;
+            uint8_t table[QZ_PW_BUCKETS];
+            bool ok = true;
+            for (uint32_t bkt = 0; bkt < QZ_PW_BUCKETS && ok; bkt++) {
+                const float thr = 360.0f + (float)bkt;
+                uint32_t first = 0;
+                while (first < sp.count && l[first] < thr) first++;
+                for (uint32_t j = first; j < sp.count; j++) if (l[j] < thr) ok = false;
+                table[bkt] = (uint8_t)first;
+            }
+            if (!ok) continue;
+            sp.aux = (int32_t)accel.size();
+            accel.insert(accel.end(), table, table + QZ_PW_BUCKETS);
+        }
+        view.spectra = put(ex, spectra.data(), spectra.size());
+        view.pw_accel = put(ex, accel.data(), accel.size());
         view.textures = put(ex, t.textures, t.n_textures);
         view.materials = put(ex, t.materials, t.n_materials);
         view.mixed_children = put(ex, t.mixed_children, t.n_mixed_children);

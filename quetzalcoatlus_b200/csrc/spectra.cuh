@@ -36,11 +36,18 @@ QZ_HD float eval_spectrum_leaf(const DScene& sc, const qz_spectrum& s, float lam
                 const float* v = l + s.count + 1;
                 if (s.count == 0 || lambda < l[0] || lambda > l[s.count - 1]) return 0.0f;
                 // std::lower_bound: first knot >= lambda
-                uint32_t first = 0, len = s.count;
-                while (len > 0) {
-                    uint32_t half = len >> 1;
-                    if (l[first + half] < lambda) { first += half + 1; len -= half + 1; }
-                    else len = half;
+                uint32_t first = 0;
+                if (s.aux >= 0 && lambda >= 360.0f && lambda < 831.0f) {
+                    // bucket table: lower_bound for floor(lambda), then at most a knot or two forward
+                    first = sc.pw_accel[(uint32_t)s.aux + (uint32_t)(int)(lambda - 360.0f)];
+                    while (l[first] < lambda) first++;
+                } else {
+                    uint32_t len = s.count;
+                    while (len > 0) {
+                        uint32_t half = len >> 1;
+                        if (l[first + half] < lambda) { first += half + 1; len -= half + 1; }
+                        else len = half;
+                    }
                 }
                 // l[count] and v[count] are the zero pads standing in for the reference's
                 // one-past-the-end read

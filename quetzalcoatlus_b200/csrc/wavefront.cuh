@@ -64,7 +64,7 @@ enum Counter {
     C_WORDS = 16
 };
 // 64-bit statistics block
-enum Stat { S_RAYS_CLOSEST = 0, S_RAYS_SHADOW = 1, S_SHADE = 2, S_NODES = 3, S_PRIMS = 4, S_PATHS_DONE = 5, S_WORDS = 8 };
+enum Stat { S_RAYS_CLOSEST = 0, S_RAYS_SHADOW = 1, S_SHADE = 2, S_NODES = 3, S_PRIMS = 4, S_PATHS_DONE = 5, S_OVERFLOW = 6, S_WORDS = 8 };
 
 struct WfBuffers {
     float4 *ray_o, *ray_d;      // o.xyz | ior_scale ; d.xyz | p_b
@@ -272,7 +272,12 @@ __global__ void __launch_bounds__(256) k_bin(const uint8_t* __restrict__ tags, c
 #define QZ_SHADE_MIN_BLOCKS_HEAVY 4   /* conductor / run-time-dispatch shade kernels */
 #endif
 
+#ifndef QZ_REFILL_MIN
 #define QZ_REFILL_MIN 8   /* idle lanes that trigger a refill from the queue */
+#endif
+#ifndef QZ_TRACE_MIN_BLOCKS
+#define QZ_TRACE_MIN_BLOCKS 5
+#endif
 #define QZ_STEPS_PER_ROUND 4
 
 // Persistent closest-hit traversal.  Each warp owns 32 lanes of traversal state; lanes whose
@@ -432,6 +437,453 @@ __global__ void __launch_bounds__(128) k_shadow(DScene sc, WfBuffers b) {
         atomicAdd(&b.stats[S_NODES], (unsigned long long)cnt.nodes);
         atomicAdd(&b.stats[S_PRIMS], (unsigned long long)cnt.prims);
     }
+}
+
+// ------------------------------------------------------------------ phase-scheduled traversal
+// One ray per lane, but the WARP decides what every lane does next.  A lane is in one of four
+// states -- NODE (has a wide node to open), PRIM (has leaf primitives of the last node pending),
+// DONE (result to write), IDLE (no ray) -- and each trip of the persistent loop runs exactly ONE
+// of three instruction streams for all lanes that are in the matching state:
+//   * finish + refill, when >= QZ_REFILL_MIN lanes wait for it (warp vote), or nothing else can run;
+//   * the primitive stream (one primitive per pending lane), when more lanes are in PRIM than in NODE;
+//   * the node stream otherwise: one 128-byte node per lane, all eight child slabs tested
+//     branch-free, hit leaf children recorded as a bit mask over the node's contiguous leaf
+//     block (NOT tested here), hit internal children sorted far-to-near by a register sorting
+//     network and pushed; then the lane pops its next node, culling against its current best.
+// So the long, expensive streams (8 slab tests; Moeller-Trumbore) always run with the majority of the
+// warp's lanes, instead of every lane dragging the other 31 through its own private
+// node / primitive / pop sequence (the first version of this kernel: 6.9 of 32 lanes active per
+// instruction on the 1M-triangle scene, profiles/r01_traversal.md).  Results are unchanged: same
+// slab and primitive arithmetic, closest hit = minimum under (t, key), which does not depend on
+// the visiting order.
+enum LaneState { LS_IDLE = 0, LS_NODE = 1, LS_PRIM = 2, LS_DONE = 3 };
+
+#define QZ_CSWAP_DESC(a, b) { const uint32_t hi_ = a > b ? a : b, lo_ = a > b ? b : a; a = hi_; b = lo_; }
+
+template <bool ANY_HIT, bool COUNT>
+__global__ void __launch_bounds__(128, QZ_TRACE_MIN_BLOCKS) k_trace_lane(DScene sc, WfBuffers b, uint32_t flags) {
+    const uint32_t count = ANY_HIT ? b.counters[C_SHADOW] : b.pool;
+    uint32_t* cursor = &b.counters[ANY_HIT ? C_CURSOR_SHADOW : C_CURSOR_TRACE];
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    int state = LS_IDLE;
+    bool exhausted = false;  // warp-uniform
+    uint32_t slot = 0, cur = 0, leafbits = 0, leaf_base = 0;
+    bool first = false, occl = false;
+    V3 O = v3(0.0f, 0.0f, 0.0f), D = v3(0.0f, 0.0f, 0.0f);
+    float inv[3] = {0.0f, 0.0f, 0.0f};
+    float limit = 0.0f;   // closest hit: best t so far; any hit: the end of the segment
+    Hit best;
+    best.t = INFINITY; best.u = 0.0f; best.v = 0.0f; best.prim = QZ_NO_HIT; best.key = 0xffffffffu;
+    best.ng = v3(0.0f, 0.0f, 0.0f); best.geom_id = QZ_NO_HIT; best.prim_id = 0;
+    uint2 stack[QZ_STACK];
+    int sp = 0;
+    uint32_t cnt_nodes = 0, cnt_prims = 0, overflow = 0;
+
+    // next node for this lane: nearest entry still within reach, or the ray is done
+    auto pop_next = [&]() {
+        for (;;) {
+            if (sp == 0) { state = LS_DONE; return; }
+            sp--;
+            const uint2 e = stack[sp];
+            if (__uint_as_float(e.x & ~7u) <= limit) { cur = e.y; state = LS_NODE; return; }
+        }
+    };
+
+    for (;;) {
+        const unsigned m_node = __ballot_sync(full, state == LS_NODE);
+        const unsigned m_prim = __ballot_sync(full, state == LS_PRIM);
+        const unsigned m_done = __ballot_sync(full, state == LS_DONE);
+        const unsigned m_idle = ~(m_node | m_prim | m_done);
+        const bool busy = (m_node | m_prim) != 0u;
+        const bool want_finish = m_done != 0u && (__popc(m_done) >= QZ_REFILL_MIN || !busy);
+        const bool want_refill = !exhausted && (__popc(m_done | m_idle) >= QZ_REFILL_MIN || !busy);
+        if (want_finish || want_refill) {
+            // ---- finish + refill stream
+            if (state == LS_DONE) {
+                if (ANY_HIT) {
+                    if (!occl) {
+                        const float4 L = b.radiance[slot], c = b.sh_c[slot];
+                        b.radiance[slot] = f4(L.x + c.x, L.y + c.y, L.z + c.z, L.w + c.w);
+                    }
+                } else {
+                    finish_closest(sc, b, slot, first, best, flags);
+                }
+                state = LS_IDLE;
+            }
+            if (!exhausted) {
+                const unsigned idle = m_done | m_idle;
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(cursor, (uint32_t)__popc(idle));
+                base = __shfl_sync(full, base, 0);
+                if (state == LS_IDLE) {
+                    const uint32_t idx = base + __popc(idle & ((1u << lane) - 1u));
+                    if (idx < count) {
+                        float4 ro, rd;
+                        bool live = true;
+                        if (ANY_HIT) {
+                            slot = b.q_shadow[idx];
+                            ro = b.sh_o[slot]; rd = b.sh_d[slot];
+                            limit = 1.0f;
+                        } else {
+                            const uint8_t st = b.stage[idx];
+                            live = st != ST_EMPTY;
+                            if (live) {
+                                slot = idx;
+                                first = st == ST_TRACE_FIRST;
+                                ro = b.ray_o[slot]; rd = b.ray_d[slot];
+                                limit = INFINITY;
+                            } else {
+                                b.fam[idx] = QZ_FAM_NONE;
+                            }
+                        }
+                        if (live) {
+                            O = v3(ro.x, ro.y, ro.z); D = v3(rd.x, rd.y, rd.z);
+                            inv[0] = 1.0f / D.x; inv[1] = 1.0f / D.y; inv[2] = 1.0f / D.z;
+                            best.t = INFINITY; best.u = 0.0f; best.v = 0.0f; best.prim = QZ_NO_HIT; best.key = 0xffffffffu;
+                            best.ng = v3(0.0f, 0.0f, 0.0f); best.geom_id = QZ_NO_HIT; best.prim_id = 0;
+                            occl = false;
+                            cur = 0; sp = 0; leafbits = 0;
+                            state = LS_NODE;
+                        }
+                    }
+                }
+                if (base + __popc(idle) >= count) exhausted = true;
+            }
+            continue;
+        }
+        if (!busy) break;  // nothing in flight, nothing to write, no slots left
+
+        if (__popc(m_prim) > __popc(m_node)) {
+            // ---- primitive stream: one pending primitive per lane
+            if (state == LS_PRIM) {
+                const uint32_t p = leaf_base + (uint32_t)(__ffs(leafbits) - 1);
+                leafbits &= leafbits - 1u;
+                if (COUNT) cnt_prims++;
+                if (ANY_HIT) {
+                    best.t = INFINITY; best.prim = QZ_NO_HIT; best.key = 0xffffffffu;
+                    prim_test(sc, p, O, D, QZ_TNEAR, INFINITY, best);
+                    // a hit beyond the segment does not occlude (scene.cpp:136-143)
+                    if (best.prim != QZ_NO_HIT && best.t <= limit) { occl = true; state = LS_DONE; }
+                } else {
+                    prim_test(sc, p, O, D, QZ_TNEAR, INFINITY, best);
+                    limit = best.t;
+                }
+                if (state == LS_PRIM && leafbits == 0u) pop_next();
+            }
+            continue;
+        }
+
+        // ---- node stream: open one node per lane
+        if (state == LS_NODE) {
+            const uint4* np = reinterpret_cast<const uint4*>(sc.nodes + cur);
+            uint4 w[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) w[i] = __ldg(np + i);
+            if (COUNT) cnt_nodes++;
+            const float org[3] = {__uint_as_float(w[0].x), __uint_as_float(w[0].y), __uint_as_float(w[0].z)};
+            const float scl[3] = {exp_scale(w[0].w & 0xffu), exp_scale((w[0].w >> 8) & 0xffu), exp_scale((w[0].w >> 16) & 0xffu)};
+            const uint32_t child_base = w[1].x;
+            leaf_base = w[1].y;
+            const uint32_t metas[2] = {w[1].z, w[1].w};
+            // quantised planes: words 2..4 = qlo[x,y,z][8], words 5..7 = qhi[x,y,z][8] (u16 each).  Per axis
+            // the ray's direction sign says which of the two is the entry plane -- chosen once per
+            // node on the packed words, not per child on the decoded distances.
+            uint32_t qn[3][4], qf[3][4];
+            float bias[3];
+#pragma unroll
+            for (int a = 0; a < 3; a++) {
+                const bool fwd = inv[a] >= 0.0f;
+                const uint32_t* lo4 = reinterpret_cast<const uint32_t*>(&w[2 + a]);
+                const uint32_t* hi4 = reinterpret_cast<const uint32_t*>(&w[5 + a]);
+#pragma unroll
+                for (int j = 0; j < 4; j++) { qn[a][j] = fwd ? lo4[j] : hi4[j]; qf[a][j] = fwd ? hi4[j] : lo4[j]; }
+                bias[a] = a == 0 ? O.x : (a == 1 ? O.y : O.z);
+            }
+            uint32_t key[8];
+            uint32_t lb = 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const uint32_t m = (metas[k >> 2] >> (8 * (k & 3))) & 0xffu;
+                float t0 = QZ_TNEAR, t1 = limit;
+#pragma unroll
+                for (int a = 0; a < 3; a++) {
+                    const uint32_t q0 = (qn[a][k >> 1] >> (16 * (k & 1))) & 0xffffu;
+                    const uint32_t q1 = (qf[a][k >> 1] >> (16 * (k & 1))) & 0xffffu;
+                    // plane = org + q * 2^e: the product is exact, so the fused form rounds once, to the same value
+                    const float pn = __fmaf_rn((float)q0, scl[a], org[a]);
+                    const float pf = __fmaf_rn((float)q1, scl[a], org[a]);
+                    t0 = fmaxf(t0, (pn - bias[a]) * inv[a]);   // fmaxf / fminf drop NaN (0 * inf)
+                    t1 = fminf(t1, (pf - bias[a]) * inv[a]);
+                }
+                // box_hit's conservative widening (bvh.cuh) is a monotone map of each slab distance, so it
+                // is applied once, to the max / min of them; QZ_TNEAR and the limit stay as they are
+                float e0 = t0 * (t0 >= 0.0f ? 0.9999995f : 1.0000005f);
+                float e1 = t1 * (t1 >= 0.0f ? 1.0000005f : 0.9999995f);
+                e0 = fmaxf(e0, QZ_TNEAR);
+                e1 = fminf(e1, limit);
+                const bool hit = m != 0u && e0 <= e1;
+                const bool internal = (m & 0x80u) != 0u;
+                key[k] = (hit && internal) ? ((__float_as_uint(e0) & ~7u) | (m & 7u)) : 0u;
+                if (hit && !internal) lb |= ((1u << (m >> 5)) - 1u) << (m & 31u);
+            }
+            // sort the (distance | child slot) keys descending: Batcher's 19-comparator network
+            QZ_CSWAP_DESC(key[0], key[1]); QZ_CSWAP_DESC(key[2], key[3]); QZ_CSWAP_DESC(key[4], key[5]); QZ_CSWAP_DESC(key[6], key[7]);
+            QZ_CSWAP_DESC(key[0], key[2]); QZ_CSWAP_DESC(key[1], key[3]); QZ_CSWAP_DESC(key[4], key[6]); QZ_CSWAP_DESC(key[5], key[7]);
+            QZ_CSWAP_DESC(key[1], key[2]); QZ_CSWAP_DESC(key[5], key[6]);
+            QZ_CSWAP_DESC(key[0], key[4]); QZ_CSWAP_DESC(key[1], key[5]); QZ_CSWAP_DESC(key[2], key[6]); QZ_CSWAP_DESC(key[3], key[7]);
+            QZ_CSWAP_DESC(key[2], key[4]); QZ_CSWAP_DESC(key[3], key[5]);
+            QZ_CSWAP_DESC(key[1], key[2]); QZ_CSWAP_DESC(key[3], key[4]); QZ_CSWAP_DESC(key[5], key[6]);
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                if (key[k]) {
+                    if (sp < QZ_STACK) { stack[sp] = make_uint2(key[k], child_base + (key[k] & 7u)); sp++; }
+                    else overflow = 1u;
+                }
+            }
+            leafbits = lb;
+            if (lb) state = LS_PRIM;
+            else pop_next();
+        }
+    }
+    if (COUNT) {
+        atomicAdd(&b.stats[S_NODES], (unsigned long long)cnt_nodes);
+        atomicAdd(&b.stats[S_PRIMS], (unsigned long long)cnt_prims);
+    }
+    if (overflow) atomicAdd(&b.stats[S_OVERFLOW], 1ull);
+}
+
+// ------------------------------------------------------------------ octet traversal
+// Warp-cooperative BVH traversal: EIGHT LANES PER RAY, one lane per child of the wide node, four
+// rays per warp advancing in lockstep (node phase, leaf phase, push/pop phase), so that lanes of a
+// warp never sit in different parts of the state machine:
+//   * node phase: the octet reads ONE 128-byte node line (header broadcast + each lane its own
+//     child's six quantised planes) and every lane slab-tests its child -- 8 box tests per
+//     instruction stream instead of 8 serial ones per lane;
+//   * leaf phase: the primitives of all leaf children that were hit form a bit mask over the
+//     node's contiguous leaf block; the octet's lanes take one primitive each;
+//   * push/pop: hit internal children are ranked by entry distance with 7 shuffles and written,
+//     far to near, to the octet's SHARED-MEMORY stack; the next node is popped with culling
+//     against the current best distance;
+//   * an octet whose ray has finished takes the next live slot of its private 16-slot chunk
+//     (one atomic per chunk) -- the persistent, vote-driven refill of the per-lane kernel at
+//     octet granularity.
+// The answer is the brute-force minimum under the (t, key) order, exactly as the per-lane
+// traversal (bvh.cuh) defines it: the same box and primitive arithmetic, a lane-local best per
+// lane and one (t, key) arg-min over the octet when the ray is done.
+#define QZ_OCT_STACK 96   /* shared stack entries per octet (internal nodes only) */
+#define QZ_OCT_CHUNK 16   /* slots an octet reserves with one atomic */
+
+__device__ __forceinline__ uint32_t nonzero_byte_nibble(uint32_t w) {
+    return ((__vcmpne4(w, 0u) & 0x08040201u) * 0x01010101u) >> 24;
+}
+__device__ __forceinline__ uint32_t equal_byte_nibble(uint32_t w, uint32_t pattern) {
+    return ((__vcmpeq4(w, pattern) & 0x08040201u) * 0x01010101u) >> 24;
+}
+
+template <bool ANY_HIT, bool COUNT>
+__global__ void __launch_bounds__(128, ANY_HIT ? 8 : 6) k_trace_oct(DScene sc, WfBuffers b, uint32_t flags) {
+    __shared__ uint2 s_stack[16][QZ_OCT_STACK + 1];
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int k = lane & 7;            // the child this lane tests
+    const int obase = lane & ~7;       // first lane of the octet
+    uint2* stack = s_stack[threadIdx.x >> 3];
+    const uint32_t count = ANY_HIT ? b.counters[C_SHADOW] : b.pool;
+    uint32_t* cursor = &b.counters[ANY_HIT ? C_CURSOR_SHADOW : C_CURSOR_TRACE];
+
+    // octet-uniform state
+    bool active = false, exhausted = false;
+    uint32_t chunk_base = 0, live = 0, firsts = 0;
+    uint32_t slot = 0, cur = 0;
+    bool first = false;
+    V3 O = v3(0.0f, 0.0f, 0.0f), D = v3(0.0f, 0.0f, 0.0f);
+    float o[3] = {0.0f, 0.0f, 0.0f}, inv[3] = {0.0f, 0.0f, 0.0f};
+    float limit = 0.0f;   // closest hit: best t of the octet so far; any hit: the segment end
+    int sp = 0;
+    // lane-local
+    Hit best;
+    best.t = INFINITY; best.u = 0.0f; best.v = 0.0f; best.prim = QZ_NO_HIT; best.key = 0xffffffffu;
+    best.ng = v3(0.0f, 0.0f, 0.0f); best.geom_id = QZ_NO_HIT; best.prim_id = 0;
+    uint32_t cnt_nodes = 0, cnt_prims = 0, overflow = 0;
+
+    for (;;) {
+        // ---- refill: idle octets take the next live slot; an empty chunk is replaced first
+        while (__any_sync(full, !active && !(exhausted && live == 0u))) {
+            const bool want = !active && !(exhausted && live == 0u);
+            const bool fetch = want && live == 0u;
+            uint32_t base = 0;
+            if (fetch && k == 0) base = atomicAdd(cursor, (uint32_t)QZ_OCT_CHUNK);
+            base = __shfl_sync(full, base, obase);
+            if (fetch) {
+                if (base >= count) {
+                    exhausted = true;
+                } else {
+                    chunk_base = base;
+                    const uint32_t n = count - base < (uint32_t)QZ_OCT_CHUNK ? count - base : (uint32_t)QZ_OCT_CHUNK;
+                    uint32_t lv = (1u << n) - 1u;
+                    if (!ANY_HIT) {
+                        // the stage tags of the chunk say which slots carry a ray this iteration
+                        const uint4 tg = *reinterpret_cast<const uint4*>(b.stage + base);
+                        const uint32_t nz = nonzero_byte_nibble(tg.x) | (nonzero_byte_nibble(tg.y) << 4) |
+                                            (nonzero_byte_nibble(tg.z) << 8) | (nonzero_byte_nibble(tg.w) << 12);
+                        const uint32_t pat = 0x01010101u * (uint32_t)ST_TRACE_FIRST;
+                        firsts = equal_byte_nibble(tg.x, pat) | (equal_byte_nibble(tg.y, pat) << 4) |
+                                 (equal_byte_nibble(tg.z, pat) << 8) | (equal_byte_nibble(tg.w, pat) << 12);
+                        lv &= nz;
+                        for (uint32_t i = (uint32_t)k; i < n; i += 8u)
+                            if (!((lv >> i) & 1u)) b.fam[base + i] = QZ_FAM_NONE;
+                    }
+                    live = lv;
+                }
+            } else if (want) {
+                const int i = __ffs(live) - 1;
+                live &= live - 1u;
+                float4 ro, rd;
+                if (ANY_HIT) {
+                    slot = b.q_shadow[chunk_base + (uint32_t)i];
+                    ro = b.sh_o[slot]; rd = b.sh_d[slot];
+                    limit = 1.0f;
+                } else {
+                    slot = chunk_base + (uint32_t)i;
+                    first = ((firsts >> i) & 1u) != 0u;
+                    ro = b.ray_o[slot]; rd = b.ray_d[slot];
+                    limit = INFINITY;
+                }
+                O = v3(ro.x, ro.y, ro.z); D = v3(rd.x, rd.y, rd.z);
+                o[0] = O.x; o[1] = O.y; o[2] = O.z;
+                inv[0] = 1.0f / D.x; inv[1] = 1.0f / D.y; inv[2] = 1.0f / D.z;
+                best.t = INFINITY; best.prim = QZ_NO_HIT; best.key = 0xffffffffu; best.geom_id = QZ_NO_HIT;
+                best.u = 0.0f; best.v = 0.0f; best.ng = v3(0.0f, 0.0f, 0.0f); best.prim_id = 0;
+                cur = 0; sp = 0;
+                active = true;
+            }
+        }
+        if (!__any_sync(full, active)) break;
+
+        // ---- node phase: lane k slab-tests child k of the octet's current node
+        bool hit_child = false;
+        float dist = 0.0f;
+        uint32_t meta = 0, child_base = 0, leaf_base = 0;
+        if (active) {
+            const uint4* np = reinterpret_cast<const uint4*>(sc.nodes + cur);
+            const uint4 h0 = __ldg(np), h1 = __ldg(np + 1);
+            meta = ((k < 4 ? h1.z : h1.w) >> (8 * (k & 3))) & 0xffu;
+            child_base = h1.x; leaf_base = h1.y;
+            if (COUNT && k == 0) cnt_nodes++;
+            if (meta) {
+                const unsigned short* q = reinterpret_cast<const unsigned short*>(np + 2);
+                const float org[3] = {__uint_as_float(h0.x), __uint_as_float(h0.y), __uint_as_float(h0.z)};
+                const float scl[3] = {exp_scale(h0.w & 0xffu), exp_scale((h0.w >> 8) & 0xffu), exp_scale((h0.w >> 16) & 0xffu)};
+                float lo[3], hi[3];
+#pragma unroll
+                for (int a = 0; a < 3; a++) {
+                    lo[a] = org[a] + (float)__ldg(q + a * 8 + k) * scl[a];
+                    hi[a] = org[a] + (float)__ldg(q + 24 + a * 8 + k) * scl[a];
+                }
+                hit_child = box_hit(lo, hi, o, inv, QZ_TNEAR, limit, dist);
+            }
+        }
+
+        // ---- leaf phase: the primitives of the hit leaf children, one per lane and round
+        uint32_t bits = (hit_child && !(meta & 0x80u)) ? (((1u << (meta >> 5)) - 1u) << (meta & 31u)) : 0u;
+        bits |= __shfl_xor_sync(full, bits, 1);
+        bits |= __shfl_xor_sync(full, bits, 2);
+        bits |= __shfl_xor_sync(full, bits, 4);
+        bool occl = false;
+        if (__any_sync(full, bits != 0u)) {
+            do {
+                uint32_t m = bits;
+                for (int i = 0; i < k; i++) m &= m - 1u;
+                if (m) {
+                    const uint32_t p = leaf_base + (uint32_t)(__ffs(m) - 1);
+                    if (COUNT) cnt_prims++;
+                    if (ANY_HIT) {
+                        best.t = INFINITY; best.prim = QZ_NO_HIT; best.key = 0xffffffffu;
+                        prim_test(sc, p, O, D, QZ_TNEAR, INFINITY, best);
+                        occl = occl || (best.prim != QZ_NO_HIT && best.t <= limit);
+                    } else {
+                        prim_test(sc, p, O, D, QZ_TNEAR, INFINITY, best);
+                    }
+                }
+                // the lowest eight set bits are done
+                if (__popc(bits) <= 8) bits = 0u;
+                else {
+#pragma unroll
+                    for (int i = 0; i < 8; i++) bits &= bits - 1u;
+                }
+            } while (__any_sync(full, bits != 0u));
+            if (ANY_HIT) {
+                occl = ((__ballot_sync(full, occl) >> obase) & 0xffu) != 0u;
+            } else {
+                float t = best.t;
+                t = fminf(t, __shfl_xor_sync(full, t, 1));
+                t = fminf(t, __shfl_xor_sync(full, t, 2));
+                t = fminf(t, __shfl_xor_sync(full, t, 4));
+                if (active) limit = t;
+            }
+        }
+
+        // ---- push the hit internal children far-to-near, pop the next node
+        const bool push = hit_child && (meta & 0x80u) && (ANY_HIT || dist <= limit);
+        const uint32_t key = push ? ((__float_as_uint(dist) & ~7u) | (uint32_t)k) : 0u;
+        int rank = 0;
+#pragma unroll
+        for (int j = 1; j < 8; j++) {
+            const uint32_t other = __shfl_sync(full, key, obase | ((k + j) & 7));
+            rank += other > key ? 1 : 0;
+        }
+        const int n_push = __popc((__ballot_sync(full, push) >> obase) & 0xffu);
+        if (push) {
+            if (sp + rank < QZ_OCT_STACK) stack[sp + rank] = make_uint2(__float_as_uint(dist), child_base + (meta & 0x7fu));
+            else overflow = 1u;
+        }
+        __syncwarp();
+        bool done = false;
+        if (active) {
+            sp = sp + n_push < QZ_OCT_STACK ? sp + n_push : QZ_OCT_STACK;
+            if (ANY_HIT && occl) {
+                done = true;
+            } else {
+                for (;;) {
+                    if (sp == 0) { done = true; break; }
+                    sp--;
+                    const uint2 e = stack[sp];
+                    if (__uint_as_float(e.x) <= limit) { cur = e.y; break; }
+                }
+            }
+        }
+        __syncwarp();
+
+        // ---- finished rays
+        if (__any_sync(full, done)) {
+            if (ANY_HIT) {
+                if (done && !occl && k == 0) {
+                    const float4 L = b.radiance[slot], c = b.sh_c[slot];
+                    b.radiance[slot] = f4(L.x + c.x, L.y + c.y, L.z + c.z, L.w + c.w);
+                }
+            } else {
+                // arg-min of (t, key) over the octet; t > 0 or +inf, so its bit pattern orders like the value
+                uint32_t bt = __float_as_uint(best.t), bk = best.key;
+#pragma unroll
+                for (int d = 1; d < 8; d <<= 1) {
+                    const uint32_t ot = __shfl_xor_sync(full, bt, d), ok = __shfl_xor_sync(full, bk, d);
+                    if (ot < bt || (ot == bt && ok < bk)) { bt = ot; bk = ok; }
+                }
+                if (done) {
+                    const bool miss = bk == 0xffffffffu;  // no lane found a hit
+                    const bool winner = miss ? k == 0 : (best.prim != QZ_NO_HIT && __float_as_uint(best.t) == bt && best.key == bk);
+                    if (winner) finish_closest(sc, b, slot, first, best, flags);
+                }
+            }
+            if (done) active = false;
+        }
+    }
+    if (COUNT) {
+        if (cnt_nodes) atomicAdd(&b.stats[S_NODES], (unsigned long long)cnt_nodes);
+        if (cnt_prims) atomicAdd(&b.stats[S_PRIMS], (unsigned long long)cnt_prims);
+    }
+    if (overflow) atomicAdd(&b.stats[S_OVERFLOW], 1ull);
 }
 
 // roles (bit mask over SampleRole) a queue's paths will read this bounce

@@ -46,7 +46,7 @@ class QzStats(ctypes.Structure):
         ("bvh_nodes", ctypes.c_uint32),
         ("bvh_bytes", ctypes.c_uint32),
         ("ms_sample", ctypes.c_float),
-        ("reserved", ctypes.c_uint32),
+        ("stack_overflows", ctypes.c_uint32),
     ]
 
     def as_dict(self) -> dict:
@@ -85,6 +85,8 @@ QZ_FLAG_UNSORTED_SHADING = 1
 QZ_FLAG_COUNT_TRAVERSAL = 2
 QZ_FLAG_STAGE_TIMING = 4
 QZ_FLAG_FORCE_BVH = 8
+QZ_FLAG_LANE_TRAVERSAL = 16
+QZ_FLAG_OCTET_TRAVERSAL = 32
 
 
 @dataclass
@@ -185,6 +187,22 @@ class Scene:
         cam = QzCamera()
         self._h._fn("camera")(self._handle, ctypes.byref(cam))
         return cam
+
+    def render_flags(self, spp: int, max_bounces: int | None = None, flags: int = 0, pool: int = 0, samples_per_pass: int = 0):
+        """qz_render through the raw C ABI with explicit render options; returns (RenderOutput, stats)."""
+        max_bounces = self.default_max_bounces if max_bounces is None else max_bounces
+        shape = (self.height, self.width, 3)
+        color, normal, albedo = (np.zeros(shape, np.float32) for _ in range(3))
+        cam, st, opts = self.c_camera(), QzStats(), QzRenderOptions(flags, pool, samples_per_pass, 0)
+        lib = self._h.lib
+        lib.qz_render.restype = ctypes.c_int
+        rc = lib.qz_render(ctypes.c_void_p(self.c_scene_handle()), ctypes.byref(cam), spp, max_bounces, None, ctypes.byref(opts),
+                           color.ctypes.data_as(ctypes.c_void_p), normal.ctypes.data_as(ctypes.c_void_p),
+                           albedo.ctypes.data_as(ctypes.c_void_p), ctypes.byref(st))
+        if rc != 0:
+            lib.qz_last_error.restype = ctypes.c_char_p
+            raise RuntimeError(f"qz_render failed: {lib.qz_last_error().decode()}")
+        return RenderOutput(color, normal, albedo, st.ms_total * 1e-3, st.rays_closest + st.rays_shadow, 0), st.as_dict()
 
     def last_stats(self) -> dict:
         st = QzStats()

@@ -118,6 +118,58 @@ def test_wavefront_film_equals_replayed_paths(qz):
         assert bits_equal(film.normal, normal / n).all(), name
 
 
+def _replayed_film(sc, w, h, spp):
+    ys, xs, ss = np.meshgrid(np.arange(h), np.arange(w), np.arange(spp), indexing="ij")
+    xys = np.stack([xs.ravel(), (h - 1 - ys).ravel(), ss.ravel()], 1).astype(np.int32)
+    rec = sc.trace_paths(xys, spp=spp).reshape(h, w, spp, 32)
+    planes = [np.zeros((h, w, 3), np.float32) for _ in range(3)]
+    for s in range(spp):
+        planes[0] += rec[:, :, s, 20:23]
+        planes[1] += rec[:, :, s, 12:15]
+        planes[2] += rec[:, :, s, 23:26]
+    return [p / np.float32(spp) for p in planes]
+
+
+@pytest.mark.parametrize("material,light", [("alluminum", "point"), ("glass", "area"), ("diffuse", "ambient")])
+def test_bvh_traversal_kernels_equal_replayed_paths(qz, small_mesh, material, light):
+    """The wavefront BVH kernels on a mesh scene -- the octet (8 lanes per ray) traversal that is the
+    default, and the one-ray-per-lane kernels behind QZ_FLAG_LANE_TRAVERSAL -- against the scalar
+    traversal of the per-path replay: bit-identical films, and counters that agree on the rays."""
+    from quetzalcoatlus_b200.harness import QZ_FLAG_COUNT_TRAVERSAL, QZ_FLAG_LANE_TRAVERSAL, QZ_FLAG_OCTET_TRAVERSAL
+
+    w, h, spp = 96, 72, 4
+    with qz.build_scene("obj_viewer", w, h, obj_path=small_mesh, obj_material=material, obj_light=light) as sc:
+        want = _replayed_film(sc, w, h, spp)
+        rays = None
+        for flags in (0, QZ_FLAG_LANE_TRAVERSAL, QZ_FLAG_OCTET_TRAVERSAL, QZ_FLAG_COUNT_TRAVERSAL,
+                      QZ_FLAG_COUNT_TRAVERSAL | QZ_FLAG_LANE_TRAVERSAL, QZ_FLAG_COUNT_TRAVERSAL | QZ_FLAG_OCTET_TRAVERSAL):
+            for pool in (0, 1000):
+                film, st = sc.render_flags(spp, flags=flags, pool=pool)
+                assert st["stack_overflows"] == 0
+                for got, ref, plane in zip((film.color, film.normal, film.albedo), want, ("color", "normal", "albedo")):
+                    assert bits_equal(got, ref).all(), (flags, pool, plane, float(1.0 - bits_equal(got, ref).mean()))
+                rays = rays or (st["rays_closest"], st["rays_shadow"])
+                assert (st["rays_closest"], st["rays_shadow"]) == rays
+                if flags & QZ_FLAG_COUNT_TRAVERSAL:
+                    assert st["node_visits"] >= st["rays_closest"] and st["prim_tests"] > 0
+
+
+def test_forced_bvh_on_analytic_scenes(qz):
+    """Scenes small enough for the flat kernels, pushed through the BVH kernels instead
+    (QZ_FLAG_FORCE_BVH): spheres, quads, grid cells and hoisted huge primitives in one tree."""
+    from quetzalcoatlus_b200.harness import QZ_FLAG_FORCE_BVH, QZ_FLAG_LANE_TRAVERSAL, QZ_FLAG_OCTET_TRAVERSAL
+
+    for name, (w, h, spp) in {"cornell_box": (40, 36, 4), "kitchen_sink": (32, 24, 4), "opposing_planes": (48, 27, 4),
+                              "mandelbrot": (32, 32, 3), "glass_spheres": (32, 32, 4)}.items():
+        with qz.build_scene(name, w, h) as sc:
+            base, _ = sc.render_flags(spp)
+            for flags in (QZ_FLAG_FORCE_BVH, QZ_FLAG_FORCE_BVH | QZ_FLAG_LANE_TRAVERSAL, QZ_FLAG_FORCE_BVH | QZ_FLAG_OCTET_TRAVERSAL):
+                film, st = sc.render_flags(spp, flags=flags)
+                assert st["stack_overflows"] == 0
+                assert bits_equal(film.color, base.color).all() and bits_equal(film.normal, base.normal).all() \
+                    and bits_equal(film.albedo, base.albedo).all(), (name, flags)
+
+
 def test_film_against_golden(qz):
     for name in ["cornell_box", "textures", "kitchen_sink"]:
         g = np.load(GOLDEN / f"film_{name}.npz")
