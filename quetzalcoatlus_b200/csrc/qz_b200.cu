@@ -81,6 +81,21 @@ struct CudaExec {
     }
 };
 
+// entry e of the concatenated prefix tables: find its dimension (dim_start is ascending), fill it
+__global__ void k_build_sampler_prefix(SamplerDim* table, const uint32_t* __restrict__ dim_start, uint32_t n) {
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    // last dimension d with dim_start[d] <= e and a table of its own
+    uint32_t lo = 0, hi = QZ_N_PRIMES;
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (dim_start[mid] <= e) lo = mid; else hi = mid;
+    }
+    const SamplerDim rec = table[lo];
+    uint16_t* prefix = reinterpret_cast<uint16_t*>(table + QZ_N_PRIMES);
+    prefix[e] = sampler_prefix_entry(rec, e - rec.pre_offset);
+}
+
 // per-device constant tables (sampler dimensions, depth-0 albedo sample warps)
 struct DeviceTables {
     SamplerDim* sampler = nullptr;
@@ -98,8 +113,24 @@ int device_tables(int dev, DeviceTables& out) {
         build_sampler_table(host.data());
         float rho[16 * 8];
         build_rho_table(rho);
-        QZ_CUDA(cudaMalloc(&t.sampler, host.size() * sizeof(SamplerDim)));
+        // records, then the prefix tables of every dimension (sampler.cuh), filled by a kernel
+        const uint32_t n_prefix = plan_sampler_prefix(host.data(), QZ_N_PRIMES, QZ_PREFIX_CAP);
+        std::vector<uint32_t> dim_start(QZ_N_PRIMES + 1);
+        // dim_start[d] = first entry of the first dimension >= d that has a table (ascending, for the kernel's search)
+        {
+            uint32_t next = n_prefix;
+            for (int d = QZ_N_PRIMES - 1; d >= 0; d--) { if (host[d].pre_pow) next = host[d].pre_offset; dim_start[d] = next; }
+            dim_start[QZ_N_PRIMES] = n_prefix;
+        }
+        QZ_CUDA(cudaMalloc(&t.sampler, host.size() * sizeof(SamplerDim) + (size_t)n_prefix * sizeof(uint16_t) + 16));
         QZ_CUDA(cudaMemcpy(t.sampler, host.data(), host.size() * sizeof(SamplerDim), cudaMemcpyHostToDevice));
+        uint32_t* d_start = nullptr;
+        QZ_CUDA(cudaMalloc(&d_start, dim_start.size() * sizeof(uint32_t)));
+        QZ_CUDA(cudaMemcpy(d_start, dim_start.data(), dim_start.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        k_build_sampler_prefix<<<(n_prefix + 255) / 256, 256>>>(t.sampler, d_start, n_prefix);
+        QZ_CUDA(cudaGetLastError());
+        QZ_CUDA(cudaDeviceSynchronize());
+        cudaFree(d_start);
         QZ_CUDA(cudaMalloc(&t.rho, sizeof(rho)));
         QZ_CUDA(cudaMemcpy(t.rho, rho, sizeof(rho), cudaMemcpyHostToDevice));
     }
@@ -212,7 +243,7 @@ struct DevBuf {
 // calls of the same or a smaller size (cudaMalloc/cudaFree of gigabytes per call would otherwise
 // dominate the end-to-end time of short renders).
 struct WorkMem {
-    DevBuf f4bufs[14], qbufs[10], tags[3], samples, counters, statsb, res_a, res_b, res_c, rowsb, sensor, acc;
+    DevBuf rec_hot, rec_side, qbufs[10], tags[3], counters, statsb, res_a, res_b, res_c, rowsb, sensor, acc;
     uint32_t pool = 0;
     uint64_t cells = 0, acc_pix = 0, rows = 0;
     uint32_t* h_counters = nullptr;  // pinned
@@ -347,13 +378,12 @@ static int render_impl(qz_scene s, const qz_camera* camera, uint32_t n_samples, 
 
     // ---- working memory (cached in the scene handle)
     WorkMem& wm = s->work;
-    DevBuf(&f4bufs)[14] = wm.f4bufs;
     DevBuf(&qbufs)[10] = wm.qbufs;
     DevBuf &counters = wm.counters, &statsb = wm.statsb, &res_a = wm.res_a, &res_b = wm.res_b, &res_c = wm.res_c,
            &rowsb = wm.rowsb, &sensor = wm.sensor, &acc = wm.acc;
-    for (auto& buf : f4bufs) QZ_CUDA(buf.reserve((size_t)pool * 16));
+    QZ_CUDA(wm.rec_hot.reserve((size_t)pool * QZ_REC_BYTES));
+    QZ_CUDA(wm.rec_side.reserve((size_t)pool * QZ_REC_BYTES));
     for (auto& buf : qbufs) QZ_CUDA(buf.reserve((size_t)pool * 4));
-    QZ_CUDA(wm.samples.reserve((size_t)pool * R_COUNT * 4));
     for (auto& buf : wm.tags) QZ_CUDA(buf.reserve((size_t)pool + 16));
     QZ_CUDA(counters.reserve(C_WORDS * 4));
     QZ_CUDA(statsb.reserve(S_WORDS * 8));
@@ -369,14 +399,13 @@ static int render_impl(qz_scene s, const qz_camera* camera, uint32_t n_samples, 
     QZ_CUDA(cudaMemsetAsync(statsb.p, 0, S_WORDS * 8, stream));
 
     WfBuffers b{};
-    b.ray_o = f4bufs[0].as<float4>(); b.ray_d = f4bufs[1].as<float4>();
-    b.hit_a = f4bufs[2].as<float4>(); b.hit_b = f4bufs[3].as<float4>();
-    b.weight = f4bufs[4].as<float4>(); b.radiance = f4bufs[5].as<float4>();
-    b.lambda = f4bufs[6].as<float4>(); b.lpdf = f4bufs[7].as<float4>();
-    b.misc = f4bufs[8].as<uint4>();
-    b.aov_n = f4bufs[9].as<float4>(); b.aov_a = f4bufs[10].as<float4>();
-    b.sh_o = f4bufs[11].as<float4>(); b.sh_d = f4bufs[12].as<float4>(); b.sh_c = f4bufs[13].as<float4>();
-    b.samples = wm.samples.as<float>();
+    static_assert(R_COUNT * sizeof(float) == 32, "the samples of a bounce fill the last two elements of the side line");
+    char* hot = wm.rec_hot.as<char>();
+    char* side = wm.rec_side.as<char>();
+    b.ray_o.base = hot + 0;   b.ray_d.base = hot + 16;  b.weight.base = hot + 32;    b.lambda.base = hot + 48;
+    b.hit_a.base = hot + 64;  b.hit_b.base = hot + 80;  b.misc.base = hot + 96;      b.lpdf.base = hot + 112;
+    b.sh_o.base = side + 0;   b.sh_d.base = side + 16;  b.sh_c.base = side + 32;     b.radiance.base = side + 48;
+    b.aov_n.base = side + 64; b.aov_a.base = side + 80; b.samples.base = side + 96;
     b.stage = wm.tags[0].as<uint8_t>(); b.fam = wm.tags[1].as<uint8_t>(); b.post = wm.tags[2].as<uint8_t>();
     for (int k = 0; k < SQ_COUNT; k++) b.q_shade[k] = qbufs[k].as<uint32_t>();
     b.q_shadow = qbufs[8].as<uint32_t>(); b.q_done = qbufs[9].as<uint32_t>();

@@ -26,7 +26,27 @@ struct SamplerDim {
     uint32_t magic;    // floor(2^32 / base)
     uint32_t hash;     // uint32(mix_bits(1 + (dim << 4)))
     uint32_t scale;    // float bits of base^-ndigits (sequential float products)
+    // prefix table (see below): the scrambled value of the index's lowest pre_k digits
+    uint32_t pre_pow;     // base^pre_k; 0 = this dimension has no prefix table
+    uint32_t pre_magic;   // floor(2^32 / pre_pow)
+    uint32_t pre_offset;  // first entry of this dimension in the prefix array
+    uint32_t pre_k;
 };
+static_assert(sizeof(SamplerDim) == 32, "two 16-byte loads per dimension record");
+
+// PREFIX TABLES.  The scrambled value of the lowest k digits of the Halton index depends on
+// nothing but (dimension, index mod base^k): digit j's permutation is keyed by the scrambled
+// digits below it.  So for every dimension the first k digits -- as many as fit
+// QZ_PREFIX_CAP entries -- are tabulated once per device (16-bit entries, since the value is
+// below base^k <= 32768), the table following the QZ_N_PRIMES records in the same allocation.
+// An evaluation then costs one division by base^k, one 2-byte gather and the remaining
+// nd - k digits: base 5 runs 5 digit rounds instead of 11, base 7 4 instead of 9, bases 37..181
+// 3 instead of 5.  The entries are produced by the very digit loop below, so the values are
+// the reference's bit for bit.
+#define QZ_PREFIX_CAP 32768u
+QZ_HD const uint16_t* sampler_prefix_array(const SamplerDim* table) {
+    return reinterpret_cast<const uint16_t*>(table + QZ_N_PRIMES);
+}
 
 // per-render constants of Sampler's constructor (sampler.cpp:383-402)
 struct SamplerParams {
@@ -82,20 +102,38 @@ QZ_HD uint32_t permutation_element(uint32_t i, uint32_t l, uint32_t magic, uint3
     return rem;
 }
 
-// sampler.cpp:335-352 for one table entry; `a` is the Halton index
-QZ_HD float owen_scrambled_radical_inv(const SamplerDim dimrec, uint32_t a) {
+// digits [k0, k1) of sampler.cpp:335-352's loop: `a` holds the index with the first k0 digits
+// already removed, `reversed` their scrambled value
+QZ_HD uint64_t owen_digits(const SamplerDim& dimrec, uint32_t a, uint32_t k0, uint32_t k1, uint64_t reversed) {
     const uint32_t base = dimrec.base_nd & 0xffffu;
-    const uint32_t nd = dimrec.base_nd >> 16;
     // w = (next power of two >= base) - 1, as the or-shift cascade of permutation_element computes it
     uint32_t w = base - 1;
     w |= w >> 1; w |= w >> 2; w |= w >> 4; w |= w >> 8; w |= w >> 16;
-    uint64_t reversed = 0;
-    for (uint32_t k = 0; k < nd; k++) {
+    for (uint32_t k = k0; k < k1; k++) {
         uint32_t digit;
         a = div_magic(a, base, dimrec.magic, digit);
         uint32_t digit_hash = (uint32_t)mix_bits((uint64_t)dimrec.hash ^ reversed);
         digit = permutation_element(digit, base, dimrec.magic, w, digit_hash);
         reversed = reversed * base + digit;
+    }
+    return reversed;
+}
+
+// sampler.cpp:335-352 for one table entry; `a` is the Halton index
+QZ_HD float owen_scrambled_radical_inv(const SamplerDim& dimrec, const uint16_t* prefix, uint32_t a) {
+    const uint32_t nd = dimrec.base_nd >> 16;
+    uint64_t reversed;
+    if (dimrec.pre_pow) {
+        uint32_t lo;
+        const uint32_t hi = div_magic(a, dimrec.pre_pow, dimrec.pre_magic, lo);
+#if defined(__CUDA_ARCH__)
+        const uint32_t head = __ldg(prefix + dimrec.pre_offset + lo);
+#else
+        const uint32_t head = prefix[dimrec.pre_offset + lo];
+#endif
+        reversed = owen_digits(dimrec, hi, dimrec.pre_k, nd, head);
+    } else {
+        reversed = owen_digits(dimrec, a, 0, nd, 0);
     }
     float r = u32_as_float(dimrec.scale) * (float)reversed;
     return std_min(r, QZ_ONE_MINUS_EPS);
@@ -142,30 +180,56 @@ QZ_HD V2 sampler_pixel_jitter(const SamplerParams& sp, const Sampler& smp) {
     return v2(radical_inv(2, smp.index >> sp.exp0), radical_inv(3, smp.index / sp.scale1));
 }
 
-QZ_HD float sample_dimension(const SamplerDim* __restrict__ table, const Sampler& smp, uint32_t dim) {
+QZ_HD SamplerDim load_dim(const SamplerDim* __restrict__ table, uint32_t dim) {
 #if defined(__CUDA_ARCH__)
-    const uint4 raw = __ldg(reinterpret_cast<const uint4*>(table) + dim);
-    SamplerDim rec; rec.base_nd = raw.x; rec.magic = raw.y; rec.hash = raw.z; rec.scale = raw.w;
+    const uint4 r0 = __ldg(reinterpret_cast<const uint4*>(table + dim)), r1 = __ldg(reinterpret_cast<const uint4*>(table + dim) + 1);
+    SamplerDim rec;
+    rec.base_nd = r0.x; rec.magic = r0.y; rec.hash = r0.z; rec.scale = r0.w;
+    rec.pre_pow = r1.x; rec.pre_magic = r1.y; rec.pre_offset = r1.z; rec.pre_k = r1.w;
+    return rec;
 #else
-    const SamplerDim rec = table[dim];
+    return table[dim];
 #endif
-    return owen_scrambled_radical_inv(rec, smp.index);
+}
+
+QZ_HD float sample_dimension(const SamplerDim* __restrict__ table, const Sampler& smp, uint32_t dim) {
+    const SamplerDim rec = load_dim(table, dim);
+    return owen_scrambled_radical_inv(rec, sampler_prefix_array(table), smp.index);
 }
 
 // two independent dimensions evaluated in one loop: the digit chains of the two dimensions do
 // not depend on each other, so interleaving them doubles the instruction-level parallelism of
 // what is otherwise one long dependent integer chain per digit
-QZ_HD V2 owen_scrambled_radical_inv_pair(const SamplerDim r0, const SamplerDim r1, uint32_t a) {
+QZ_HD V2 owen_scrambled_radical_inv_pair(const SamplerDim& r0, const SamplerDim& r1, const uint16_t* prefix, uint32_t a) {
     const uint32_t b0 = r0.base_nd & 0xffffu, b1 = r1.base_nd & 0xffffu;
     const uint32_t n0 = r0.base_nd >> 16, n1 = r1.base_nd >> 16;
     uint32_t w0 = b0 - 1, w1 = b1 - 1;
     w0 |= w0 >> 1; w0 |= w0 >> 2; w0 |= w0 >> 4; w0 |= w0 >> 8; w0 |= w0 >> 16;
     w1 |= w1 >> 1; w1 |= w1 >> 2; w1 |= w1 >> 4; w1 |= w1 >> 8; w1 |= w1 >> 16;
     uint64_t rev0 = 0, rev1 = 0;
-    uint32_t a0 = a, a1 = a;
-    const uint32_t nmin = n0 < n1 ? n0 : n1;
-    uint32_t k = 0;
-    for (; k < nmin; k++) {
+    uint32_t a0 = a, a1 = a, k0 = 0, k1 = 0;
+    if (r0.pre_pow) {
+        uint32_t lo;
+        a0 = div_magic(a, r0.pre_pow, r0.pre_magic, lo);
+#if defined(__CUDA_ARCH__)
+        rev0 = __ldg(prefix + r0.pre_offset + lo);
+#else
+        rev0 = prefix[r0.pre_offset + lo];
+#endif
+        k0 = r0.pre_k;
+    }
+    if (r1.pre_pow) {
+        uint32_t lo;
+        a1 = div_magic(a, r1.pre_pow, r1.pre_magic, lo);
+#if defined(__CUDA_ARCH__)
+        rev1 = __ldg(prefix + r1.pre_offset + lo);
+#else
+        rev1 = prefix[r1.pre_offset + lo];
+#endif
+        k1 = r1.pre_k;
+    }
+    // the two chains advance together while both have digits left
+    while (k0 < n0 && k1 < n1) {
         uint32_t d0, d1;
         a0 = div_magic(a0, b0, r0.magic, d0);
         a1 = div_magic(a1, b1, r1.magic, d1);
@@ -175,31 +239,12 @@ QZ_HD V2 owen_scrambled_radical_inv_pair(const SamplerDim r0, const SamplerDim r
         d1 = permutation_element(d1, b1, r1.magic, w1, h1);
         rev0 = rev0 * b0 + d0;
         rev1 = rev1 * b1 + d1;
+        k0++; k1++;
     }
-    for (uint32_t j = k; j < n0; j++) {
-        uint32_t d0;
-        a0 = div_magic(a0, b0, r0.magic, d0);
-        d0 = permutation_element(d0, b0, r0.magic, w0, (uint32_t)mix_bits((uint64_t)r0.hash ^ rev0));
-        rev0 = rev0 * b0 + d0;
-    }
-    for (uint32_t j = k; j < n1; j++) {
-        uint32_t d1;
-        a1 = div_magic(a1, b1, r1.magic, d1);
-        d1 = permutation_element(d1, b1, r1.magic, w1, (uint32_t)mix_bits((uint64_t)r1.hash ^ rev1));
-        rev1 = rev1 * b1 + d1;
-    }
+    if (k0 < n0) rev0 = owen_digits(r0, a0, k0, n0, rev0);
+    if (k1 < n1) rev1 = owen_digits(r1, a1, k1, n1, rev1);
     return v2(std_min(u32_as_float(r0.scale) * (float)rev0, QZ_ONE_MINUS_EPS),
               std_min(u32_as_float(r1.scale) * (float)rev1, QZ_ONE_MINUS_EPS));
-}
-
-QZ_HD SamplerDim load_dim(const SamplerDim* __restrict__ table, uint32_t dim) {
-#if defined(__CUDA_ARCH__)
-    const uint4 raw = __ldg(reinterpret_cast<const uint4*>(table) + dim);
-    SamplerDim rec; rec.base_nd = raw.x; rec.magic = raw.y; rec.hash = raw.z; rec.scale = raw.w;
-    return rec;
-#else
-    return table[dim];
-#endif
 }
 
 // Sampler::sample_1d / sample_2d (sampler.cpp:433-447): dimensions wrap to 2 past the table.
@@ -223,7 +268,7 @@ QZ_HD float sample_1d(const SamplerDim* __restrict__ table, Sampler& smp) {
 }
 QZ_HD V2 sample_2d(const SamplerDim* __restrict__ table, Sampler& smp) {
     const uint32_t d = sample_2d_skip(smp);
-    return owen_scrambled_radical_inv_pair(load_dim(table, d), load_dim(table, d + 1), smp.index);
+    return owen_scrambled_radical_inv_pair(load_dim(table, d), load_dim(table, d + 1), sampler_prefix_array(table), smp.index);
 }
 
 // ---- host-side table construction (runs once per process) ---------------------------
@@ -243,8 +288,33 @@ inline void build_sampler_table(SamplerDim* out /* QZ_N_PRIMES entries */) {
         rec.magic = (uint32_t)((1ull << 32) / n);
         rec.hash = (uint32_t)mix_bits((uint64_t)(1 + (int)(dim << 4)));
         rec.scale = float_as_u32(inv_base_m);
+        rec.pre_pow = 0; rec.pre_magic = 0; rec.pre_offset = 0; rec.pre_k = 0;
         out[dim] = rec;
     }
+}
+
+// Lays the prefix tables of dimensions [2, n_dims) out behind each other: per dimension the
+// largest k < ndigits with base^k <= cap.  Returns the total number of 16-bit entries.
+inline uint32_t plan_sampler_prefix(SamplerDim* recs, uint32_t n_dims, uint32_t cap) {
+    uint32_t total = 0;
+    for (uint32_t dim = 2; dim < n_dims && dim < QZ_N_PRIMES; dim++) {
+        SamplerDim& r = recs[dim];
+        const uint32_t base = r.base_nd & 0xffffu, nd = r.base_nd >> 16;
+        uint32_t k = 0, pw = 1;
+        while (k + 1 < nd && (uint64_t)pw * base <= cap && (uint64_t)pw * base <= 65536ull) { pw *= base; k++; }
+        if (k == 0) continue;
+        r.pre_pow = pw;
+        r.pre_magic = (uint32_t)((1ull << 32) / pw);
+        r.pre_offset = total;
+        r.pre_k = k;
+        total += pw;
+    }
+    return total;
+}
+
+// entry j of a dimension's prefix table
+QZ_HD uint16_t sampler_prefix_entry(const SamplerDim& rec, uint32_t j) {
+    return (uint16_t)owen_digits(rec, j, 0, rec.pre_k, 0);
 }
 
 inline SamplerParams make_sampler_params(int x_res, int y_res) {

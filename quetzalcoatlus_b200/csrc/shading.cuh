@@ -174,7 +174,7 @@ struct SamplesOnTheFly {
         Sampler s; s.index = index; s.dim = 0;
         return sample_dimension(tab, s, dim);
     }
-    QZ_HD V2 two(int, uint32_t dim) const { return owen_scrambled_radical_inv_pair(load_dim(tab, dim), load_dim(tab, dim + 1), index); }
+    QZ_HD V2 two(int, uint32_t dim) const { return owen_scrambled_radical_inv_pair(load_dim(tab, dim), load_dim(tab, dim + 1), sampler_prefix_array(tab), index); }
 };
 
 struct SamplesPrecomputed {

@@ -66,14 +66,36 @@ enum Counter {
 // 64-bit statistics block
 enum Stat { S_RAYS_CLOSEST = 0, S_RAYS_SHADOW = 1, S_SHADE = 2, S_NODES = 3, S_PRIMS = 4, S_PATHS_DONE = 5, S_OVERFLOW = 6, S_WORDS = 8 };
 
+// A field of the per-slot path record: 16-byte elements, QZ_REC_BYTES apart.  b.field[slot]
+// reads and writes like a plain array; the stride is what the layout below is about.
+#define QZ_REC_BYTES 128
+template <class T>
+struct RecField {
+    char* base;
+    __device__ __forceinline__ T& operator[](uint32_t slot) const {
+        return *reinterpret_cast<T*>(base + (size_t)slot * QZ_REC_BYTES);
+    }
+};
+
+// PATH STATE LAYOUT.  A slot owns two 128-byte records (two arrays of cache lines), every field a
+// 16-byte element at a fixed offset:
+//   hot line :  ray_o | ray_d | weight | lambda | hit_a | hit_b | misc | lpdf
+//   side line:  sh_o  | sh_d  | sh_c   | radiance | aov_n | aov_a | samples (8 floats)
+// The shade queue of one material family holds a THIRD of the slots, in slot order but with
+// gaps: with one array per field (the first layout of this pipeline) every 16-byte access of a
+// lane then sat alone in its 32-byte sector and 64-byte DRAM burst, nine different DRAM pages per
+// path, and the shading kernels ran at 2.8 TB/s of mostly wasted sectors, insensitive to
+// occupancy and instruction count (profiles/r01_shading.md).  With the record layout a bounce reads
+// ONE full line and writes back three of its four sectors; what a kernel does not need (the
+// closest-hit stage reads 32 bytes and writes 32) it does not touch, at sector granularity.
 struct WfBuffers {
-    float4 *ray_o, *ray_d;      // o.xyz | ior_scale ; d.xyz | p_b
-    float4 *hit_a, *hit_b;      // t, u, v, primID ; Ng.xyz, geomID (0xffffffff = miss)
-    float4 *weight, *radiance, *lambda, *lpdf;
-    uint4* misc;                // path id, halton index, dim | depth << 16 | flags << 24, rays issued
-    float4 *aov_n, *aov_a;
-    float4 *sh_o, *sh_d, *sh_c;
-    float* samples;             // R_COUNT floats per slot: this bounce's draws, written by k_sample
+    RecField<float4> ray_o, ray_d;      // o.xyz | ior_scale ; d.xyz | p_b
+    RecField<float4> hit_a, hit_b;      // t, u, v, primID ; Ng.xyz, geomID (0xffffffff = miss)
+    RecField<float4> weight, radiance, lambda, lpdf;
+    RecField<uint4> misc;               // path id, halton index, dim | depth << 16 | flags << 24, rays issued
+    RecField<float4> aov_n, aov_a;
+    RecField<float4> sh_o, sh_d, sh_c;
+    RecField<float4> samples;           // R_COUNT floats per slot (two elements): this bounce's draws, written by k_sample
     uint8_t *stage, *fam, *post;  // per-slot tags (StageTag, family queue id or QZ_FAM_NONE, QZ_POST_* bits)
     uint32_t* q_shade[SQ_COUNT];
     uint32_t *q_shadow, *q_done;  // (adjacent in memory order is not required)
@@ -943,7 +965,7 @@ __global__ void __launch_bounds__(256) k_sample(DScene sc, WfBuffers b) {
         bounce_dims(misc.z & 0xffffu, nee, sc.n_lights != 0, dims);
         Sampler smp;
         smp.index = misc.y; smp.dim = 0;
-        b.samples[(size_t)slot * R_COUNT + role] = sample_dimension(sc.sampler_table, smp, dims[role]);
+        reinterpret_cast<float*>(&b.samples[slot])[role] = sample_dimension(sc.sampler_table, smp, dims[role]);
     }
 }
 
@@ -956,7 +978,6 @@ __global__ void __launch_bounds__(128, (KH == KH_DIFFUSE || KH == KH_DIELECTRIC)
 k_shade(DScene sc, WfBuffers b, int queue_id, uint32_t max_bounces) {
     const uint32_t count = b.counters[C_SHADE0 + queue_id];
     const uint32_t* queue = b.q_shade[queue_id];
-    constexpr bool kPdf = KH == KH_DIELECTRIC || KH == KH_ANY;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
         const uint32_t slot = queue[i];
         PathState ps;
@@ -965,7 +986,7 @@ k_shade(DScene sc, WfBuffers b, int queue_id, uint32_t max_bounces) {
         ps.ray.d = v3(d.x, d.y, d.z); ps.p_b = d.w;
         ps.weight = s4(b.weight[slot]);
         ps.lambda = s4(b.lambda[slot]);
-        ps.pdf = kPdf ? s4(b.lpdf[slot]) : spec4(0.0f);
+        ps.pdf = s4(b.lpdf[slot]);   // same 32-byte sector as misc: free to read, and written back whole
         ps.L = spec4(0.0f);
         const uint4 m = b.misc[slot];
         ps.smp.index = m.y;
@@ -992,7 +1013,7 @@ k_shade(DScene sc, WfBuffers b, int queue_id, uint32_t max_bounces) {
             src.tab = sc.sampler_table; src.index = ps.smp.index;
             alive = shade_bounce<KH, FIRST>(sc, ps, aov, hit, max_bounces, sh, src, gain, has_gain);
         } else {
-            const float4* sv = reinterpret_cast<const float4*>(b.samples + (size_t)slot * R_COUNT);
+            const float4* sv = &b.samples[slot];
             const float4 s0 = sv[0], s1 = sv[1];
             SamplesPrecomputed src;
             src.v[0] = s0.x; src.v[1] = s0.y; src.v[2] = s0.z; src.v[3] = s0.w;
@@ -1017,9 +1038,11 @@ k_shade(DScene sc, WfBuffers b, int queue_id, uint32_t max_bounces) {
         if (alive) {
             b.ray_o[slot] = f4(ps.ray.o.x, ps.ray.o.y, ps.ray.o.z, ps.ior_scale);
             b.ray_d[slot] = f4(ps.ray.d.x, ps.ray.d.y, ps.ray.d.z, ps.p_b);
+            // weight and lambda share a sector: writing both keeps it a full-sector store
             b.weight[slot] = f4(ps.weight);
+            b.lambda[slot] = f4(ps.lambda);
         }
-        if (kPdf) b.lpdf[slot] = f4(ps.pdf);
+        b.lpdf[slot] = f4(ps.pdf);
         b.misc[slot] = make_uint4(m.x, ps.smp.index, ps.smp.dim | (ps.depth << 16) | (ps.flags << 24), ps.n_rays);
         b.post[slot] = (uint8_t)post;
         b.stage[slot] = alive ? (ps.depth == 0 ? ST_TRACE_FIRST : ST_TRACE) : ST_EMPTY;

@@ -35,13 +35,24 @@ struct SeqExec {
 
 thread_local std::string g_error;
 SeqExec g_exec;
-SamplerDim g_sampler_table[QZ_N_PRIMES];
+// records followed by the prefix tables (sampler.cuh); the emulation tabulates a few dimensions
+// with a small cap -- enough to run the prefixed evaluation path through every CPU parity test
+std::vector<SamplerDim> g_sampler_storage;
+SamplerDim* g_sampler_table = nullptr;
 float g_rho_tab[16 * 8];
 bool g_tables_ready = false;
 
 void ensure_tables() {
     if (g_tables_ready) return;
-    build_sampler_table(g_sampler_table);
+    std::vector<SamplerDim> recs(QZ_N_PRIMES);
+    build_sampler_table(recs.data());
+    const uint32_t n_prefix = plan_sampler_prefix(recs.data(), 40, 4096);
+    g_sampler_storage.assign(QZ_N_PRIMES + (n_prefix * sizeof(uint16_t) + sizeof(SamplerDim) - 1) / sizeof(SamplerDim) + 1, SamplerDim{});
+    std::copy(recs.begin(), recs.end(), g_sampler_storage.begin());
+    g_sampler_table = g_sampler_storage.data();
+    uint16_t* prefix = reinterpret_cast<uint16_t*>(g_sampler_table + QZ_N_PRIMES);
+    for (uint32_t d = 0; d < QZ_N_PRIMES; d++)
+        for (uint32_t j = 0; j < recs[d].pre_pow; j++) prefix[recs[d].pre_offset + j] = sampler_prefix_entry(recs[d], j);
     build_rho_table(g_rho_tab);
     g_tables_ready = true;
 }
