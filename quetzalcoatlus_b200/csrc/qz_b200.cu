@@ -12,6 +12,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -425,7 +426,8 @@ static int render_impl(qz_scene s, const qz_camera* camera, uint32_t n_samples, 
     int n_sm = 148;
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, s->device);
     const int trav_blocks = n_sm * 8;   // persistent: 8 CTAs of 4 warps per SM
-    const int shade_blocks = n_sm * 8;
+    static const int shade_per_sm = [] { const char* e = std::getenv("QZ_SHADE_BLOCKS_PER_SM"); int v = e ? std::atoi(e) : 0; return v > 0 ? v : 8; }();
+    const int shade_blocks = n_sm * shade_per_sm;
 
     if (!wm.ev_begin) {
         QZ_CUDA(cudaEventCreate(&wm.ev_begin)); QZ_CUDA(cudaEventCreate(&wm.ev_end));

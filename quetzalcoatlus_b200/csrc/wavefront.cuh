@@ -116,6 +116,15 @@ struct PassParams {
     SamplerParams spar;
 };
 
+// start fetching the 128-byte line that holds p
+__device__ __forceinline__ void prefetch_line(const void* p) {
+#ifndef QZ_PREFETCH_L2
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#else
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#endif
+}
+
 // ------------------------------------------------------------------ SoA helpers
 __device__ __forceinline__ float4 f4(float a, float b, float c, float d) { return make_float4(a, b, c, d); }
 __device__ __forceinline__ float4 f4(const Spec4& s) { return make_float4(s.v[0], s.v[1], s.v[2], s.v[3]); }
@@ -978,8 +987,22 @@ __global__ void __launch_bounds__(128, (KH == KH_DIFFUSE || KH == KH_DIELECTRIC)
 k_shade(DScene sc, WfBuffers b, int queue_id, uint32_t max_bounces) {
     const uint32_t count = b.counters[C_SHADE0 + queue_id];
     const uint32_t* queue = b.q_shade[queue_id];
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
-        const uint32_t slot = queue[i];
+    // A bounce is: read one record, ~2000 dependent instructions, write it back -- nothing in
+    // it overlaps the read.  So the read of the thread's NEXT path is started a whole bounce
+    // early: its queue entry is loaded two trips ahead, its record lines prefetched one trip ahead.
+    const uint32_t stride = gridDim.x * blockDim.x;
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t slot_cur = i < count ? queue[i] : 0u;
+    uint32_t slot_next = i + stride < count ? queue[i + stride] : 0u;
+    for (; i < count; i += stride) {
+        const uint32_t slot = slot_cur;
+        const uint32_t slot_after = (i + 2u * stride < count && i + 2u * stride >= i) ? queue[i + 2u * stride] : 0u;
+        if (i + stride < count) {
+            prefetch_line(&b.ray_o[slot_next]);
+            if (KH != KH_ANY) prefetch_line(&b.samples[slot_next]);
+        }
+        slot_cur = slot_next;
+        slot_next = slot_after;
         PathState ps;
         const float4 o = b.ray_o[slot], d = b.ray_d[slot];
         ps.ray.o = v3(o.x, o.y, o.z); ps.ior_scale = o.w;
