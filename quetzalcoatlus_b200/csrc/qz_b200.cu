@@ -243,6 +243,8 @@ struct DevBuf {
 // Working memory of render(): allocated on first use, kept with the scene and re-used by later
 // calls of the same or a smaller size (cudaMalloc/cudaFree of gigabytes per call would otherwise
 // dominate the end-to-end time of short renders).
+#define QZ_MAX_PIPELINES 4
+
 struct WorkMem {
     DevBuf rec_hot, rec_side, qbufs[10], tags[3], counters, statsb, res_a, res_b, res_c, rowsb, sensor, acc;
     uint32_t pool = 0;
@@ -253,11 +255,17 @@ struct WorkMem {
     size_t h_film_bytes = 0;
     std::vector<cudaEvent_t> stage_events;
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_a = nullptr, ev_b = nullptr;
+    cudaStream_t pipe_stream[QZ_MAX_PIPELINES] = {};
+    cudaEvent_t pipe_done[QZ_MAX_PIPELINES] = {};
+    cudaEvent_t fork = nullptr;
     ~WorkMem() {
         if (h_counters) cudaFreeHost(h_counters);
         if (h_film) cudaFreeHost(h_film);
         for (cudaEvent_t e : {ev_begin, ev_end, ev_a, ev_b}) if (e) cudaEventDestroy(e);
         for (cudaEvent_t e : stage_events) cudaEventDestroy(e);
+        for (cudaStream_t q : pipe_stream) if (q) cudaStreamDestroy(q);
+        for (cudaEvent_t e : pipe_done) if (e) cudaEventDestroy(e);
+        if (fork) cudaEventDestroy(fork);
     }
 };
 
@@ -377,16 +385,36 @@ static int render_impl(qz_scene s, const qz_camera* camera, uint32_t n_samples, 
     pool = (uint32_t)std::min<uint64_t>(pool, cells);
     pool = std::max(pool, 1u);
 
+    const bool count_trav = (flags & QZ_FLAG_COUNT_TRAVERSAL) != 0;
+    const bool stage_timing = (flags & QZ_FLAG_STAGE_TIMING) != 0;
+    const bool lane_trav = (flags & QZ_FLAG_LANE_TRAVERSAL) != 0;  // first-generation per-lane kernels (evidence arm)
+    const bool oct_trav = (flags & QZ_FLAG_OCTET_TRAVERSAL) != 0;  // eight lanes per ray (evidence arm); default: phase-scheduled
+
+    // PIPELINES.  The pool is cut into P independent sub-pools, each with its own queues, tags and
+    // counters and its own stream, all drawing new paths from one shared cursor.  Every stage kernel
+    // is a persistent grid-stride loop, so it is launched with 1/P of the CTAs an SM can hold: the
+    // stages of different pipelines then run SIDE BY SIDE on every SM -- the integer-bound sampler
+    // and the slab tests of one pipeline issue in the slots the latency-bound shading kernels of
+    // the other leave empty, and one pipeline's tail overlaps the other's next stage.  Stage timing
+    // (one event pair per stage) only makes sense serially, so it uses one pipeline.
+    static const int env_pipes = [] { const char* e = std::getenv("QZ_PIPELINES"); int v = e ? std::atoi(e) : 0; return v; }();
+    int P = env_pipes > 0 ? env_pipes : 3;
+    if (stage_timing || pool < 65536u) P = 1;
+    P = std::min(P, QZ_MAX_PIPELINES);
+    const uint32_t sub_pool = (pool + (uint32_t)P - 1) / (uint32_t)P;
+    const uint32_t tag_stride = ((sub_pool + 15u) & ~15u) + 16u;   // per-pipeline slice of the tag arrays (16-byte aligned, padded)
+    const uint32_t q_stride = (sub_pool + 3u) & ~3u;
+
     // ---- working memory (cached in the scene handle)
     WorkMem& wm = s->work;
     DevBuf(&qbufs)[10] = wm.qbufs;
     DevBuf &counters = wm.counters, &statsb = wm.statsb, &res_a = wm.res_a, &res_b = wm.res_b, &res_c = wm.res_c,
            &rowsb = wm.rowsb, &sensor = wm.sensor, &acc = wm.acc;
-    QZ_CUDA(wm.rec_hot.reserve((size_t)pool * QZ_REC_BYTES));
-    QZ_CUDA(wm.rec_side.reserve((size_t)pool * QZ_REC_BYTES));
-    for (auto& buf : qbufs) QZ_CUDA(buf.reserve((size_t)pool * 4));
-    for (auto& buf : wm.tags) QZ_CUDA(buf.reserve((size_t)pool + 16));
-    QZ_CUDA(counters.reserve(C_WORDS * 4));
+    QZ_CUDA(wm.rec_hot.reserve((size_t)sub_pool * P * QZ_REC_BYTES));
+    QZ_CUDA(wm.rec_side.reserve((size_t)sub_pool * P * QZ_REC_BYTES));
+    for (auto& buf : qbufs) QZ_CUDA(buf.reserve((size_t)q_stride * P * 4));
+    for (auto& buf : wm.tags) QZ_CUDA(buf.reserve((size_t)tag_stride * P));
+    QZ_CUDA(counters.reserve((size_t)C_WORDS * 4 * QZ_MAX_PIPELINES));
     QZ_CUDA(statsb.reserve(S_WORDS * 8));
     QZ_CUDA(res_a.reserve(cells * 16));
     QZ_CUDA(res_b.reserve(cells * 16));
@@ -399,44 +427,57 @@ static int render_impl(qz_scene s, const qz_camera* camera, uint32_t n_samples, 
     QZ_CUDA(cudaMemcpyAsync(sensor.p, camera->sensor_rgb, 3 * 471 * 4, cudaMemcpyHostToDevice, stream));
     QZ_CUDA(cudaMemsetAsync(statsb.p, 0, S_WORDS * 8, stream));
 
-    WfBuffers b{};
     static_assert(R_COUNT * sizeof(float) == 32, "the samples of a bounce fill the last two elements of the side line");
-    char* hot = wm.rec_hot.as<char>();
-    char* side = wm.rec_side.as<char>();
-    b.ray_o.base = hot + 0;   b.ray_d.base = hot + 16;  b.weight.base = hot + 32;    b.lambda.base = hot + 48;
-    b.hit_a.base = hot + 64;  b.hit_b.base = hot + 80;  b.misc.base = hot + 96;      b.lpdf.base = hot + 112;
-    b.sh_o.base = side + 0;   b.sh_d.base = side + 16;  b.sh_c.base = side + 32;     b.radiance.base = side + 48;
-    b.aov_n.base = side + 64; b.aov_a.base = side + 80; b.samples.base = side + 96;
-    b.stage = wm.tags[0].as<uint8_t>(); b.fam = wm.tags[1].as<uint8_t>(); b.post = wm.tags[2].as<uint8_t>();
-    for (int k = 0; k < SQ_COUNT; k++) b.q_shade[k] = qbufs[k].as<uint32_t>();
-    b.q_shadow = qbufs[8].as<uint32_t>(); b.q_done = qbufs[9].as<uint32_t>();
-    b.counters = counters.as<uint32_t>();
-    b.stats = statsb.as<unsigned long long>();
-    b.res_a = res_a.as<float4>(); b.res_b = res_b.as<float4>(); b.res_c = res_c.as<float>();
-    b.pool = pool;
+    WfBuffers bufs[QZ_MAX_PIPELINES];
+    for (int p = 0; p < P; p++) {
+        WfBuffers& b = bufs[p];
+        b = WfBuffers{};
+        char* hot = wm.rec_hot.as<char>() + (size_t)p * sub_pool * QZ_REC_BYTES;
+        char* side = wm.rec_side.as<char>() + (size_t)p * sub_pool * QZ_REC_BYTES;
+        b.ray_o.base = hot + 0;   b.ray_d.base = hot + 16;  b.weight.base = hot + 32;    b.lambda.base = hot + 48;
+        b.hit_a.base = hot + 64;  b.hit_b.base = hot + 80;  b.misc.base = hot + 96;      b.lpdf.base = hot + 112;
+        b.sh_o.base = side + 0;   b.sh_d.base = side + 16;  b.sh_c.base = side + 32;     b.radiance.base = side + 48;
+        b.aov_n.base = side + 64; b.aov_a.base = side + 80; b.samples.base = side + 96;
+        b.stage = wm.tags[0].as<uint8_t>() + (size_t)p * tag_stride;
+        b.fam = wm.tags[1].as<uint8_t>() + (size_t)p * tag_stride;
+        b.post = wm.tags[2].as<uint8_t>() + (size_t)p * tag_stride;
+        for (int k = 0; k < SQ_COUNT; k++) b.q_shade[k] = qbufs[k].as<uint32_t>() + (size_t)p * q_stride;
+        b.q_shadow = qbufs[8].as<uint32_t>() + (size_t)p * q_stride;
+        b.q_done = qbufs[9].as<uint32_t>() + (size_t)p * q_stride;
+        b.counters = counters.as<uint32_t>() + (size_t)p * C_WORDS;
+        b.next_path = counters.as<uint32_t>() + C_NEXT_PATH;   // pipeline 0's block holds the shared cursor
+        b.stats = statsb.as<unsigned long long>();
+        b.res_a = res_a.as<float4>(); b.res_b = res_b.as<float4>(); b.res_c = res_c.as<float>();
+        b.pool = sub_pool;
+    }
 
     DCamera cam = make_camera(camera, sensor.as<float>());
-    const bool count_trav = (flags & QZ_FLAG_COUNT_TRAVERSAL) != 0;
-    const bool stage_timing = (flags & QZ_FLAG_STAGE_TIMING) != 0;
-    const bool lane_trav = (flags & QZ_FLAG_LANE_TRAVERSAL) != 0;  // first-generation per-lane kernels (evidence arm)
-    const bool oct_trav = (flags & QZ_FLAG_OCTET_TRAVERSAL) != 0;  // eight lanes per ray (evidence arm); default: phase-scheduled
     // tiny scenes skip the BVH (k_closest_flat); counting runs and QZ_FLAG_FORCE_BVH keep the traversal kernels
     const bool flat = sc.n_prims <= QZ_FLAT_MAX_PRIMS && sc.n_prims > 0 && !count_trav && !(flags & QZ_FLAG_FORCE_BVH);
 
+    PassParams pp_cur{};   // the pass being rendered (captured by the iteration lambda)
     int n_sm = 148;
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, s->device);
-    const int trav_blocks = n_sm * 8;   // persistent: 8 CTAs of 4 warps per SM
-    static const int shade_per_sm = [] { const char* e = std::getenv("QZ_SHADE_BLOCKS_PER_SM"); int v = e ? std::atoi(e) : 0; return v > 0 ? v : 8; }();
-    const int shade_blocks = n_sm * shade_per_sm;
+    static const int env_per_sm = [] { const char* e = std::getenv("QZ_BLOCKS_PER_SM"); int v = e ? std::atoi(e) : 0; return v; }();
+    const int per_sm = env_per_sm > 0 ? env_per_sm : (P == 1 ? 8 : (P == 2 ? 4 : (P == 3 ? 3 : 2)));
+    const int trav_blocks = n_sm * per_sm;   // persistent CTAs of 4 warps
+    const int shade_blocks = n_sm * per_sm;
 
     if (!wm.ev_begin) {
         QZ_CUDA(cudaEventCreate(&wm.ev_begin)); QZ_CUDA(cudaEventCreate(&wm.ev_end));
         QZ_CUDA(cudaEventCreate(&wm.ev_a)); QZ_CUDA(cudaEventCreate(&wm.ev_b));
-        QZ_CUDA(cudaMallocHost(&wm.h_counters, C_WORDS * 4));
+        QZ_CUDA(cudaMallocHost(&wm.h_counters, (size_t)C_WORDS * 4 * QZ_MAX_PIPELINES));
+        for (int p = 0; p < QZ_MAX_PIPELINES; p++) {
+            QZ_CUDA(cudaStreamCreateWithFlags(&wm.pipe_stream[p], cudaStreamNonBlocking));
+            QZ_CUDA(cudaEventCreateWithFlags(&wm.pipe_done[p], cudaEventDisableTiming));
+        }
+        QZ_CUDA(cudaEventCreateWithFlags(&wm.fork, cudaEventDisableTiming));
     }
-    cudaEvent_t ev_begin = wm.ev_begin, ev_end = wm.ev_end, ev_a = wm.ev_a, ev_b = wm.ev_b;
-    uint32_t* h_counters = wm.h_counters;
+    cudaEvent_t ev_begin = wm.ev_begin, ev_end = wm.ev_end;
     QZ_CUDA(cudaEventRecord(ev_begin, stream));
+    // with one pipeline everything runs on the caller's stream; otherwise the pipelines fork from it and join back
+    cudaStream_t ps[QZ_MAX_PIPELINES];
+    for (int p = 0; p < P; p++) ps[p] = P == 1 ? stream : wm.pipe_stream[p];
 
     // Stage timing: events are recorded asynchronously between the stages (no host sync inside
     // the pipeline) and read back once per pass, so the figures are device time per stage of the
@@ -462,15 +503,76 @@ static int render_impl(qz_scene s, const qz_camera* camera, uint32_t n_samples, 
         ev_used = 0;
         ev_target.clear();
     };
-    auto timed = [&](float& acc_ms, auto&& launch) -> cudaError_t {
+    auto timed = [&](cudaStream_t q, float& acc_ms, auto&& launch) -> cudaError_t {
         if (!stage_timing) { launch(); return cudaGetLastError(); }
         cudaEvent_t a = next_event(), c = next_event();
-        cudaEventRecord(a, stream);
+        cudaEventRecord(a, q);
         launch();
-        cudaEventRecord(c, stream);
+        cudaEventRecord(c, q);
         ev_target.push_back(&acc_ms);
         if (ev_used >= 8192) flush_events();
         return cudaGetLastError();
+    };
+
+    const int bin_blocks = (int)std::min<uint32_t>((sub_pool + 2047u) / 2048u, (uint32_t)n_sm * 8u);
+    // one wavefront iteration of pipeline p
+    auto enqueue_iteration = [&](int p) -> cudaError_t {
+        const WfBuffers& b = bufs[p];
+        cudaStream_t q = ps[p];
+        cudaError_t e;
+        e = timed(q, st.ms_closest, [&] {
+            if (flat) k_closest_flat<<<shade_blocks, 256, 0, q>>>(sc, b, flags);
+            else if (lane_trav && count_trav) k_closest_hit<true><<<trav_blocks, 128, 0, q>>>(sc, b, flags);
+            else if (lane_trav) k_closest_hit<false><<<trav_blocks, 128, 0, q>>>(sc, b, flags);
+            else if (oct_trav && count_trav) k_trace_oct<false, true><<<trav_blocks, 128, 0, q>>>(sc, b, flags);
+            else if (oct_trav) k_trace_oct<false, false><<<trav_blocks, 128, 0, q>>>(sc, b, flags);
+            else if (count_trav) k_trace_lane<false, true><<<trav_blocks, 128, 0, q>>>(sc, b, flags);
+            else k_trace_lane<false, false><<<trav_blocks, 128, 0, q>>>(sc, b, flags);
+        });
+        if (e != cudaSuccess) return e;
+        e = timed(q, st.ms_other, [&] {
+            k_bin<SQ_COUNT, true><<<bin_blocks, 256, 0, q>>>(b.fam, nullptr, b.pool, b.counters + C_SHADE0, b, 0);
+        });
+        if (e != cudaSuccess) return e;
+        if (!(flags & QZ_FLAG_UNSORTED_SHADING)) {
+            e = timed(q, st.ms_sample, [&] { k_sample<<<shade_blocks * 2, 256, 0, q>>>(sc, b); });
+            if (e != cudaSuccess) return e;
+        }
+        e = timed(q, st.ms_shade, [&] {
+            if (flags & QZ_FLAG_UNSORTED_SHADING) {
+                k_shade<KH_ANY, -1><<<shade_blocks, 128, 0, q>>>(sc, b, SQ_MISC, max_bounces);
+            } else {
+                k_shade<KH_ANY, 1><<<shade_blocks, 128, 0, q>>>(sc, b, SQ_FAMILIES + SQ_MISC, max_bounces);
+                k_shade<KH_DIFFUSE, 1><<<shade_blocks, 128, 0, q>>>(sc, b, SQ_FAMILIES + SQ_DIFFUSE, max_bounces);
+                k_shade<KH_CONDUCTOR, 1><<<shade_blocks, 128, 0, q>>>(sc, b, SQ_FAMILIES + SQ_CONDUCTOR, max_bounces);
+                k_shade<KH_DIELECTRIC, 1><<<shade_blocks, 128, 0, q>>>(sc, b, SQ_FAMILIES + SQ_DIELECTRIC, max_bounces);
+                k_shade<KH_ANY, 0><<<shade_blocks, 128, 0, q>>>(sc, b, SQ_MISC, max_bounces);
+                k_shade<KH_DIFFUSE, 0><<<shade_blocks, 128, 0, q>>>(sc, b, SQ_DIFFUSE, max_bounces);
+                k_shade<KH_CONDUCTOR, 0><<<shade_blocks, 128, 0, q>>>(sc, b, SQ_CONDUCTOR, max_bounces);
+                k_shade<KH_DIELECTRIC, 0><<<shade_blocks, 128, 0, q>>>(sc, b, SQ_DIELECTRIC, max_bounces);
+            }
+        });
+        if (e != cudaSuccess) return e;
+        e = timed(q, st.ms_other, [&] {
+            k_bin<2, false><<<bin_blocks, 256, 0, q>>>(b.post, b.fam, b.pool, b.counters + C_SHADOW, b, 1);
+        });
+        if (e != cudaSuccess) return e;
+        e = timed(q, st.ms_shadow, [&] {
+            if (flat) k_shadow_flat<<<shade_blocks, 256, 0, q>>>(sc, b);
+            else if (lane_trav && count_trav) k_shadow<true><<<trav_blocks, 128, 0, q>>>(sc, b);
+            else if (lane_trav) k_shadow<false><<<trav_blocks, 128, 0, q>>>(sc, b);
+            else if (oct_trav && count_trav) k_trace_oct<true, true><<<trav_blocks, 128, 0, q>>>(sc, b, flags);
+            else if (oct_trav) k_trace_oct<true, false><<<trav_blocks, 128, 0, q>>>(sc, b, flags);
+            else if (count_trav) k_trace_lane<true, true><<<trav_blocks, 128, 0, q>>>(sc, b, flags);
+            else k_trace_lane<true, false><<<trav_blocks, 128, 0, q>>>(sc, b, flags);
+        });
+        if (e != cudaSuccess) return e;
+        e = timed(q, st.ms_other, [&] {
+            k_finish<<<shade_blocks, 256, 0, q>>>(sc, cam, b, pp_cur);
+            k_next_iteration<<<1, 32, 0, q>>>(b);
+        });
+        st.kernel_launches += (flags & QZ_FLAG_UNSORTED_SHADING) ? 7 : 15;
+        return e;
     };
 
     int rc = QZ_OK;
@@ -484,77 +586,61 @@ static int render_impl(qz_scene s, const qz_camera* camera, uint32_t n_samples, 
         pp.owned_rows = rowsb.as<uint32_t>();
         pp.width = W; pp.height = H;
         pp.spar = spar;
+        pp_cur = pp;
 
-        const uint32_t first = std::min<uint32_t>(pool, pp.total);
-        uint32_t init[C_WORDS] = {0};
-        init[C_NEXT_PATH] = first;
-        QZ_CUDA(cudaMemcpyAsync(b.counters, init, sizeof(init), cudaMemcpyHostToDevice, stream));
-        k_generate<<<shade_blocks, 256, 0, stream>>>(sc, cam, b, pp, first);
-        st.kernel_launches++;
+        // initial fill: pipeline p starts with the next `first[p]` path ids; the shared cursor continues behind them
+        uint32_t init[C_WORDS * QZ_MAX_PIPELINES] = {0};
+        uint32_t first[QZ_MAX_PIPELINES], handed = 0;
+        for (int p = 0; p < P; p++) { first[p] = std::min<uint32_t>(sub_pool, pp.total - handed); handed += first[p]; }
+        init[C_NEXT_PATH] = handed;
+        QZ_CUDA(cudaMemcpyAsync(counters.p, init, sizeof(uint32_t) * C_WORDS * P, cudaMemcpyHostToDevice, stream));
+        if (P > 1) {
+            QZ_CUDA(cudaEventRecord(wm.fork, stream));
+            for (int p = 0; p < P; p++) QZ_CUDA(cudaStreamWaitEvent(ps[p], wm.fork, 0));
+        }
+        uint32_t id0 = 0;
+        for (int p = 0; p < P; p++) {
+            k_generate<<<shade_blocks, 256, 0, ps[p]>>>(sc, cam, bufs[p], pp, id0, first[p]);
+            id0 += first[p];
+            st.kernel_launches++;
+        }
         QZ_CUDA(cudaGetLastError());
 
+        bool live[QZ_MAX_PIPELINES];
+        for (int p = 0; p < P; p++) live[p] = first[p] > 0;
         uint64_t it = 0;
-        const int bin_blocks = (int)std::min<uint32_t>((pool + 2047u) / 2048u, (uint32_t)n_sm * 8u);
         for (;;) {
-            QZ_CUDA(timed(st.ms_closest, [&] {
-                if (flat) k_closest_flat<<<shade_blocks, 256, 0, stream>>>(sc, b, flags);
-                else if (lane_trav && count_trav) k_closest_hit<true><<<trav_blocks, 128, 0, stream>>>(sc, b, flags);
-                else if (lane_trav) k_closest_hit<false><<<trav_blocks, 128, 0, stream>>>(sc, b, flags);
-                else if (oct_trav && count_trav) k_trace_oct<false, true><<<trav_blocks, 128, 0, stream>>>(sc, b, flags);
-                else if (oct_trav) k_trace_oct<false, false><<<trav_blocks, 128, 0, stream>>>(sc, b, flags);
-                else if (count_trav) k_trace_lane<false, true><<<trav_blocks, 128, 0, stream>>>(sc, b, flags);
-                else k_trace_lane<false, false><<<trav_blocks, 128, 0, stream>>>(sc, b, flags);
-            }));
-            QZ_CUDA(timed(st.ms_other, [&] {
-                k_bin<SQ_COUNT, true><<<bin_blocks, 256, 0, stream>>>(b.fam, nullptr, pool, b.counters + C_SHADE0, b, 0);
-            }));
-            if (!(flags & QZ_FLAG_UNSORTED_SHADING)) {
-                QZ_CUDA(timed(st.ms_sample, [&] { k_sample<<<shade_blocks * 2, 256, 0, stream>>>(sc, b); }));
+            bool any = false;
+            for (int p = 0; p < P; p++) {
+                if (!live[p]) continue;
+                any = true;
+                QZ_CUDA(enqueue_iteration(p));
             }
-            QZ_CUDA(timed(st.ms_shade, [&] {
-                if (flags & QZ_FLAG_UNSORTED_SHADING) {
-                    k_shade<KH_ANY, -1><<<shade_blocks, 128, 0, stream>>>(sc, b, SQ_MISC, max_bounces);
-                } else {
-                    k_shade<KH_ANY, 1><<<shade_blocks, 128, 0, stream>>>(sc, b, SQ_FAMILIES + SQ_MISC, max_bounces);
-                    k_shade<KH_DIFFUSE, 1><<<shade_blocks, 128, 0, stream>>>(sc, b, SQ_FAMILIES + SQ_DIFFUSE, max_bounces);
-                    k_shade<KH_CONDUCTOR, 1><<<shade_blocks, 128, 0, stream>>>(sc, b, SQ_FAMILIES + SQ_CONDUCTOR, max_bounces);
-                    k_shade<KH_DIELECTRIC, 1><<<shade_blocks, 128, 0, stream>>>(sc, b, SQ_FAMILIES + SQ_DIELECTRIC, max_bounces);
-                    k_shade<KH_ANY, 0><<<shade_blocks, 128, 0, stream>>>(sc, b, SQ_MISC, max_bounces);
-                    k_shade<KH_DIFFUSE, 0><<<shade_blocks, 128, 0, stream>>>(sc, b, SQ_DIFFUSE, max_bounces);
-                    k_shade<KH_CONDUCTOR, 0><<<shade_blocks, 128, 0, stream>>>(sc, b, SQ_CONDUCTOR, max_bounces);
-                    k_shade<KH_DIELECTRIC, 0><<<shade_blocks, 128, 0, stream>>>(sc, b, SQ_DIELECTRIC, max_bounces);
-                }
-            }));
-            QZ_CUDA(timed(st.ms_other, [&] {
-                k_bin<2, false><<<bin_blocks, 256, 0, stream>>>(b.post, b.fam, pool, b.counters + C_SHADOW, b, 1);
-            }));
-            QZ_CUDA(timed(st.ms_shadow, [&] {
-                if (flat) k_shadow_flat<<<shade_blocks, 256, 0, stream>>>(sc, b);
-                else if (lane_trav && count_trav) k_shadow<true><<<trav_blocks, 128, 0, stream>>>(sc, b);
-                else if (lane_trav) k_shadow<false><<<trav_blocks, 128, 0, stream>>>(sc, b);
-                else if (oct_trav && count_trav) k_trace_oct<true, true><<<trav_blocks, 128, 0, stream>>>(sc, b, flags);
-                else if (oct_trav) k_trace_oct<true, false><<<trav_blocks, 128, 0, stream>>>(sc, b, flags);
-                else if (count_trav) k_trace_lane<true, true><<<trav_blocks, 128, 0, stream>>>(sc, b, flags);
-                else k_trace_lane<true, false><<<trav_blocks, 128, 0, stream>>>(sc, b, flags);
-            }));
-            QZ_CUDA(timed(st.ms_other, [&] {
-                k_finish<<<shade_blocks, 256, 0, stream>>>(sc, cam, b, pp);
-                k_next_iteration<<<1, 32, 0, stream>>>(b);
-            }));
-            st.kernel_launches += (flags & QZ_FLAG_UNSORTED_SHADING) ? 7 : 15;
+            if (!any) break;
             st.iterations++;
             it++;
-            // the active count is read back every 4th iteration (every iteration would serialise host and device)
+            // the active counts are read back every 4th iteration (every iteration would serialise host and device);
+            // while the host waits for one pipeline the others still have their four iterations queued
             if ((it & 3u) == 0) {
-                QZ_CUDA(cudaMemcpyAsync(h_counters, b.counters, C_WORDS * 4, cudaMemcpyDeviceToHost, stream));
-                QZ_CUDA(cudaStreamSynchronize(stream));
-                if (h_counters[C_ACTIVE] == 0) break;
+                for (int p = 0; p < P; p++)
+                    if (live[p]) QZ_CUDA(cudaMemcpyAsync(wm.h_counters + (size_t)p * C_WORDS, bufs[p].counters, C_WORDS * 4, cudaMemcpyDeviceToHost, ps[p]));
+                for (int p = 0; p < P; p++) {
+                    if (!live[p]) continue;
+                    QZ_CUDA(cudaStreamSynchronize(ps[p]));
+                    if (wm.h_counters[(size_t)p * C_WORDS + C_ACTIVE] == 0) live[p] = false;
+                }
             }
             if (it > 1000000ull) { rc = fail(QZ_ERR_CUDA, "wavefront did not terminate"); break; }
         }
         if (rc != QZ_OK) break;
+        if (P > 1) {
+            for (int p = 0; p < P; p++) {
+                QZ_CUDA(cudaEventRecord(wm.pipe_done[p], ps[p]));
+                QZ_CUDA(cudaStreamWaitEvent(stream, wm.pipe_done[p], 0));
+            }
+        }
         const bool first_pass = s_begin == 0, last_pass = s_begin + pp.s_count >= n_samples;
-        k_film<<<shade_blocks, 256, 0, stream>>>(b, pp, acc.as<float>(), first_pass, last_pass, n_samples, d_color, d_normal, d_albedo);
+        k_film<<<n_sm * 8, 256, 0, stream>>>(bufs[0], pp, acc.as<float>(), first_pass, last_pass, n_samples, d_color, d_normal, d_albedo);
         st.kernel_launches++;
         QZ_CUDA(cudaGetLastError());
     }
@@ -563,7 +649,7 @@ static int render_impl(qz_scene s, const qz_camera* camera, uint32_t n_samples, 
     if (stage_timing) flush_events();
     QZ_CUDA(cudaEventElapsedTime(&st.ms_total, ev_begin, ev_end));
     unsigned long long h_stats[S_WORDS];
-    QZ_CUDA(cudaMemcpy(h_stats, b.stats, sizeof(h_stats), cudaMemcpyDeviceToHost));
+    QZ_CUDA(cudaMemcpy(h_stats, statsb.p, sizeof(h_stats), cudaMemcpyDeviceToHost));
     st.paths = (uint64_t)n_pix * n_samples;
     st.rays_closest = h_stats[S_RAYS_CLOSEST];
     st.rays_shadow = h_stats[S_RAYS_SHADOW];

@@ -60,7 +60,7 @@ enum Counter {
     C_SHADE0 = 2,                         // .. C_SHADE0 + SQ_COUNT - 1
     C_SHADOW = 10, C_DONE = 11,           // (adjacent: k_bin<2, true> fills both)
     C_CURSOR_TRACE = 12, C_CURSOR_SHADOW = 13,
-    C_NEXT_PATH = 14,                     // next path id of the pass to hand out
+    C_NEXT_PATH = 14,                     // (pipeline 0's block only) next path id of the pass to hand out
     C_WORDS = 16
 };
 // 64-bit statistics block
@@ -99,8 +99,9 @@ struct WfBuffers {
     uint8_t *stage, *fam, *post;  // per-slot tags (StageTag, family queue id or QZ_FAM_NONE, QZ_POST_* bits)
     uint32_t* q_shade[SQ_COUNT];
     uint32_t *q_shadow, *q_done;  // (adjacent in memory order is not required)
-    uint32_t* counters;
-    unsigned long long* stats;
+    uint32_t* counters;         // this pipeline's counter block
+    uint32_t* next_path;        // next path id of the pass to hand out (shared by all pipelines)
+    unsigned long long* stats;  // shared by all pipelines (atomics)
     float4 *res_a, *res_b;      // per pixel-sample: (color rgb, normal.x), (albedo rgb, normal.y)
     float* res_c;               // normal.z
     uint32_t pool;
@@ -185,10 +186,10 @@ __device__ __forceinline__ void init_slot(const DScene& sc, const DCamera& cam, 
 }
 
 // ------------------------------------------------------------------ kernels
-__global__ void __launch_bounds__(256) k_generate(DScene sc, DCamera cam, WfBuffers b, PassParams pp, uint32_t n) {
+__global__ void __launch_bounds__(256) k_generate(DScene sc, DCamera cam, WfBuffers b, PassParams pp, uint32_t first_id, uint32_t n) {
     for (uint32_t i = n + blockIdx.x * blockDim.x + threadIdx.x; i < b.pool; i += gridDim.x * blockDim.x) b.stage[i] = ST_EMPTY;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        init_slot(sc, cam, b, pp, i, i);
+        init_slot(sc, cam, b, pp, i, first_id + i);
         b.stage[i] = ST_TRACE_FIRST;
     }
 }
@@ -1090,7 +1091,7 @@ __global__ void __launch_bounds__(256) k_finish(DScene sc, DCamera cam, WfBuffer
         const int lane = threadIdx.x & 31;
         const int leader = __ffs(peers) - 1;
         uint32_t base = 0;
-        if (lane == leader) base = atomicAdd(&b.counters[C_NEXT_PATH], (uint32_t)__popc(peers));
+        if (lane == leader) base = atomicAdd(b.next_path, (uint32_t)__popc(peers));
         base = __shfl_sync(peers, base, leader);
         const uint32_t next_id = base + __popc(peers & ((1u << lane) - 1u));
         if (next_id < pp.total) {
@@ -1106,10 +1107,10 @@ __global__ void k_next_iteration(WfBuffers b) {
         uint32_t* c = b.counters;
         unsigned long long shade = 0;
         for (int k = 0; k < SQ_COUNT; k++) shade += c[C_SHADE0 + k];
-        b.stats[S_RAYS_CLOSEST] += shade;  // every traced slot lands in exactly one shade queue
-        b.stats[S_RAYS_SHADOW] += c[C_SHADOW];
-        b.stats[S_SHADE] += shade;
-        b.stats[S_PATHS_DONE] += c[C_DONE];
+        atomicAdd(&b.stats[S_RAYS_CLOSEST], shade);  // every traced slot lands in exactly one shade queue
+        atomicAdd(&b.stats[S_RAYS_SHADOW], (unsigned long long)c[C_SHADOW]);
+        atomicAdd(&b.stats[S_SHADE], shade);
+        atomicAdd(&b.stats[S_PATHS_DONE], (unsigned long long)c[C_DONE]);
         c[C_ACTIVE] = (uint32_t)shade;
         for (int k = 0; k < SQ_COUNT; k++) c[C_SHADE0 + k] = 0;
         c[C_SHADOW] = 0;

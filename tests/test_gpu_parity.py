@@ -209,6 +209,26 @@ def test_film_is_independent_of_pool_pass_and_sharding(qz):
         assert bits_equal(render(None, [QzRegion(4, 3, k) for k in range(3)]), base).all()  # 3 shards of 4-row strips
 
 
+def test_pipelines_do_not_change_the_film(qz, small_mesh):
+    """Renders large enough for the pool to be split into concurrent pipelines (two streams drawing
+    paths from one cursor) against the single-pipeline run of the same call (stage timing forces one
+    pipeline): bit-identical films and identical ray counts."""
+    from quetzalcoatlus_b200.harness import QZ_FLAG_STAGE_TIMING
+
+    cases = [("cornell_box", dict(), 320, 240, 6), ("kitchen_sink", dict(), 256, 256, 4),
+             ("obj_viewer", dict(obj_path=small_mesh, obj_material="alluminum", obj_light="point"), 320, 240, 4)]
+    for name, kw, w, h, spp in cases:
+        with qz.build_scene(name, w, h, **kw) as sc:
+            one, st1 = sc.render_flags(spp, flags=QZ_FLAG_STAGE_TIMING)
+            two, st2 = sc.render_flags(spp)
+            odd, st3 = sc.render_flags(spp, pool=70001, samples_per_pass=3)
+        for other, st in ((two, st2), (odd, st3)):
+            assert bits_equal(one.color, other.color).all(), name
+            assert bits_equal(one.normal, other.normal).all(), name
+            assert bits_equal(one.albedo, other.albedo).all(), name
+            assert (st["rays_closest"], st["rays_shadow"], st["shade_calls"]) == (st1["rays_closest"], st1["rays_shadow"], st1["shade_calls"]), name
+
+
 def test_equal_spp_rmse_matches_cpu(qz, oracle):
     """At equal spp the GPU film's RMSE against a high-spp reference must be statistically
     indistinguishable from the CPU film's (north_star)."""
