@@ -303,11 +303,24 @@ def run_ours(args) -> None:
         d_ms, d_bytes = stages[dom]
         peak, how = measured_peaks()
         achieved = d_bytes / (d_ms * 1e-3) / 1e9 if d_ms > 0 else 0.0
-        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                    "kernel": dom, "peak_source": how,
+        # DRAM bytes the stage really moved, per step: ncu dram__bytes_read+write per ray / per shaded bounce of a whole
+        # (smaller) render of the same scene (profiles/r01_traffic.json, tools/profile_step.py) x this step's counts
+        traffic = None
+        tj = ROOT / "profiles" / "r01_traffic.json"
+        scene_name = WORKLOADS[args.workload][0]
+        if tj.exists() and scene_name in json.loads(tj.read_text()):
+            t = json.loads(tj.read_text())[scene_name]
+            per = {"traversal (k_closest_* + k_shadow_*)": t["traversal"]["dram_bytes_per_ray"] * n_rays,
+                   "shading (k_shade<family, first>)": t["shading"]["dram_bytes_per_shade_call"] * inst["shade_calls"],
+                   "sampler (k_sample)": t["sampler"]["dram_bytes_per_shade_call"] * inst["shade_calls"]}
+            traffic = per[dom]
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                    "algorithmic_bytes": d_bytes, "kernel": dom, "peak_source": how,
                     "stage_ms": {**{k: v[0] for k, v in stages.items()}, "finish + regenerate + bin": inst["ms_other"], "step": inst["ms_total"]},
-                    "note": "algorithmic bytes (SURVEY.md 8.d) over the stage's device time; analytic scenes are SM-issue-bound "
-                            "(integer sampler, IEEE float), so the HBM fraction is low by nature; see DESIGN.md section 6"}
+                    "note": "algorithmic bytes per step (SURVEY.md 8.d) over the stage's device time in a serial (one-pipeline, "
+                            "event-per-stage) step of this run; traffic = measured DRAM bytes per step of that stage (ncu); the "
+                            "shading and sampler stages are bound by dependent-instruction latency and integer issue, not by HBM "
+                            "(DESIGN.md section 6)"}
         extra = {"n_node_per_ray": n_node, "n_prim_per_ray": n_prim, "bounces_per_path": inst["shade_calls"] / max(inst["paths"], 1),
                  "shadow_ray_fraction": inst["rays_shadow"] / max(n_rays, 1), "bvh_nodes": inst["bvh_nodes"],
                  "whole_pipeline_algorithmic_gbs": (bytes_trav + bytes_shade + bytes_sample) / (inst["ms_total"] * 1e-3) / 1e9}
