@@ -537,6 +537,8 @@ static int render_impl(qz_scene s, const qz_camera* camera, uint32_t n_samples, 
         if (!(flags & QZ_FLAG_UNSORTED_SHADING)) {
             e = timed(q, st.ms_sample, [&] { k_sample<<<shade_blocks * 2, 256, 0, q>>>(sc, b); });
             if (e != cudaSuccess) return e;
+            e = timed(q, st.ms_shade, [&] { k_albedo_conductor<<<shade_blocks * 2, 256, 0, q>>>(sc, b, max_bounces); });
+            if (e != cudaSuccess) return e;
         }
         e = timed(q, st.ms_shade, [&] {
             if (flags & QZ_FLAG_UNSORTED_SHADING) {
@@ -571,7 +573,7 @@ static int render_impl(qz_scene s, const qz_camera* camera, uint32_t n_samples, 
             k_finish<<<shade_blocks, 256, 0, q>>>(sc, cam, b, pp_cur);
             k_next_iteration<<<1, 32, 0, q>>>(b);
         });
-        st.kernel_launches += (flags & QZ_FLAG_UNSORTED_SHADING) ? 7 : 15;
+        st.kernel_launches += (flags & QZ_FLAG_UNSORTED_SHADING) ? 7 : 16;
         return e;
     };
 

@@ -318,7 +318,8 @@ QZ_HD bool shade_bounce(const DScene& sc, PathState& ps, PathAov& aov, const Hit
     const int32_t mat = KH == KH_ANY ? resolve_material(sc, sp.material, mat_sample) : sp.material;
     Bsdf f = make_bsdf<KH>(sc, mat, sp, ps.lambda, ps.pdf);
 
-    if (first) aov.albedo = bsdf_rho_hd<KH>(sc, f, sp.wo);
+    // the wavefront's first-hit conductor kernel leaves the estimate to k_albedo_conductor (wavefront.cuh)
+    if (first && !(KH == KH_CONDUCTOR && FIRST == 1)) aov.albedo = bsdf_rho_hd<KH>(sc, f, sp.wo);
 
     if (!bsdf_is_specular<KH>(f)) {
         bool has_shadow;

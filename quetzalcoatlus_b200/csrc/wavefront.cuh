@@ -979,6 +979,60 @@ __global__ void __launch_bounds__(256) k_sample(DScene sc, WfBuffers b) {
     }
 }
 
+// Depth-0 albedo of conductors as its own stage.  The reference estimates the albedo AOV at the first
+// hit with 16 fixed BxDF samples (render.cpp:150-170, bxdf.hpp:46-56); for a rough conductor that is
+// 16 x (visible-normal sample, D, G, complex Fresnel at 4 wavelengths) -- about three times the rest
+// of the bounce, executed as one serial chain per thread inside a 128-register kernel.  Here SIXTEEN
+// LANES share a path, one sample each, in a lean kernel at high occupancy; the 16 terms are then
+// added in sample order by every lane of the group (shuffles), which is the reference's
+// summation order, so the value is unchanged bit for bit.
+__global__ void __launch_bounds__(256) k_albedo_conductor(DScene sc, WfBuffers b, uint32_t max_bounces) {
+    if (max_bounces == 0) return;  // the path loop breaks before the estimate (render.cpp:137): the AOV stays zero
+    const uint32_t count = b.counters[C_SHADE0 + SQ_FAMILIES + SQ_CONDUCTOR];
+    const uint32_t* queue = b.q_shade[SQ_FAMILIES + SQ_CONDUCTOR];
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int i = lane & 15;          // this lane's sample
+    const int gbase = lane & 16;      // first lane of the 16-lane group
+    const uint32_t n_groups = gridDim.x * blockDim.x / 16u;
+    const uint32_t rounds = (count + n_groups - 1u) / n_groups;
+    uint32_t e = (blockIdx.x * blockDim.x + threadIdx.x) / 16u;
+    for (uint32_t r = 0; r < rounds; r++, e += n_groups) {
+        const bool live = e < count;   // uniform within the group; the warp stays converged for the shuffles
+        Spec4 term = spec4(0.0f);
+        bool valid = false;
+        uint32_t slot = 0;
+        if (live) {
+            slot = queue[e];
+            const float4 o = b.ray_o[slot], d = b.ray_d[slot], ha = b.hit_a[slot], hb = b.hit_b[slot];
+            Ray ray;
+            ray.o = v3(o.x, o.y, o.z); ray.d = v3(d.x, d.y, d.z);
+            Hit hit;
+            hit.t = ha.x; hit.u = ha.y; hit.v = ha.z; hit.prim_id = __float_as_uint(ha.w);
+            hit.ng = v3(hb.x, hb.y, hb.z); hit.geom_id = __float_as_uint(hb.w); hit.prim = hit.geom_id; hit.key = 0;
+            const Spec4 lambda = s4(b.lambda[slot]);
+            SurfacePoint sp = make_surface_point(sc, ray, hit);
+            Spec4 unused_pdf = spec4(0.0f);
+            const Bsdf f = make_bsdf<KH_CONDUCTOR>(sc, sp.material, sp, lambda, unused_pdf);
+            const V3 wo = to_local(f, sp.wo);
+            const float* t = sc.rho_tab + i * 8;
+            const BsdfSample smp = bxdf_sample<KH_CONDUCTOR>(f, wo, t[0], v2(t[1], t[2]), true, v3(t[6], t[7], 0.0f));
+            valid = smp.valid;
+            if (valid) term = smp.spec * fabsf(smp.wi.z) / smp.pdf;
+        }
+        Spec4 acc = spec4(0.0f);
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+            const bool ok = __shfl_sync(full, (int)valid, gbase + j) != 0;
+            Spec4 v;
+#pragma unroll
+            for (int c = 0; c < 4; c++) v.v[c] = __shfl_sync(full, term.v[c], gbase + j);
+            if (ok) acc = acc + v;
+        }
+        if (live && i == 0) b.aov_a[slot] = f4(acc / 16.0f);
+    }
+}
+
 // One bounce for every path of one (family, first-hit?) queue.  Only what the family can change
 // is loaded and stored: the radiance buffer is touched only when the hit itself adds radiance
 // (emitters and misses live in the run-time-dispatch queue), the wavelength pdf only by the
@@ -1049,7 +1103,8 @@ k_shade(DScene sc, WfBuffers b, int queue_id, uint32_t max_bounces) {
             // depth is still 0 after an emitter pass-through, so these may be written more than
             // once per path; the last write (the first real surface) wins, as in the reference
             if (hit.prim != QZ_NO_HIT) b.aov_n[slot] = f4(aov.normal.x, aov.normal.y, aov.normal.z, 0.0f);
-            if (ps.depth != 0 || !alive) b.aov_a[slot] = f4(aov.albedo);
+            // (first-hit conductors: the albedo comes from k_albedo_conductor)
+            if (!(KH == KH_CONDUCTOR && FIRST == 1) && (ps.depth != 0 || !alive)) b.aov_a[slot] = f4(aov.albedo);
         }
         uint32_t post = alive ? 0u : QZ_POST_DONE;
         if (ps.flags & QZ_FLAG_HAS_SHADOW) {
