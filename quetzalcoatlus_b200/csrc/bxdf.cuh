@@ -389,6 +389,7 @@ template <int KH>
 QZ_HD Spec4 bsdf_rho_hd(const DScene& sc, const Bsdf& f, V3 wo_r) {
     V3 wo = to_local(f, wo_r);
     Spec4 acc = spec4(0.0f);
+#pragma unroll 1
     for (int i = 0; i < 16; i++) {
         const float* t = sc.rho_tab + i * 8;
         V3 disk = is_kind<KH>(f, BX_DIFFUSE) ? v3(t[3], t[4], t[5]) : v3(t[6], t[7], 0.0f);

@@ -22,9 +22,19 @@
 #if defined(__CUDACC__)
 #define QZ_HD __host__ __device__ __forceinline__
 #define QZ_D __device__ __forceinline__
+// QZ_HD_CALL: large, rarely repeated bodies (double-precision transcendentals, the spectrum
+// switch) are real calls on the device.  Inlined at every site they made each shading kernel
+// 350-700 KB of straight-line code that every warp streams through once per bounce: the
+// instruction caches miss constantly (no_instruction stalls, profiles/r01_summary.md).
+#ifndef QZ_INLINE_EVERYTHING
+#define QZ_HD_CALL __host__ __device__ __noinline__
+#else
+#define QZ_HD_CALL __host__ __device__ __forceinline__
+#endif
 #else
 #define QZ_HD inline
 #define QZ_D inline
+#define QZ_HD_CALL inline
 #endif
 
 namespace qz {

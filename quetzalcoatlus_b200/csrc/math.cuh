@@ -13,28 +13,28 @@
 
 namespace qz {
 
-QZ_HD float qz_sinf(float x) {
+QZ_HD_CALL float qz_sinf(float x) {
 #if defined(__CUDA_ARCH__)
     return (float)sin((double)x);
 #else
     return sinf(x);
 #endif
 }
-QZ_HD float qz_cosf(float x) {
+QZ_HD_CALL float qz_cosf(float x) {
 #if defined(__CUDA_ARCH__)
     return (float)cos((double)x);
 #else
     return cosf(x);
 #endif
 }
-QZ_HD float qz_atan2f(float y, float x) {
+QZ_HD_CALL float qz_atan2f(float y, float x) {
 #if defined(__CUDA_ARCH__)
     return (float)atan2((double)y, (double)x);
 #else
     return atan2f(y, x);
 #endif
 }
-QZ_HD float qz_acosf(float x) {
+QZ_HD_CALL float qz_acosf(float x) {
 #if defined(__CUDA_ARCH__)
     return (float)acos((double)x);
 #else

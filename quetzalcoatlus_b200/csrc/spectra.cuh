@@ -73,7 +73,7 @@ QZ_HD float eval_spectrum_leaf(const DScene& sc, const qz_spectrum& s, float lam
     }
 }
 
-QZ_HD float eval_spectrum(const DScene& sc, int32_t id, float lambda) {
+QZ_HD_CALL float eval_spectrum(const DScene& sc, int32_t id, float lambda) {
     const qz_spectrum s = sc.spectra[id];
     if (s.kind == QZ_SPEC_RGB_ILLUMINANT) {
         if (s.aux < 0) return 0.0f;
@@ -94,7 +94,7 @@ QZ_HD Spec4 from_spectrum(const DScene& sc, int32_t id, const Spec4& lambda) {
 
 // RGBColorSpace::to_spectrum + RGBToSpectrumTable::operator() (rgb.cpp:50-57, 78-140);
 // returns (c0, c1, c2) of the sigmoid polynomial
-QZ_HD V3 rgb_to_sigmoid(const DScene& sc, float r, float g, float b) {
+QZ_HD_CALL V3 rgb_to_sigmoid(const DScene& sc, float r, float g, float b) {
     r = std_clamp(r, 0.0f, 1.0f); g = std_clamp(g, 0.0f, 1.0f); b = std_clamp(b, 0.0f, 1.0f);
     if (r == g && g == b) {
         return v3(0.0f, 0.0f, (r - 0.5f) / sqrtf(std_max(0.0f, r * (1.0f - r))));
