@@ -518,7 +518,11 @@ __global__ void __launch_bounds__(128, QZ_TRACE_MIN_BLOCKS) k_trace_lane(DScene 
             if (sp == 0) { state = LS_DONE; return; }
             sp--;
             const uint2 e = stack[sp];
-            if (__uint_as_float(e.x & ~7u) <= limit) { cur = e.y; state = LS_NODE; return; }
+            if (__uint_as_float(e.x & ~7u) <= limit) {
+                cur = e.y; state = LS_NODE;
+                prefetch_line(sc.nodes + cur);   // the node stream that opens it is at least a trip away
+                return;
+            }
         }
     };
 
@@ -601,7 +605,10 @@ __global__ void __launch_bounds__(128, QZ_TRACE_MIN_BLOCKS) k_trace_lane(DScene 
                     prim_test(sc, p, O, D, QZ_TNEAR, INFINITY, best);
                     limit = best.t;
                 }
-                if (state == LS_PRIM && leafbits == 0u) pop_next();
+                if (state == LS_PRIM) {
+                    if (leafbits == 0u) pop_next();
+                    else prefetch_line(sc.prims + (size_t)(leaf_base + (uint32_t)(__ffs(leafbits) - 1)) * 4);
+                }
             }
             continue;
         }
@@ -674,8 +681,12 @@ __global__ void __launch_bounds__(128, QZ_TRACE_MIN_BLOCKS) k_trace_lane(DScene 
                 }
             }
             leafbits = lb;
-            if (lb) state = LS_PRIM;
-            else pop_next();
+            if (lb) {
+                state = LS_PRIM;
+                prefetch_line(sc.prims + (size_t)(leaf_base + (uint32_t)(__ffs(lb) - 1)) * 4);  // first pending primitive record
+            } else {
+                pop_next();
+            }
         }
     }
     if (COUNT) {
