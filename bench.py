@@ -46,6 +46,7 @@ WORKLOADS = {
     "textures": ("textures", 800, 800, 36, 32),
     "opposing_planes": ("opposing_planes", 1920, 1080, 256, 64),
     "obj_viewer": ("obj_viewer", 800, 600, 24, 32),         # synthetic ~1M-triangle mesh
+    "mandelbrot": ("mandelbrot_full", 800, 800, 32, 12),    # examples/mandelbrot.cpp: 1200x1200 height grid (2.87M triangles), copper
 }
 STRIP_ROWS = 8
 

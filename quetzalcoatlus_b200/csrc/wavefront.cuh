@@ -590,7 +590,10 @@ __global__ void __launch_bounds__(128, QZ_TRACE_MIN_BLOCKS) k_trace_lane(DScene 
         }
         if (!busy) break;  // nothing in flight, nothing to write, no slots left
 
-        if (__popc(m_prim) > __popc(m_node)) {
+#ifndef QZ_PRIM_FIRST_MIN
+#define QZ_PRIM_FIRST_MIN 33   /* run the primitive stream whenever at least this many lanes wait for it (33 = majority rule only) */
+#endif
+        if (__popc(m_prim) > __popc(m_node) || __popc(m_prim) >= QZ_PRIM_FIRST_MIN) {
             // ---- primitive stream: one pending primitive per lane
             if (state == LS_PRIM) {
                 const uint32_t p = leaf_base + (uint32_t)(__ffs(leafbits) - 1);

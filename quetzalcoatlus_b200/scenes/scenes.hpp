@@ -272,6 +272,7 @@ inline std::unique_ptr<Bundle> build(const std::string& name, const Options& o) 
     else if (name == "textures") build_textures(*b, o);
     else if (name == "opposing_planes") build_opposing_planes(*b, o);
     else if (name == "mandelbrot") build_mandelbrot(*b, o, 96);
+    else if (name == "mandelbrot_full") build_mandelbrot(*b, o, 1200);  // the grid as shipped: 1199 x 1199 cells = 2.87 M triangles
     else if (name == "kitchen_sink") build_kitchen_sink(*b, o);
     else if (name == "obj_viewer") { if (!build_obj_viewer(*b, o)) return nullptr; }
     else return nullptr;

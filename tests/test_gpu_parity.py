@@ -209,6 +209,21 @@ def test_film_is_independent_of_pool_pass_and_sharding(qz):
         assert bits_equal(render(None, [QzRegion(4, 3, k) for k in range(3)]), base).all()  # 3 shards of 4-row strips
 
 
+def test_mandelbrot_grid_at_full_scale(qz, oracle):
+    """examples/mandelbrot.cpp with its shipped 1200 x 1200 height grid (1.44 M grid cells =
+    2.87 M triangles, rough copper): replayed paths against the oracle, and the wavefront BVH kernels
+    against the replay on a crop-sized film."""
+    with qz.build_scene("mandelbrot_full", 96, 96) as sg, oracle.build_scene("mandelbrot_full", 96, 96) as so:
+        xys = pixel_samples(so, 3000, seed=9)
+        got, want = sg.trace_paths(xys), so.trace_paths(xys)
+        assert 1.0 - path_agreement(want, got, REL_TOL).mean() <= MAX_DIVERGENT
+        film, st = sg.render_flags(3)
+        ref = _replayed_film(sg, 96, 96, 3)
+    assert st["stack_overflows"] == 0
+    for got_plane, want_plane in zip((film.color, film.normal, film.albedo), ref):
+        assert bits_equal(got_plane, want_plane).all()
+
+
 def test_pipelines_do_not_change_the_film(qz, small_mesh):
     """Renders large enough for the pool to be split into concurrent pipelines (two streams drawing
     paths from one cursor) against the single-pipeline run of the same call (stage timing forces one
