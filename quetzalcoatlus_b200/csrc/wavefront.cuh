@@ -1016,6 +1016,9 @@ __global__ void __launch_bounds__(256) k_albedo_conductor(DScene sc, WfBuffers b
         Spec4 term = spec4(0.0f);
         bool valid = false;
         uint32_t slot = 0;
+        SurfacePoint sp;
+        qz_material mat;
+        float coeff = 0.0f;
         if (live) {
             slot = queue[e];
             const float4 o = b.ray_o[slot], d = b.ray_d[slot], ha = b.hit_a[slot], hb = b.hit_b[slot];
@@ -1025,9 +1028,24 @@ __global__ void __launch_bounds__(256) k_albedo_conductor(DScene sc, WfBuffers b
             hit.t = ha.x; hit.u = ha.y; hit.v = ha.z; hit.prim_id = __float_as_uint(ha.w);
             hit.ng = v3(hb.x, hb.y, hb.z); hit.geom_id = __float_as_uint(hb.w); hit.prim = hit.geom_id; hit.key = 0;
             const Spec4 lambda = s4(b.lambda[slot]);
-            SurfacePoint sp = make_surface_point(sc, ray, hit);
-            Spec4 unused_pdf = spec4(0.0f);
-            const Bsdf f = make_bsdf<KH_CONDUCTOR>(sc, sp.material, sp, lambda, unused_pdf);
+            sp = make_surface_point(sc, ray, hit);
+            // Material::bsdf for a conductor (material.cpp:16-20) is eight spectrum lookups (eta and k at four
+            // wavelengths): lane j of the group does lookup j, the group exchanges them below
+            mat = sc.materials[sp.material];
+            const int j = i & 7;
+            const float lam = j & 2 ? (j & 1 ? lambda.v[3] : lambda.v[2]) : (j & 1 ? lambda.v[1] : lambda.v[0]);
+            coeff = eval_spectrum(sc, j < 4 ? mat.a : mat.b, lam);
+        }
+        Bsdf f;
+        f.kind = BX_CONDUCTOR; f.ior = 1.0f;
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            f.a.v[c] = __shfl_sync(full, coeff, gbase + c);
+            f.b.v[c] = __shfl_sync(full, coeff, gbase + 4 + c);
+        }
+        if (live) {
+            f.rough.ax = mat.alpha_x; f.rough.ay = mat.alpha_y;
+            make_basis(sp.normal, f.u0, f.u1, f.u2);
             const V3 wo = to_local(f, sp.wo);
             const float* t = sc.rho_tab + i * 8;
             const BsdfSample smp = bxdf_sample<KH_CONDUCTOR>(f, wo, t[0], v2(t[1], t[2]), true, v3(t[6], t[7], 0.0f));
