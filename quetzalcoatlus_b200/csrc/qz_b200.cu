@@ -381,7 +381,7 @@ static int render_impl(qz_scene s, const qz_camera* camera, uint32_t n_samples, 
     s_pass = std::min(s_pass, n_samples);
     while ((uint64_t)s_pass * n_pix >= (1ull << 31)) s_pass = std::max(1u, s_pass / 2);
     const uint64_t cells = (uint64_t)s_pass * n_pix;
-    uint32_t pool = options && options->pool_paths ? options->pool_paths : (1u << 21);
+    uint32_t pool = options && options->pool_paths ? options->pool_paths : (1u << 23);
     pool = (uint32_t)std::min<uint64_t>(pool, cells);
     pool = std::max(pool, 1u);
 
