@@ -294,6 +294,12 @@ def run_ours(args) -> None:
         n_prim = inst["prim_tests"] / max(n_rays, 1)
         # B_ray = N_node*128 + N_prim*64 + 32 (ray read) + 32 (hit write; 4 for shadow rays)
         bytes_trav = inst["node_visits"] * 128 + inst["prim_tests"] * 64 + inst["rays_closest"] * 64 + inst["rays_shadow"] * 36
+        # scenes of <= 96 primitives are intersected by the flat kernels (primitive records staged in shared memory
+        # once per CTA, no BVH): per ray only the ray read and the result write are memory traffic
+        n_prims_scene = (inst["bvh_bytes"] - inst["bvh_nodes"] * 128) // 64
+        flat_scene = 0 < n_prims_scene <= 96 and not (args.flags & 8)
+        if flat_scene:
+            bytes_trav = inst["rays_closest"] * 64 + inst["rays_shadow"] * 36
         # per shaded bounce: the path record is read and written once (288 B) and the sampler stage adds 32 B each way
         bytes_shade = inst["shade_calls"] * 288 + inst["rays_shadow"] * 48
         bytes_sample = inst["shade_calls"] * 64
@@ -322,7 +328,7 @@ def run_ours(args) -> None:
                             "event-per-stage) step of this run; traffic = measured DRAM bytes per step of that stage (ncu); the "
                             "shading and sampler stages are bound by dependent-instruction latency and integer issue, not by HBM "
                             "(DESIGN.md section 6)"}
-        extra = {"n_node_per_ray": n_node, "n_prim_per_ray": n_prim, "bounces_per_path": inst["shade_calls"] / max(inst["paths"], 1),
+        extra = {"flat_intersection": flat_scene, "n_node_per_ray": n_node, "n_prim_per_ray": n_prim, "bounces_per_path": inst["shade_calls"] / max(inst["paths"], 1),
                  "shadow_ray_fraction": inst["rays_shadow"] / max(n_rays, 1), "bvh_nodes": inst["bvh_nodes"],
                  "whole_pipeline_algorithmic_gbs": (bytes_trav + bytes_shade + bytes_sample) / (inst["ms_total"] * 1e-3) / 1e9}
 
