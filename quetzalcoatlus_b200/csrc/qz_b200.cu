@@ -462,6 +462,9 @@ static int render_impl(qz_scene s, const qz_camera* camera, uint32_t n_samples, 
     const int per_sm = env_per_sm > 0 ? env_per_sm : (P == 1 ? 8 : (P == 2 ? 4 : (P == 3 ? 3 : 2)));
     const int trav_blocks = n_sm * per_sm;   // persistent CTAs of 4 warps
     const int shade_blocks = n_sm * per_sm;
+    // the lean stages (sampler, flat intersection, albedo, finish, generate: 32-80 registers, 256-thread CTAs)
+    static const int env_lean = [] { const char* e = std::getenv("QZ_LEAN_BLOCKS_PER_SM"); int v = e ? std::atoi(e) : 0; return v; }();
+    const int lean_blocks = n_sm * (env_lean > 0 ? env_lean : per_sm);
 
     if (!wm.ev_begin) {
         QZ_CUDA(cudaEventCreate(&wm.ev_begin)); QZ_CUDA(cudaEventCreate(&wm.ev_end));
@@ -521,7 +524,7 @@ static int render_impl(qz_scene s, const qz_camera* camera, uint32_t n_samples, 
         cudaStream_t q = ps[p];
         cudaError_t e;
         e = timed(q, st.ms_closest, [&] {
-            if (flat) k_closest_flat<<<shade_blocks, 256, 0, q>>>(sc, b, flags);
+            if (flat) k_closest_flat<<<lean_blocks, 256, 0, q>>>(sc, b, flags);
             else if (lane_trav && count_trav) k_closest_hit<true><<<trav_blocks, 128, 0, q>>>(sc, b, flags);
             else if (lane_trav) k_closest_hit<false><<<trav_blocks, 128, 0, q>>>(sc, b, flags);
             else if (oct_trav && count_trav) k_trace_oct<false, true><<<trav_blocks, 128, 0, q>>>(sc, b, flags);
@@ -535,9 +538,9 @@ static int render_impl(qz_scene s, const qz_camera* camera, uint32_t n_samples, 
         });
         if (e != cudaSuccess) return e;
         if (!(flags & QZ_FLAG_UNSORTED_SHADING)) {
-            e = timed(q, st.ms_sample, [&] { k_sample<<<shade_blocks * 2, 256, 0, q>>>(sc, b); });
+            e = timed(q, st.ms_sample, [&] { k_sample<<<lean_blocks * 2, 256, 0, q>>>(sc, b); });
             if (e != cudaSuccess) return e;
-            e = timed(q, st.ms_shade, [&] { k_albedo_conductor<<<shade_blocks * 2, 256, 0, q>>>(sc, b, max_bounces); });
+            e = timed(q, st.ms_shade, [&] { k_albedo_conductor<<<lean_blocks * 2, 256, 0, q>>>(sc, b, max_bounces); });
             if (e != cudaSuccess) return e;
         }
         e = timed(q, st.ms_shade, [&] {
@@ -560,7 +563,7 @@ static int render_impl(qz_scene s, const qz_camera* camera, uint32_t n_samples, 
         });
         if (e != cudaSuccess) return e;
         e = timed(q, st.ms_shadow, [&] {
-            if (flat) k_shadow_flat<<<shade_blocks, 256, 0, q>>>(sc, b);
+            if (flat) k_shadow_flat<<<lean_blocks, 256, 0, q>>>(sc, b);
             else if (lane_trav && count_trav) k_shadow<true><<<trav_blocks, 128, 0, q>>>(sc, b);
             else if (lane_trav) k_shadow<false><<<trav_blocks, 128, 0, q>>>(sc, b);
             else if (oct_trav && count_trav) k_trace_oct<true, true><<<trav_blocks, 128, 0, q>>>(sc, b, flags);
@@ -570,7 +573,7 @@ static int render_impl(qz_scene s, const qz_camera* camera, uint32_t n_samples, 
         });
         if (e != cudaSuccess) return e;
         e = timed(q, st.ms_other, [&] {
-            k_finish<<<shade_blocks, 256, 0, q>>>(sc, cam, b, pp_cur);
+            k_finish<<<lean_blocks, 256, 0, q>>>(sc, cam, b, pp_cur);
             k_next_iteration<<<1, 32, 0, q>>>(b);
         });
         st.kernel_launches += (flags & QZ_FLAG_UNSORTED_SHADING) ? 7 : 16;
@@ -602,7 +605,7 @@ static int render_impl(qz_scene s, const qz_camera* camera, uint32_t n_samples, 
         }
         uint32_t id0 = 0;
         for (int p = 0; p < P; p++) {
-            k_generate<<<shade_blocks, 256, 0, ps[p]>>>(sc, cam, bufs[p], pp, id0, first[p]);
+            k_generate<<<lean_blocks, 256, 0, ps[p]>>>(sc, cam, bufs[p], pp, id0, first[p]);
             id0 += first[p];
             st.kernel_launches++;
         }
