@@ -255,6 +255,31 @@ inline void build_kitchen_sink(Bundle& b, const Options& o) {
     b.max_bounces = 24;
 }
 
+// Edge cases the shipped examples never reach: a scene WITHOUT lights (sample_lights draws its two
+// 2-D samples without using them, render.cpp:62-66; all radiance comes from the background) ...
+inline void build_no_lights(Bundle& b, const Options& o) {
+    Scene& scene = *b.scene;
+    scene.set_bg_light(spectra::ILLUM_D65(), 0.8f);
+    scene.add_plane(Pt3(0.f, -1.f, 0.f), Vec3(0.f, 1.f, 0.f), b.keep(DiffuseMaterial(SolidColor(0.6f, 0.5f, 0.4f))), 40.0f);
+    scene.add_sphere(Pt3(-1.1f, 0.f, -4.f), 1.0f, b.keep(ConductiveMaterial::copper(0.25, 0.1)));
+    scene.add_sphere(Pt3(1.1f, 0.f, -4.5f), 1.0f, b.keep(DiffuseMaterial(DummyTexture{})));
+    scene.add_sphere(Pt3(0.f, -0.5f, -2.5f), 0.5f, b.keep(DielectricMaterial(spectra::GLASS_BK7_IOR())));
+    scene.commit();
+    b.camera = std::make_unique<Camera>(o.width ? o.width : 200, o.height ? o.height : 150, M_PI / 3.0f);
+    b.n_samples = 8;
+    b.max_bounces = 16;
+}
+
+// ... and a scene without any geometry: every path misses at depth 0 and returns the background.
+inline void build_empty_sky(Bundle& b, const Options& o) {
+    Scene& scene = *b.scene;
+    scene.set_bg_light(std::make_shared<RGBIlluminantSpectrum>(RGB(0.3f, 0.5f, 0.9f)), 1.5f);
+    scene.commit();
+    b.camera = std::make_unique<Camera>(o.width ? o.width : 64, o.height ? o.height : 48, M_PI / 3.0f);
+    b.n_samples = 4;
+    b.max_bounces = 8;
+}
+
 inline const char* const* scene_names(int* n) {
     static const char* const names[] = {"cornell_box", "glass_spheres", "textures", "opposing_planes",
                                         "obj_viewer", "cornell_mixed", "mandelbrot", "kitchen_sink"};
@@ -274,6 +299,8 @@ inline std::unique_ptr<Bundle> build(const std::string& name, const Options& o) 
     else if (name == "mandelbrot") build_mandelbrot(*b, o, 96);
     else if (name == "mandelbrot_full") build_mandelbrot(*b, o, 1200);  // the grid as shipped: 1199 x 1199 cells = 2.87 M triangles
     else if (name == "kitchen_sink") build_kitchen_sink(*b, o);
+    else if (name == "no_lights") build_no_lights(*b, o);
+    else if (name == "empty_sky") build_empty_sky(*b, o);
     else if (name == "obj_viewer") { if (!build_obj_viewer(*b, o)) return nullptr; }
     else return nullptr;
     return b;

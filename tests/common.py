@@ -3,6 +3,9 @@ import numpy as np
 
 ANALYTIC_SCENES = ["cornell_box", "glass_spheres", "textures", "opposing_planes", "cornell_mixed", "mandelbrot", "kitchen_sink"]
 
+# scenes for the branches no shipped example reaches (no golden fixtures: compared with the oracle directly)
+EDGE_SCENES = ["no_lights", "empty_sky"]
+
 # record layout of trace_paths (include/qz_b200.h)
 LAMBDA, PDF, RADIANCE, NORMAL, RAYS, ALBEDO, RGB, ARGB = (slice(0, 4), slice(4, 8), slice(8, 12), slice(12, 15), 15,
                                                           slice(16, 20), slice(20, 23), slice(23, 26))

@@ -8,7 +8,7 @@ from pathlib import Path
 import numpy as np
 import pytest
 
-from common import ANALYTIC_SCENES, bits_equal, pixel_samples
+from common import ANALYTIC_SCENES, EDGE_SCENES, bits_equal, pixel_samples
 
 GOLDEN = Path(__file__).resolve().parent / "golden"
 
@@ -89,3 +89,22 @@ def test_ragged_and_edge_inputs(emu, oracle):
         # max_bounces = 0: only directly visible emission
         assert bits_equal(se.trace_paths(xys, max_bounces=0), so.trace_paths(xys, max_bounces=0)).all()
         assert bits_equal(se.render(2).color, so.render(2).color).all()
+
+
+@pytest.mark.parametrize("name", EDGE_SCENES)
+def test_edge_scenes_bit_exact(emu, oracle, name):
+    """A scene without lights (sample_lights' unused draws, render.cpp:62-66) and a scene without geometry."""
+    with emu.build_scene(name) as se, oracle.build_scene(name) as so:
+        xys = pixel_samples(so, 1500, seed=6)
+        assert bits_equal(se.trace_paths(xys), so.trace_paths(xys)).all()
+        a, b = se.render(2), so.render(2)
+        assert bits_equal(a.color, b.color).all() and bits_equal(a.normal, b.normal).all() and bits_equal(a.albedo, b.albedo).all()
+
+
+@pytest.mark.parametrize("max_bounces", [0, 1, 2])
+def test_bounce_limits_bit_exact(emu, oracle, max_bounces):
+    """depth == max_bounces breaks the path loop before the BSDF is built (render.cpp:137): limits 0, 1, 2."""
+    for name in ("cornell_box", "kitchen_sink"):
+        with emu.build_scene(name) as se, oracle.build_scene(name) as so:
+            xys = pixel_samples(so, 800, seed=8)
+            assert bits_equal(se.trace_paths(xys, max_bounces=max_bounces), so.trace_paths(xys, max_bounces=max_bounces)).all(), name

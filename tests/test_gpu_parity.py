@@ -13,7 +13,7 @@ from pathlib import Path
 import numpy as np
 import pytest
 
-from common import ANALYTIC_SCENES, RADIANCE, RAYS, bits_equal, path_agreement, pixel_samples
+from common import ANALYTIC_SCENES, EDGE_SCENES, RADIANCE, RAYS, bits_equal, path_agreement, pixel_samples
 
 pytestmark = pytest.mark.gpu
 GOLDEN = Path(__file__).resolve().parent / "golden"
@@ -222,6 +222,41 @@ def test_mandelbrot_grid_at_full_scale(qz, oracle):
     assert st["stack_overflows"] == 0
     for got_plane, want_plane in zip((film.color, film.normal, film.albedo), ref):
         assert bits_equal(got_plane, want_plane).all()
+
+
+@pytest.mark.parametrize("name", EDGE_SCENES)
+def test_edge_scenes(qz, oracle, name):
+    """No lights / no geometry: replayed paths against the oracle, wavefront film against the replay."""
+    with qz.build_scene(name) as sg, oracle.build_scene(name) as so:
+        xys = pixel_samples(so, 5000, seed=6)
+        got, want = sg.trace_paths(xys), so.trace_paths(xys)
+        assert 1.0 - path_agreement(want, got, REL_TOL).mean() <= MAX_DIVERGENT
+        w, h = sg.width, sg.height
+        film, st = sg.render_flags(3)
+        ref = _replayed_film(sg, w, h, 3)
+    for got_plane, want_plane in zip((film.color, film.normal, film.albedo), ref):
+        assert bits_equal(got_plane, want_plane).all()
+    assert st["paths"] == w * h * 3
+
+
+@pytest.mark.parametrize("max_bounces", [0, 1, 2])
+def test_bounce_limits(qz, oracle, max_bounces):
+    """max_bounces 0, 1, 2: the loop's early break (render.cpp:137), incl. the separate conductor albedo stage."""
+    for name in ("cornell_box", "kitchen_sink"):
+        with qz.build_scene(name, 64, 48) as sg, oracle.build_scene(name, 64, 48) as so:
+            xys = pixel_samples(so, 3000, seed=8, spp=4)
+            got = sg.trace_paths(xys, spp=4, max_bounces=max_bounces)
+            want = so.trace_paths(xys, spp=4, max_bounces=max_bounces)
+            assert 1.0 - path_agreement(want, got, REL_TOL).mean() <= MAX_DIVERGENT, name
+            film, _ = sg.render_flags(4, max_bounces=max_bounces)
+            ys, xs, ss = np.meshgrid(np.arange(48), np.arange(64), np.arange(4), indexing="ij")
+            all_xys = np.stack([xs.ravel(), (47 - ys).ravel(), ss.ravel()], 1).astype(np.int32)
+            rec = sg.trace_paths(all_xys, spp=4, max_bounces=max_bounces).reshape(48, 64, 4, 32)
+            color = np.zeros((48, 64, 3), np.float32); albedo = np.zeros_like(color)
+            for s in range(4):
+                color += rec[:, :, s, 20:23]; albedo += rec[:, :, s, 23:26]
+            assert bits_equal(film.color, color / np.float32(4)).all(), name
+            assert bits_equal(film.albedo, albedo / np.float32(4)).all(), name
 
 
 def test_pipelines_do_not_change_the_film(qz, small_mesh):
