@@ -669,13 +669,16 @@ __global__ void __launch_bounds__(128, QZ_TRACE_MIN_BLOCKS) k_trace_lane(DScene 
                 key[k] = (hit && internal) ? ((__float_as_uint(e0) & ~7u) | (m & 7u)) : 0u;
                 if (hit && !internal) lb |= ((1u << (m >> 5)) - 1u) << (m & 31u);
             }
-            // sort the (distance | child slot) keys descending: Batcher's 19-comparator network
-            QZ_CSWAP_DESC(key[0], key[1]); QZ_CSWAP_DESC(key[2], key[3]); QZ_CSWAP_DESC(key[4], key[5]); QZ_CSWAP_DESC(key[6], key[7]);
-            QZ_CSWAP_DESC(key[0], key[2]); QZ_CSWAP_DESC(key[1], key[3]); QZ_CSWAP_DESC(key[4], key[6]); QZ_CSWAP_DESC(key[5], key[7]);
-            QZ_CSWAP_DESC(key[1], key[2]); QZ_CSWAP_DESC(key[5], key[6]);
-            QZ_CSWAP_DESC(key[0], key[4]); QZ_CSWAP_DESC(key[1], key[5]); QZ_CSWAP_DESC(key[2], key[6]); QZ_CSWAP_DESC(key[3], key[7]);
-            QZ_CSWAP_DESC(key[2], key[4]); QZ_CSWAP_DESC(key[3], key[5]);
-            QZ_CSWAP_DESC(key[1], key[2]); QZ_CSWAP_DESC(key[3], key[4]); QZ_CSWAP_DESC(key[5], key[6]);
+            // sort the (distance | child slot) keys descending: Batcher's 19-comparator network.  Shadow rays stop at
+            // the first occluder wherever it is, so any-hit traversal pushes the children as they come.
+            if (!ANY_HIT) {
+                QZ_CSWAP_DESC(key[0], key[1]); QZ_CSWAP_DESC(key[2], key[3]); QZ_CSWAP_DESC(key[4], key[5]); QZ_CSWAP_DESC(key[6], key[7]);
+                QZ_CSWAP_DESC(key[0], key[2]); QZ_CSWAP_DESC(key[1], key[3]); QZ_CSWAP_DESC(key[4], key[6]); QZ_CSWAP_DESC(key[5], key[7]);
+                QZ_CSWAP_DESC(key[1], key[2]); QZ_CSWAP_DESC(key[5], key[6]);
+                QZ_CSWAP_DESC(key[0], key[4]); QZ_CSWAP_DESC(key[1], key[5]); QZ_CSWAP_DESC(key[2], key[6]); QZ_CSWAP_DESC(key[3], key[7]);
+                QZ_CSWAP_DESC(key[2], key[4]); QZ_CSWAP_DESC(key[3], key[5]);
+                QZ_CSWAP_DESC(key[1], key[2]); QZ_CSWAP_DESC(key[3], key[4]); QZ_CSWAP_DESC(key[5], key[6]);
+            }
 #pragma unroll
             for (int k = 0; k < 8; k++) {
                 if (key[k]) {
