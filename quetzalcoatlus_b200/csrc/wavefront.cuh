@@ -1,38 +1,40 @@
 // Wavefront path-tracing pipeline: the reference's per-pixel loop (render.cpp:247-319
-// render_pixels, :91-212 sample_pixel) re-cut into stages connected by SoA queues.
+// render_pixels, :91-212 sample_pixel) re-cut into stages connected by index queues.
 //
-//   k_generate        camera ray + wavelengths for new pixel-samples (render.cpp:268-273)
-//   k_closest_hit     persistent, warp-scheduled BVH traversal (scene.cpp:61-117 / rtcIntersect1);
-//                     tags each hit with its material family (k_closest_flat: BVH-less variant for
-//                     scenes of <= 96 primitives)
-//   k_bin             ordered compaction of the tags into one queue per family x {first hit, later}
-//   k_sample          this bounce's Owen-scrambled Halton draws, one thread per dimension
-//   k_shade<family>   emission + MIS, BSDF construction, depth-0 albedo, light sampling,
-//                     BSDF sampling, throughput update and Russian roulette for ONE family
-//                     (diffuse / conductor / dielectric); a fourth "misc" kernel takes misses,
-//                     emitter pass-throughs and MixedMaterial hits with run-time dispatch
-//   k_shadow          persistent any-hit traversal of the next-event shadow rays
-//                     (scene.cpp:136-143); adds the pending contribution when unoccluded
-//   k_finish          PixelSensor::to_sensor_rgb of finished paths (sensor.cpp:57-70) into the
-//                     per-sample result buffer, then regenerates a new path in the freed slot
-//   k_film            ordered per-pixel sum over the sample index (render.cpp:264-294)
+//   k_generate          camera ray + wavelengths for new pixel-samples (render.cpp:268-273)
+//   k_trace_lane<false> persistent, phase-scheduled BVH traversal, closest hit (scene.cpp:61-117 /
+//                       rtcIntersect1); tags each hit with its material family.  k_closest_flat:
+//                       BVH-less variant for scenes of <= 96 primitives.  (k_closest_hit, k_trace_oct:
+//                       earlier generations, kept behind flags as evidence arms.)
+//   k_bin               ordered compaction of the tags into one queue per family x {first hit, later}
+//   k_sample            this bounce's Owen-scrambled Halton draws, one thread per dimension
+//   k_albedo_conductor  depth-0 albedo of conductors, sixteen lanes per path (render.cpp:150-170)
+//   k_shade<family>     emission + MIS, BSDF construction, depth-0 albedo, light sampling,
+//                       BSDF sampling, throughput update and Russian roulette for ONE family
+//                       (diffuse / conductor / dielectric); a fourth "misc" kernel takes misses,
+//                       emitter pass-throughs and MixedMaterial hits with run-time dispatch
+//   k_trace_lane<true>  any-hit traversal of the next-event shadow rays (scene.cpp:136-143); adds the
+//                       pending contribution when unoccluded (k_shadow_flat for tiny scenes)
+//   k_finish            PixelSensor::to_sensor_rgb of finished paths (sensor.cpp:57-70) into the
+//                       per-sample result buffer, then regenerates a new path in the freed slot
+//   k_film              ordered per-pixel sum over the sample index (render.cpp:264-294)
 //
-// Path state lives in structure-of-arrays buffers of 16-byte elements indexed by slot; the
-// queues carry 4-byte slot indices.  QUEUES ARE BUILT IN SLOT ORDER: the stages do not append to
-// queues with atomics (which scatters neighbouring slots across a queue and turns every 16-byte
-// state access into its own 64-byte DRAM burst); they write a one-byte tag per slot, and k_bin
-// -- an ordered compaction, one block per 2048 consecutive slots, one atomic per block and queue
-// -- turns the tags into queues whose entries ascend within each 2048-slot chunk.  Consecutive
-// lanes of the shading kernels then touch neighbouring slots, and the closest-hit stage simply
-// walks the slots densely.  Russian roulette stays fused at the end of k_shade: it
-// needs the freshly updated throughput and the next sampler dimension, so a separate kernel
-// would only re-read what is in registers.
+// Path state lives in two 128-byte records per slot (WfBuffers below), every field a 16-byte element;
+// the queues carry 4-byte slot indices.  QUEUES ARE BUILT IN SLOT ORDER: the stages do not append to
+// queues with atomics (which scatters neighbouring slots across a queue); they write a one-byte tag
+// per slot, and k_bin -- an ordered compaction, one block per 2048 consecutive slots, one atomic
+// per block and queue -- turns the tags into queues whose entries ascend within each 2048-slot
+// chunk.  Consecutive lanes of the shading kernels then touch neighbouring slots, and the
+// closest-hit stage simply walks the slots densely.  Russian roulette stays fused at the end of
+// k_shade: it needs the freshly updated throughput and the next sampler dimension, so a separate
+// kernel would only re-read what is in registers.  The host (qz_b200.cu: render_impl) runs several
+// such pipelines side by side, each on a sub-pool with its own queues and stream.
 //
 // DETERMINISM: a path's arithmetic depends only on (x, y, s); queue order varies from run to
 // run but no result depends on it.  Every pixel-sample writes its sensor RGB into its own
 // result cell and k_film adds the cells of a pixel in ascending s, exactly the reference's
 // summation order, so the film is bit-stable and independent of the pool size, the pass
-// size and the number of GPUs.
+// size, the number of pipelines and the number of GPUs.
 #pragma once
 
 #include <cooperative_groups.h>
