@@ -30,11 +30,9 @@ struct PrimHit {
     V3 ng;
 };
 
-// Moeller-Trumbore, Embree operation order; `flip` = second triangle of a quad
-QZ_HD bool tri_test(V3 O, V3 D, float tnear, float tfar, V3 v0, V3 v1, V3 v2, bool flip, PrimHit& h) {
-    V3 e1 = v0 - v1;
-    V3 e2 = v2 - v0;
-    V3 ng = cross(e2, e1);
+// Moeller-Trumbore, Embree operation order, on a triangle given by v0 and its precomputed
+// e1 = v0 - v1, e2 = v2 - v0, ng = e2 x e1; `flip` = second triangle of a quad
+QZ_HD bool tri_test_pre(V3 O, V3 D, float tnear, float tfar, V3 v0, V3 e1, V3 e2, V3 ng, bool flip, PrimHit& h) {
     V3 C = v0 - O;
     V3 R = cross(C, D);
     float den = dot(ng, D);
@@ -55,6 +53,13 @@ QZ_HD bool tri_test(V3 O, V3 D, float tnear, float tfar, V3 v0, V3 v1, V3 v2, bo
     }
     h.ng = ng;
     return true;
+}
+
+QZ_HD bool tri_test(V3 O, V3 D, float tnear, float tfar, V3 v0, V3 v1, V3 v2, bool flip, PrimHit& h) {
+    V3 e1 = v0 - v1;
+    V3 e2 = v2 - v0;
+    V3 ng = cross(e2, e1);
+    return tri_test_pre(O, D, tnear, tfar, v0, e1, e2, ng, flip, h);
 }
 
 QZ_HD bool sphere_test(V3 O, V3 D, float tnear, float tfar, V3 c, float r, PrimHit& h) {
@@ -131,6 +136,75 @@ QZ_HD void prim_test_rec(const DScene& sc, const F4& a, const F4& b, const F4& c
     if (h.t < best.t || (h.t == best.t && key < best.key)) {
         best.t = h.t; best.u = h.u; best.v = h.v; best.ng = h.ng; best.prim = slot; best.key = key;
         best.geom_id = float_as_u32(a.w); best.prim_id = float_as_u32(b.w);
+    }
+}
+
+// The flat kernels (scenes of a few dozen primitives, every ray tests every primitive) keep the
+// ray-independent part of Moeller-Trumbore -- the two edges and the normal of each triangle --
+// next to the vertices: 8 x 16 bytes per primitive, built once per CTA by the same expressions
+// tri_test uses, so every result is unchanged.
+struct FlatPrim {
+    F4 a;        // v0 of triangle A (sphere: centre) | geomID
+    F4 b;        // (sphere: radius in x)             | primID
+    F4 e1a, e2a, nga;   // triangle A = (a, b, d) of a quad / (a, b, c) of a triangle; e1a.w = kind | key << 2, e2a.w = grid cell
+    F4 c;        // v0 of triangle B = (c, d, b) of a quad; c.w = 1 when triangle B exists
+    F4 e1b, e2b; // ngb.xyz is stored in (nga.w, e1b.w, e2b.w)
+};
+
+QZ_HD FlatPrim make_flat_prim(const F4& a, const F4& b, const F4& c, const F4& d) {
+    FlatPrim f;
+    const uint32_t w2 = float_as_u32(c.w);
+    const uint32_t kind = prim_kind(w2);
+    f.a = a; f.b = b; f.c = c;
+    f.c.w = 0.0f;
+    V3 e1 = v3(0.0f, 0.0f, 0.0f), e2 = e1, ng = e1, e1b = e1, e2b = e1, ngb = e1;
+    if (kind == QZ_PRIM_TRIANGLE) {
+        e1 = xyz(a) - xyz(b); e2 = xyz(c) - xyz(a); ng = cross(e2, e1);
+    } else if (kind != QZ_PRIM_SPHERE) {
+        e1 = xyz(a) - xyz(b); e2 = xyz(d) - xyz(a); ng = cross(e2, e1);                 // (a, b, d)
+        const bool degenerate = c.x == d.x && c.y == d.y && c.z == d.z;                  // see prim_test_rec
+        if (!degenerate) {
+            e1b = xyz(c) - xyz(d); e2b = xyz(b) - xyz(c); ngb = cross(e2b, e1b);         // (c, d, b)
+            f.c.w = 1.0f;
+        }
+    }
+    f.e1a.x = e1.x; f.e1a.y = e1.y; f.e1a.z = e1.z; f.e1a.w = c.w;
+    f.e2a.x = e2.x; f.e2a.y = e2.y; f.e2a.z = e2.z; f.e2a.w = d.w;
+    f.nga.x = ng.x; f.nga.y = ng.y; f.nga.z = ng.z; f.nga.w = ngb.x;
+    f.e1b.x = e1b.x; f.e1b.y = e1b.y; f.e1b.z = e1b.z; f.e1b.w = ngb.y;
+    f.e2b.x = e2b.x; f.e2b.y = e2b.y; f.e2b.z = e2b.z; f.e2b.w = ngb.z;
+    return f;
+}
+
+// prim_test_rec on a FlatPrim
+QZ_HD void flat_prim_test(const DScene& sc, const FlatPrim& f, uint32_t slot, V3 O, V3 D, float tnear, float tfar, Hit& best) {
+    const uint32_t w2 = float_as_u32(f.e1a.w);
+    const uint32_t kind = prim_kind(w2);
+    PrimHit h;
+    bool found = false;
+    if (kind == QZ_PRIM_SPHERE) {
+        found = sphere_test(O, D, tnear, tfar, xyz(f.a), f.b.x, h);
+    } else if (kind == QZ_PRIM_TRIANGLE) {
+        found = tri_test_pre(O, D, tnear, tfar, xyz(f.a), xyz(f.e1a), xyz(f.e2a), xyz(f.nga), false, h);
+    } else {
+        PrimHit ha, hb;
+        bool fa = tri_test_pre(O, D, tnear, tfar, xyz(f.a), xyz(f.e1a), xyz(f.e2a), xyz(f.nga), false, ha);
+        bool fb = f.c.w != 0.0f &&
+                  tri_test_pre(O, D, tnear, tfar, xyz(f.c), xyz(f.e1b), xyz(f.e2b), v3(f.nga.w, f.e1b.w, f.e2b.w), true, hb);
+        if (fa && (!fb || ha.t <= hb.t)) { h = ha; found = true; }
+        else if (fb) { h = hb; found = true; }
+        if (found && kind == QZ_PRIM_GRIDCELL) {
+            const uint32_t cell = float_as_u32(f.e2a.w);
+            const uint32_t dims = sc.grid_dims[float_as_u32(f.a.w)];
+            h.u = ((float)(cell & 0xffffu) + h.u) / (float)(dims & 0xffffu);
+            h.v = ((float)(cell >> 16) + h.v) / (float)(dims >> 16);
+        }
+    }
+    if (!found) return;
+    const uint32_t key = prim_key(w2);
+    if (h.t < best.t || (h.t == best.t && key < best.key)) {
+        best.t = h.t; best.u = h.u; best.v = h.v; best.ng = h.ng; best.prim = slot; best.key = key;
+        best.geom_id = float_as_u32(f.a.w); best.prim_id = float_as_u32(f.b.w);
     }
 }
 

@@ -378,9 +378,10 @@ __global__ void __launch_bounds__(128) k_closest_hit(DScene sc, WfBuffers b, uin
 // reads.  The result is the brute-force minimum under the (t, key) order, i.e. exactly what the
 // BVH traversal is defined to return.
 __global__ void __launch_bounds__(256) k_closest_flat(DScene sc, WfBuffers b, uint32_t flags) {
-    __shared__ F4 s_prims[QZ_FLAT_MAX_PRIMS * 4];
+    __shared__ FlatPrim s_prims[QZ_FLAT_MAX_PRIMS];
     const uint32_t n_prims = sc.n_prims;
-    for (uint32_t i = threadIdx.x; i < n_prims * 4; i += blockDim.x) s_prims[i] = sc.prims[i];
+    for (uint32_t i = threadIdx.x; i < n_prims; i += blockDim.x)
+        s_prims[i] = make_flat_prim(sc.prims[4 * i], sc.prims[4 * i + 1], sc.prims[4 * i + 2], sc.prims[4 * i + 3]);
     __syncthreads();
     for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < b.pool; slot += gridDim.x * blockDim.x) {
         const uint8_t st = b.stage[slot];
@@ -392,15 +393,16 @@ __global__ void __launch_bounds__(256) k_closest_flat(DScene sc, WfBuffers b, ui
         best.ng = v3(0.0f, 0.0f, 0.0f); best.geom_id = QZ_NO_HIT; best.prim_id = 0;
 #pragma unroll 1
         for (uint32_t p = 0; p < n_prims; p++)
-            prim_test_rec(sc, s_prims[4 * p], s_prims[4 * p + 1], s_prims[4 * p + 2], s_prims[4 * p + 3], p, O, D, QZ_TNEAR, INFINITY, best);
+            flat_prim_test(sc, s_prims[p], p, O, D, QZ_TNEAR, INFINITY, best);
         finish_closest(sc, b, slot, st == ST_TRACE_FIRST, best, flags);
     }
 }
 
 __global__ void __launch_bounds__(256) k_shadow_flat(DScene sc, WfBuffers b) {
-    __shared__ F4 s_prims[QZ_FLAT_MAX_PRIMS * 4];
+    __shared__ FlatPrim s_prims[QZ_FLAT_MAX_PRIMS];
     const uint32_t n_prims = sc.n_prims;
-    for (uint32_t i = threadIdx.x; i < n_prims * 4; i += blockDim.x) s_prims[i] = sc.prims[i];
+    for (uint32_t i = threadIdx.x; i < n_prims; i += blockDim.x)
+        s_prims[i] = make_flat_prim(sc.prims[4 * i], sc.prims[4 * i + 1], sc.prims[4 * i + 2], sc.prims[4 * i + 3]);
     __syncthreads();
     const uint32_t count = b.counters[C_SHADOW];
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
@@ -413,7 +415,7 @@ __global__ void __launch_bounds__(256) k_shadow_flat(DScene sc, WfBuffers b) {
         // occluded iff the closest hit has t <= 1 (scene.cpp:136-143)
 #pragma unroll 1
         for (uint32_t p = 0; p < n_prims; p++)
-            prim_test_rec(sc, s_prims[4 * p], s_prims[4 * p + 1], s_prims[4 * p + 2], s_prims[4 * p + 3], p, O, D, QZ_TNEAR, INFINITY, best);
+            flat_prim_test(sc, s_prims[p], p, O, D, QZ_TNEAR, INFINITY, best);
         if (!(best.prim != QZ_NO_HIT && best.t <= 1.0f)) {
             const float4 L = b.radiance[slot], c = b.sh_c[slot];
             b.radiance[slot] = f4(L.x + c.x, L.y + c.y, L.z + c.z, L.w + c.w);
