@@ -62,8 +62,8 @@ QZ_HD bool tri_test(V3 O, V3 D, float tnear, float tfar, V3 v0, V3 v1, V3 v2, bo
     return tri_test_pre(O, D, tnear, tfar, v0, e1, e2, ng, flip, h);
 }
 
-QZ_HD bool sphere_test(V3 O, V3 D, float tnear, float tfar, V3 c, float r, PrimHit& h) {
-    float rd2 = 1.0f / dot(D, D);
+// rd2 = 1 / dot(D, D) depends on the ray only: callers that test many spheres per ray pass it in
+QZ_HD bool sphere_test_rd2(V3 O, V3 D, float rd2, float tnear, float tfar, V3 c, float r, PrimHit& h) {
     V3 c0 = c - O;
     float projC0 = dot(c0, D) * rd2;
     V3 perp = c0 - D * projC0;
@@ -85,6 +85,11 @@ QZ_HD bool sphere_test(V3 O, V3 D, float tnear, float tfar, V3 c, float r, PrimH
     h.u = 0.0f;
     h.v = 0.0f;
     return true;
+}
+
+QZ_HD bool sphere_test(V3 O, V3 D, float tnear, float tfar, V3 c, float r, PrimHit& h) {
+    float rd2 = 1.0f / dot(D, D);
+    return sphere_test_rd2(O, D, rd2, tnear, tfar, c, r, h);
 }
 
 QZ_HD V3 xyz(const F4& f) { return v3(f.x, f.y, f.z); }
@@ -177,13 +182,13 @@ QZ_HD FlatPrim make_flat_prim(const F4& a, const F4& b, const F4& c, const F4& d
 }
 
 // prim_test_rec on a FlatPrim
-QZ_HD void flat_prim_test(const DScene& sc, const FlatPrim& f, uint32_t slot, V3 O, V3 D, float tnear, float tfar, Hit& best) {
+QZ_HD void flat_prim_test(const DScene& sc, const FlatPrim& f, uint32_t slot, V3 O, V3 D, float rd2, float tnear, float tfar, Hit& best) {
     const uint32_t w2 = float_as_u32(f.e1a.w);
     const uint32_t kind = prim_kind(w2);
     PrimHit h;
     bool found = false;
     if (kind == QZ_PRIM_SPHERE) {
-        found = sphere_test(O, D, tnear, tfar, xyz(f.a), f.b.x, h);
+        found = sphere_test_rd2(O, D, rd2, tnear, tfar, xyz(f.a), f.b.x, h);
     } else if (kind == QZ_PRIM_TRIANGLE) {
         found = tri_test_pre(O, D, tnear, tfar, xyz(f.a), xyz(f.e1a), xyz(f.e2a), xyz(f.nga), false, h);
     } else {

@@ -388,12 +388,13 @@ __global__ void __launch_bounds__(256) k_closest_flat(DScene sc, WfBuffers b, ui
         if (st == ST_EMPTY) { b.fam[slot] = QZ_FAM_NONE; continue; }
         const float4 o = b.ray_o[slot], d = b.ray_d[slot];
         const V3 O = v3(o.x, o.y, o.z), D = v3(d.x, d.y, d.z);
+        const float rd2 = 1.0f / dot(D, D);   // the ray's share of every sphere test
         Hit best;
         best.t = INFINITY; best.u = 0.0f; best.v = 0.0f; best.prim = QZ_NO_HIT; best.key = 0xffffffffu;
         best.ng = v3(0.0f, 0.0f, 0.0f); best.geom_id = QZ_NO_HIT; best.prim_id = 0;
 #pragma unroll 1
         for (uint32_t p = 0; p < n_prims; p++)
-            flat_prim_test(sc, s_prims[p], p, O, D, QZ_TNEAR, INFINITY, best);
+            flat_prim_test(sc, s_prims[p], p, O, D, rd2, QZ_TNEAR, INFINITY, best);
         finish_closest(sc, b, slot, st == ST_TRACE_FIRST, best, flags);
     }
 }
@@ -409,13 +410,14 @@ __global__ void __launch_bounds__(256) k_shadow_flat(DScene sc, WfBuffers b) {
         const uint32_t slot = b.q_shadow[i];
         const float4 o = b.sh_o[slot], d = b.sh_d[slot];
         const V3 O = v3(o.x, o.y, o.z), D = v3(d.x, d.y, d.z);
+        const float rd2 = 1.0f / dot(D, D);   // the ray's share of every sphere test
         Hit best;
         best.t = INFINITY; best.u = 0.0f; best.v = 0.0f; best.prim = QZ_NO_HIT; best.key = 0xffffffffu;
         best.ng = v3(0.0f, 0.0f, 0.0f); best.geom_id = QZ_NO_HIT; best.prim_id = 0;
         // occluded iff the closest hit has t <= 1 (scene.cpp:136-143)
 #pragma unroll 1
         for (uint32_t p = 0; p < n_prims; p++)
-            flat_prim_test(sc, s_prims[p], p, O, D, QZ_TNEAR, INFINITY, best);
+            flat_prim_test(sc, s_prims[p], p, O, D, rd2, QZ_TNEAR, INFINITY, best);
         if (!(best.prim != QZ_NO_HIT && best.t <= 1.0f)) {
             const float4 L = b.radiance[slot], c = b.sh_c[slot];
             b.radiance[slot] = f4(L.x + c.x, L.y + c.y, L.z + c.z, L.w + c.w);
