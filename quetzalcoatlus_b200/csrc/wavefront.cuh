@@ -966,12 +966,21 @@ __device__ __forceinline__ uint32_t queue_roles(int queue_id, uint32_t n_lights)
 __global__ void __launch_bounds__(256) k_sample(DScene sc, WfBuffers b) {
     // prefix sums of (entries x roles) over the six sampled queues
     uint32_t start[SQ_COUNT + 1];
-    uint32_t roles[SQ_COUNT], nrole[SQ_COUNT];
+    uint32_t nrole[SQ_COUNT], rmagic[SQ_COUNT], rlist[SQ_COUNT];
     start[0] = 0;
 #pragma unroll
     for (int q = 0; q < SQ_COUNT; q++) {
-        roles[q] = queue_roles(q, sc.n_lights);
-        nrole[q] = __popc(roles[q]);
+        const uint32_t roles = queue_roles(q, sc.n_lights);
+        nrole[q] = __popc(roles);
+        // item -> (entry, role) without an integer division: ceil(2^32 / n) as a multiply-high magic (exact for
+        // items < 2^32 / 7), and the queue's roles listed in a nibble string
+        rmagic[q] = nrole[q] ? (uint32_t)(((1ull << 32) + nrole[q] - 1u) / nrole[q]) : 0u;
+        uint32_t list = 0, m = roles;
+#pragma unroll
+        for (int j = 0; j < R_COUNT; j++) {
+            if (m) { list |= (uint32_t)(__ffs(m) - 1) << (4 * j); m &= m - 1u; }
+        }
+        rlist[q] = list;
         start[q + 1] = start[q] + b.counters[C_SHADE0 + q] * nrole[q];
     }
     const uint32_t total = start[SQ_COUNT];
@@ -980,11 +989,9 @@ __global__ void __launch_bounds__(256) k_sample(DScene sc, WfBuffers b) {
 #pragma unroll
         for (int k = 1; k < SQ_COUNT; k++) q += (t >= start[k]) ? 1 : 0;
         const uint32_t local = t - start[q];
-        const uint32_t entry = local / nrole[q], r = local % nrole[q];
-        // r-th set bit of the role mask
-        uint32_t m = roles[q];
-        for (uint32_t k = 0; k < r; k++) m &= m - 1;
-        const int role = __ffs(m) - 1;
+        const uint32_t entry = nrole[q] == 1u ? local : __umulhi(local, rmagic[q]);
+        const uint32_t r = local - entry * nrole[q];
+        const int role = (int)((rlist[q] >> (4u * r)) & 15u);
         const uint32_t slot = b.q_shade[q][entry];
         const uint4 misc = b.misc[slot];
         const int fam = q % SQ_FAMILIES;
