@@ -1001,11 +1001,23 @@ __global__ void __launch_bounds__(256) k_sample(DScene sc, WfBuffers b) {
             const qz_material mat = sc.materials[sc.geoms[geom].material];
             nee = !(mat.alpha_x < 1e-3f && mat.alpha_y < 1e-3f);
         }
-        uint32_t dims[R_COUNT];
-        bounce_dims(misc.z & 0xffffu, nee, sc.n_lights != 0, dims);
+        // the dimension of this role: bounce_dims() in closed form while the bounce cannot wrap past the prime table
+        const uint32_t d0 = misc.z & 0xffffu;
+        const bool has_lights = sc.n_lights != 0;
+        uint32_t dim;
+        if (d0 + 10u < QZ_N_PRIMES) {
+            const uint32_t light0 = d0 + 1u + ((nee && has_lights) ? 1u : 0u);
+            const uint32_t bsdf0 = nee ? light0 + (has_lights ? 2u : 4u) : d0 + 1u;
+            dim = role == R_MAT ? d0 : role == R_PICK ? ((nee && has_lights) ? d0 + 1u : 2u) : role == R_LIGHT ? light0 : role == R_LIGHT + 1 ? light0 + 1u
+                : role == R_BSDF ? bsdf0 : role == R_BSDF + 1 ? bsdf0 + 1u : role == R_U1 ? bsdf0 + 2u : bsdf0 + 3u;
+        } else {
+            uint32_t dims[R_COUNT];
+            bounce_dims(d0, nee, has_lights, dims);
+            dim = dims[role];
+        }
         Sampler smp;
         smp.index = misc.y; smp.dim = 0;
-        reinterpret_cast<float*>(&b.samples[slot])[role] = sample_dimension(sc.sampler_table, smp, dims[role]);
+        reinterpret_cast<float*>(&b.samples[slot])[role] = sample_dimension(sc.sampler_table, smp, dim);
     }
 }
 
