@@ -176,9 +176,15 @@ typedef struct qz_region {
 #define QZ_FLAG_UNSORTED_SHADING 1u /* one uber shading kernel over the unsorted queue (evidence runs only) */
 #define QZ_FLAG_COUNT_TRAVERSAL 2u  /* count wide-node visits and primitive tests (slower; for B_ray)        */
 #define QZ_FLAG_FORCE_BVH 8u        /* use the BVH traversal kernels even for scenes small enough for the flat kernel */
-#define QZ_FLAG_LANE_TRAVERSAL 16u  /* first-generation one-ray-per-lane BVH kernels (evidence runs only) */
-#define QZ_FLAG_OCTET_TRAVERSAL 32u /* eight-lanes-per-ray BVH kernels (evidence runs only) */
+#define QZ_FLAG_LANE_TRAVERSAL 16u  /* (round-1 evidence arm, no longer built: QZ_ERR_INVALID) */
+#define QZ_FLAG_OCTET_TRAVERSAL 32u /* (round-1 evidence arm, no longer built: QZ_ERR_INVALID) */
 #define QZ_FLAG_STAGE_TIMING 4u     /* CUDA events around every stage (serialises the pipeline; for profiles) */
+/* Arithmetic mode.  By default radiometric values (spectra, BSDF values, pdfs, MIS weights, throughput, sensor
+ * response) use fused multiply-adds and the hardware reciprocal / square root: a few 1e-7 relative per operation,
+ * geometry and discrete decisions untouched (per-path radiance within ~1e-6 of the reference, 1e-4 allowed).  With
+ * this flag every float operation is performed as the reference's x86-64 build performs it: paths are
+ * bit-identical to the reference's, at about twice the shading time.                                             */
+#define QZ_FLAG_EXACT_ARITHMETIC 64u
 
 typedef struct qz_render_options {
     uint32_t flags;
@@ -211,6 +217,11 @@ int qz_abi_version(void);
  * (replaces initialize_device(), scene.cpp:12-20).                                        */
 int qz_init(int device);
 int qz_device_name(char* buf, size_t n);
+
+/* Flags OR-ed into the options of every later qz_render* / qz_trace_paths call of this thread (the reference's
+ * render() has no options argument: this is how a host application selects QZ_FLAG_EXACT_ARITHMETIC). Returns
+ * the previous value.                                                                                     */
+uint32_t qz_set_default_flags(uint32_t flags);
 
 /* Scene::Scene / ~Scene (scene.hpp:44-49) */
 int qz_scene_create(qz_scene* out);
@@ -255,6 +266,10 @@ int qz_eval_spectrum(qz_scene scene, int32_t id, uint32_t n, const float* lambda
 
 /* PixelSensor::to_sensor_rgb on the device (sensor.cpp:57-70): n x (u, L0..L3) -> n x rgb */
 int qz_sensor_eval(const qz_camera* camera, uint32_t n, const float* in, float* out);
+
+/* Device math probe, for parity of the restated libm functions: op 0 = (sinf, cosf) of n arguments -> 2n floats
+ * (csrc/math.cuh restates glibc's sincosf, which the oracle's std::sin / std::cos calls compile to).           */
+int qz_math_probe(int op, uint32_t n, const float* in, float* out);
 
 #ifdef __cplusplus
 }

@@ -389,6 +389,7 @@ struct Trav {
     float cur_dist;
     bool done;
     bool occluded;
+    bool overflow;   // a child was dropped because the stack was full: the result cannot be trusted
 };
 
 QZ_HD void trav_init(Trav& tv, const Ray& ray, float tmax_any) {
@@ -404,6 +405,7 @@ QZ_HD void trav_init(Trav& tv, const Ray& ray, float tmax_any) {
     tv.cur_dist = 0.0f;
     tv.done = false;
     tv.occluded = false;
+    tv.overflow = false;
 }
 
 // ANY_HIT: stop at the first primitive hit with t <= tmax_any (Scene::occluded,
@@ -444,6 +446,8 @@ QZ_HD void trav_step(const DScene& sc, Trav& tv, TraversalCounters* cnt) {
                     tv.stack[tv.sp].dist = d;
                     tv.stack[tv.sp].node = n.child_base + (m & 0x7fu);
                     tv.sp++;
+                } else {
+                    tv.overflow = true;
                 }
             } else {
                 const uint32_t first = n.leaf_base + (m & 31u);
@@ -479,6 +483,7 @@ QZ_HD bool closest_hit(const DScene& sc, const Ray& ray, Hit& hit, TraversalCoun
     Trav tv;
     trav_init(tv, ray, INFINITY);
     while (!tv.done) trav_step<false, COUNT>(sc, tv, cnt);
+    if (tv.overflow && sc.overflow) *sc.overflow = 1u;   // every writer stores the same value
     hit = tv.best;
     return hit.prim != QZ_NO_HIT;
 }
@@ -489,6 +494,7 @@ QZ_HD bool occluded(const DScene& sc, const Ray& ray, TraversalCounters* cnt) {
     Trav tv;
     trav_init(tv, ray, 1.0f);
     while (!tv.done) trav_step<true, COUNT>(sc, tv, cnt);
+    if (tv.overflow && sc.overflow) *sc.overflow = 1u;
     return tv.occluded;
 }
 

@@ -111,6 +111,20 @@ bool build_wide_bvh(Exec& ex, const F4* d_src_prims, uint32_t n, BvhBuildResult&
     ex.download(h_bounds, d_bounds, 12);
     float scene_ext = 0.0f;
     for (int a = 0; a < 3; a++) scene_ext = std::max(scene_ext, ordered_to_float(h_bounds[3 + a]) - ordered_to_float(h_bounds[a]));
+    // prim_box pads a box relative to the primitive's OWN coordinates, but the rounding error of the intersection
+    // arithmetic (C = v0 - O, perp = c0 - D * projC0) grows with the distance to the ray's ORIGIN, which may lie
+    // anywhere in the scene (a path leaving a 2000-unit plane towards a 0.8-unit sphere).  A second pad proportional to
+    // the largest coordinate of the scene keeps "BVH answer == brute force" for such rays too.
+    {
+        float far = 0.0f;
+        for (int a = 0; a < 6; a++) { const float v = std::fabs(ordered_to_float(h_bounds[a])); if (v <= 3.0e38f) far = std::max(far, v); }
+        const float far_pad = 3e-7f * far;
+        ex.parallel_for(n, QZ_LAMBDA(uint32_t i) {
+            Aabb b = d_box[i];
+            for (int a = 0; a < 3; a++) { b.lo[a] -= far_pad; b.hi[a] += far_pad; }
+            d_box[i] = b;
+        });
+    }
 
     // ---- hoisting of huge primitives
     uint32_t* d_large = ex.template alloc<uint32_t>(64);

@@ -29,20 +29,26 @@ QZ_HD V2 sample_uniform_disk(V2 uv) {
         r = off.y;
         theta = (float)(QZ_PI_2 - QZ_PI_4 * (double)(off.x / off.y));
     }
-    return v2(r * qz_cosf(theta), r * qz_sinf(theta));
+    float sn, cs;
+    qz_sincosf(theta, sn, cs);
+    return v2(r * cs, r * sn);
 }
 
 QZ_HD V2 sample_uniform_disk_polar(V2 uv) {
     float r = sqrtf(uv.x);
     float theta = (float)(QZ_2_PI * (double)uv.y);
-    return v2(r * qz_cosf(theta), r * qz_sinf(theta));
+    float sn, cs;
+    qz_sincosf(theta, sn, cs);
+    return v2(r * cs, r * sn);
 }
 
 QZ_HD V3 sample_uniform_sphere(V2 uv) {
     float z = 1.0f - 2.0f * uv.x;
     float r = sqrtf(std_max(0.0f, 1.0f - z * z));
     float phi = (float)(2.0 * QZ_PI * (double)uv.y);
-    return v3(r * qz_cosf(phi), r * qz_sinf(phi), z);
+    float sn, cs;
+    qz_sincosf(phi, sn, cs);
+    return v3(r * cs, r * sn, z);
 }
 
 QZ_HD V3 sample_cosine_hemisphere(V2 uv) {
@@ -52,7 +58,13 @@ QZ_HD V3 sample_cosine_hemisphere(V2 uv) {
 }
 
 // sampler.hpp:55-57: cos_theta * M_1_PI evaluated in double
-QZ_HD float cosine_hemisphere_pdf(float cos_theta) { return (float)((double)cos_theta * QZ_1_PI); }
+QZ_HD float cosine_hemisphere_pdf(float cos_theta) {
+#if QZ_FAST
+    return cos_theta * (float)QZ_1_PI;
+#else
+    return (float)((double)cos_theta * QZ_1_PI);
+#endif
+}
 
 // ------------------------------------------------------------------ local-frame helpers (bxdf.cpp:8-45)
 QZ_HD float cos2_theta(V3 w) { return w.z * w.z; }
@@ -139,7 +151,44 @@ QZ_HD float fresnel_complex(float cos_theta_i, Cx ior) {
     return 0.5f * (n_par + n_perp);
 }
 
+#if QZ_FAST
+// Radiometric build: the same formula in float complex arithmetic (cos_theta_i >= 0 at every call site).
+QZ_HD Cx fcx_div(Cx a, Cx b) {
+    const float inv = r_rcp(r_fma(b.re, b.re, b.im * b.im));
+    return cx(r_fma(a.re, b.re, a.im * b.im) * inv, r_fma(a.im, b.re, -(a.re * b.im)) * inv);
+}
+QZ_HD Cx fcx_sqrt(Cx z) {
+    // principal square root; (re, im) = (r, im / 2r) with r = sqrt((|z| + re) / 2) for re >= 0, mirrored otherwise
+    const float d = r_sqrt(r_fma(z.re, z.re, z.im * z.im));
+    if (d == 0.0f) return cx(0.0f, 0.0f);
+    if (z.re >= 0.0f) {
+        const float r = r_sqrt(0.5f * (d + z.re));
+        return cx(r, 0.5f * r_div(z.im, r));
+    }
+    const float sI = r_sqrt(0.5f * (d - z.re));
+    return cx(fabsf(0.5f * r_div(z.im, sI)), copysignf(sI, z.im));
+}
+QZ_HD float fresnel_complex_fast(float cos_theta_i, Cx ior) {
+    cos_theta_i = std_clamp(cos_theta_i, 0.0f, 1.0f);
+    const float sin2_theta_i = r_fma(-cos_theta_i, cos_theta_i, 1.0f);
+    const Cx ior2 = cx(r_fma(ior.re, ior.re, -(ior.im * ior.im)), 2.0f * ior.re * ior.im);
+    const Cx sin2_theta_t = fcx_div(cx(sin2_theta_i, 0.0f), ior2);
+    const Cx cos_theta_t = fcx_sqrt(cx(1.0f - sin2_theta_t.re, -sin2_theta_t.im));
+    const Cx ic = cx(ior.re * cos_theta_i, ior.im * cos_theta_i);
+    const Cx r_parallel = fcx_div(cx(ic.re - cos_theta_t.re, ic.im - cos_theta_t.im), cx(ic.re + cos_theta_t.re, ic.im + cos_theta_t.im));
+    const Cx it = cx(r_fma(ior.re, cos_theta_t.re, -(ior.im * cos_theta_t.im)), r_fma(ior.re, cos_theta_t.im, ior.im * cos_theta_t.re));
+    const Cx r_perp = fcx_div(cx(cos_theta_i - it.re, -it.im), cx(cos_theta_i + it.re, it.im));
+    const float n_par = r_fma(r_parallel.re, r_parallel.re, r_parallel.im * r_parallel.im);
+    const float n_perp = r_fma(r_perp.re, r_perp.re, r_perp.im * r_perp.im);
+    return 0.5f * (n_par + n_perp);
+}
+#endif
+
 QZ_HD Spec4 fresnel_conductor(float cos_theta_i, const Spec4& eta, const Spec4& k) {
+#if QZ_FAST
+    return spec4(fresnel_complex_fast(cos_theta_i, cx(eta.v[0], k.v[0])), fresnel_complex_fast(cos_theta_i, cx(eta.v[1], k.v[1])),
+                 fresnel_complex_fast(cos_theta_i, cx(eta.v[2], k.v[2])), fresnel_complex_fast(cos_theta_i, cx(eta.v[3], k.v[3])));
+#endif
     return spec4(fresnel_complex(cos_theta_i, cx(eta.v[0], k.v[0])), fresnel_complex(cos_theta_i, cx(eta.v[1], k.v[1])),
                  fresnel_complex(cos_theta_i, cx(eta.v[2], k.v[2])), fresnel_complex(cos_theta_i, cx(eta.v[3], k.v[3])));
 }
@@ -150,6 +199,37 @@ struct TRDist {
 };
 QZ_HD bool tr_is_smooth(const TRDist& d) { return d.ax < 1e-3f && d.ay < 1e-3f; }
 
+#if QZ_FAST
+// radiometric build of D, Lambda, G1, G, D_visible: float throughout, one reciprocal square root for cos/sin phi
+QZ_HD void tr_phi(V3 w, float& cphi, float& sphi, float& sin2) {
+    sin2 = std_max(0.0f, r_fma(-w.z, w.z, 1.0f));
+    if (sin2 == 0.0f) { cphi = 1.0f; sphi = 0.0f; return; }
+    const float inv = r_rsqrt(sin2);
+    cphi = std_clamp(w.x * inv, -1.0f, 1.0f);
+    sphi = std_clamp(w.y * inv, -1.0f, 1.0f);
+}
+QZ_HD float tr_D(const TRDist& d, V3 wm) {
+    float cphi, sphi, sin2;
+    tr_phi(wm, cphi, sphi, sin2);
+    const float c2 = wm.z * wm.z;
+    const float tan2 = r_div(sin2, c2);
+    if (is_inf(tan2) || tan2 != tan2) return 0.0f;
+    const float a = r_div(cphi, d.ax), b = r_div(sphi, d.ay);
+    const float e1 = r_fma(tan2, r_fma(a, a, b * b), 1.0f);
+    return r_rcp((float)QZ_PI * d.ax * d.ay * (c2 * c2) * (e1 * e1));
+}
+QZ_HD float tr_lambda(const TRDist& d, V3 w) {
+    float cphi, sphi, sin2;
+    tr_phi(w, cphi, sphi, sin2);
+    const float tan2 = r_div(sin2, w.z * w.z);
+    if (is_inf(tan2) || tan2 != tan2) return 0.0f;
+    const float a = cphi * d.ax, b = sphi * d.ay;
+    return 0.5f * (r_sqrt(r_fma(r_fma(a, a, b * b), tan2, 1.0f)) - 1.0f);
+}
+QZ_HD float tr_G1(const TRDist& d, V3 w) { return r_rcp(1.0f + tr_lambda(d, w)); }
+QZ_HD float tr_G(const TRDist& d, V3 wo, V3 wi) { return r_rcp(1.0f + tr_lambda(d, wo) + tr_lambda(d, wi)); }
+QZ_HD float tr_D_visible(const TRDist& d, V3 w, V3 wm) { return r_div(tr_G1(d, w), fabsf(w.z)) * tr_D(d, wm) * fabsf(dot(w, wm)); }
+#else
 QZ_HD float tr_D(const TRDist& d, V3 wm) {
     float tan2 = tan2_theta(wm);
     if (is_inf(tan2)) return 0.0f;
@@ -172,6 +252,7 @@ QZ_HD float tr_G1(const TRDist& d, V3 w) { return 1.0f / (1.0f + tr_lambda(d, w)
 QZ_HD float tr_G(const TRDist& d, V3 wo, V3 wi) { return 1.0f / (1.0f + tr_lambda(d, wo) + tr_lambda(d, wi)); }
 // distribution of visible normals (bxdf.cpp:230-232)
 QZ_HD float tr_D_visible(const TRDist& d, V3 w, V3 wm) { return (tr_G1(d, w) / fabsf(w.z)) * tr_D(d, wm) * fabsf(dot(w, wm)); }
+#endif
 
 // visible-normal sampling from an already warped polar-disk point p (bxdf.cpp:255-272)
 QZ_HD V3 tr_sample_from_disk(const TRDist& d, V3 w, V2 p) {
@@ -253,9 +334,9 @@ QZ_HD Spec4 bxdf_f(const Bsdf& f, V3 wo, V3 wi) {
         if (cos_i == 0.0f || cos_o == 0.0f) return spec4(0.0f);
         V3 wm = wi + wo;
         if (norm_squared(wm) == 0.0f) return spec4(0.0f);
-        wm = normalized(wm);
+        wm = r_normalized(wm);
         Spec4 F = fresnel_conductor(fabsf(dot(wo, wm)), f.a, f.b);
-        return F * (tr_D(f.rough, wm) * tr_G(f.rough, wo, wi) / (4.0f * cos_i * cos_o));
+        return F * r_div(tr_D(f.rough, wm) * tr_G(f.rough, wo, wi), 4.0f * cos_i * cos_o);
     }
     return spec4(0.0f);
 }
@@ -270,8 +351,8 @@ QZ_HD float bxdf_pdf(const Bsdf& f, V3 wo, V3 wi) {
         if (wo.z * wi.z <= 0.0f || tr_is_smooth(f.rough)) return 0.0f;
         V3 wm = wo + wi;
         if (norm_squared(wm) == 0.0f) return 0.0f;
-        wm = dot(wm, v3(0.0f, 0.0f, 1.0f)) > 0.0f ? normalized(wm) : -normalized(wm);
-        return tr_D_visible(f.rough, wo, wm) / (4.0f * fabsf(dot(wo, wm)));
+        wm = dot(wm, v3(0.0f, 0.0f, 1.0f)) > 0.0f ? r_normalized(wm) : -r_normalized(wm);
+        return r_div(tr_D_visible(f.rough, wo, wm), 4.0f * fabsf(dot(wo, wm)));
     }
     return 0.0f;
 }
@@ -296,17 +377,17 @@ QZ_HD BsdfSample bxdf_sample(const Bsdf& f, V3 wo, float u1, V2 u2, bool use_dis
     if (is_kind<KH>(f, BX_CONDUCTOR)) {
         if (tr_is_smooth(f.rough)) {
             V3 wi = v3(-wo.x, -wo.y, wo.z);
-            s.spec = fresnel_conductor(fabsf(wi.z), f.a, f.b) / fabsf(wi.z);
+            s.spec = r_div(fresnel_conductor(fabsf(wi.z), f.a, f.b), fabsf(wi.z));
             s.wi = wi; s.pdf = 1.0f; s.specular = true; s.valid = true;
             return s;
         }
         V3 wm = use_disk ? tr_sample_from_disk(f.rough, wo, v2(disk.x, disk.y)) : tr_sample(f.rough, wo, u2);
         V3 wi = reflect(wo, wm);
         if (wo.z * wi.z <= 0.0f) return s;
-        s.pdf = tr_D_visible(f.rough, wo, wm) / (4.0f * fabsf(dot(wo, wm)));
+        s.pdf = r_div(tr_D_visible(f.rough, wo, wm), 4.0f * fabsf(dot(wo, wm)));
         float cos_o = fabsf(wo.z), cos_i = fabsf(wi.z);
         Spec4 F = fresnel_conductor(fabsf(dot(wo, wm)), f.a, f.b);
-        s.spec = F * (tr_D(f.rough, wm) * tr_G(f.rough, wo, wi) / (4.0f * cos_i * cos_o));
+        s.spec = F * r_div(tr_D(f.rough, wm) * tr_G(f.rough, wo, wi), 4.0f * cos_i * cos_o);
         s.wi = wi; s.valid = true;
         return s;
     }
@@ -388,18 +469,24 @@ QZ_HD BsdfSample bsdf_sample(const Bsdf& f, V3 wo_r, float u1, V2 u2) {
 template <int KH>
 QZ_HD Spec4 bsdf_rho_hd(const DScene& sc, const Bsdf& f, V3 wo_r) {
     V3 wo = to_local(f, wo_r);
+#if QZ_FAST
+    // diffuse: every one of the 16 terms is reflectance * (1/pi * |z_i|) / (|z_i| * 1/pi) -- the sum over the
+    // constant sample points is folded into one factor (rho_tab[128], build_rho_table)
+    if (is_kind<KH>(f, BX_DIFFUSE)) return f.a * sc.rho_tab[128];
+#endif
     Spec4 acc = spec4(0.0f);
 #pragma unroll 1
     for (int i = 0; i < 16; i++) {
         const float* t = sc.rho_tab + i * 8;
         V3 disk = is_kind<KH>(f, BX_DIFFUSE) ? v3(t[3], t[4], t[5]) : v3(t[6], t[7], 0.0f);
         BsdfSample s = bxdf_sample<KH>(f, wo, t[0], v2(t[1], t[2]), true, disk);
-        if (s.valid) acc = acc + s.spec * fabsf(s.wi.z) / s.pdf;
+        if (s.valid) acc = acc + r_div(s.spec * fabsf(s.wi.z), s.pdf);
     }
     return acc / 16.0f;
 }
 
-inline void build_rho_table(float* out /* 16 x 8 */) {
+#define QZ_RHO_TAB_FLOATS (16 * 8 + 1)
+inline void build_rho_table(float* out /* QZ_RHO_TAB_FLOATS */) {
     // render.cpp:153-167 (double literals narrowed to float, as the std::array initialisers do)
     const float uc[16] = {0.75741637, 0.37870818, 0.7083487, 0.18935409, 0.9149363, 0.35417435, 0.5990858, 0.09467703,
                           0.8578725, 0.45746812, 0.686759, 0.17708716, 0.9674518, 0.2995429, 0.5083201, 0.047338516};
@@ -415,6 +502,15 @@ inline void build_rho_table(float* out /* 16 x 8 */) {
         V2 p = sample_uniform_disk_polar(v2(u2[i][0], u2[i][1]));
         t[6] = p.x; t[7] = p.y;
     }
+    // [128]: mean over the 16 points of (1/pi * z) / pdf(z) with the reference's float / double roundings -- the
+    // factor the radiometric build multiplies a diffuse reflectance with (bsdf_rho_hd)
+    float acc = 0.0f;
+    for (int i = 0; i < 16; i++) {
+        const float z = fabsf(out[i * 8 + 5]);
+        const float pdf = (float)((double)z * QZ_1_PI);
+        if (pdf != 0.0f) acc += ((float)QZ_1_PI * z) / pdf;
+    }
+    out[128] = acc / 16.0f;
 }
 
 }  // namespace qz

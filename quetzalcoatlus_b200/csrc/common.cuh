@@ -19,6 +19,25 @@
 #include <stdint.h>
 #include <math.h>
 
+// ARITHMETIC MODES.  The device code exists in two builds (two translation units over the same
+// headers, csrc/k_shade_exact.cu and csrc/k_shade_fast.cu; the second renames the namespace):
+//   QZ_FAST == 0  every float operation as the reference's x86-64 build performs it (see below);
+//   QZ_FAST == 1  GEOMETRY and every DISCRETE DECISION still so -- ray origins and directions, hit
+//                 points, normals, frames, sampled directions, the dielectric interface (index of
+//                 refraction, Fresnel split, reflect-or-refract choice), texel and light picks --
+//                 while RADIOMETRIC values (spectra, BSDF values, pdfs, MIS weights, throughput,
+//                 sensor response, the depth-0 albedo AOV) use explicit fused multiply-adds, the
+//                 hardware reciprocal / reciprocal square root and float instead of double
+//                 intermediates: a few 1e-7 relative per operation, nothing fed back into the
+//                 geometry.  The only discrete decision that reads a radiometric value is Russian
+//                 roulette (throughput against a sample).
+// Both builds are compiled with -fmad=false: a fused multiply-add exists only where the source
+// says r_fma(), so a function gives the same bits in every kernel it is inlined into (the
+// wavefront film stays bit-identical to the per-path replay in either mode).
+#ifndef QZ_FAST
+#define QZ_FAST 0
+#endif
+
 #if defined(__CUDACC__)
 #define QZ_HD __host__ __device__ __forceinline__
 #define QZ_D __device__ __forceinline__
@@ -27,9 +46,9 @@
 // 350-700 KB of straight-line code that every warp streams through once per bounce: the
 // instruction caches miss constantly (no_instruction stalls, profiles/r01_summary.md).
 #ifndef QZ_INLINE_EVERYTHING
-#define QZ_HD_CALL __host__ __device__ __noinline__
+#define QZ_HD_CALL inline __host__ __device__ __noinline__
 #else
-#define QZ_HD_CALL __host__ __device__ __forceinline__
+#define QZ_HD_CALL inline __host__ __device__ __forceinline__
 #endif
 #else
 #define QZ_HD inline
@@ -100,6 +119,78 @@ QZ_HD float average(Spec4 a) {
     float sum = 0.0f;
     sum += a.v[0]; sum += a.v[1]; sum += a.v[2]; sum += a.v[3];
     return sum / 4.0f;
+}
+
+// ---- radiometric primitives (see ARITHMETIC MODES above).  With QZ_FAST == 0 each is the plain
+// IEEE expression, so code written with them is still the reference's arithmetic.
+QZ_HD float r_fma(float a, float b, float c) {
+#if QZ_FAST
+    return fmaf(a, b, c);
+#else
+    return a * b + c;
+#endif
+}
+// (the .approx.ftz forms are one MUFU instruction each; 1-2 ulp, denormal operands count as zero)
+QZ_HD float r_rcp(float x) {
+#if QZ_FAST && defined(__CUDA_ARCH__)
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#else
+    return 1.0f / x;
+#endif
+}
+QZ_HD float r_div(float a, float b) {
+#if QZ_FAST && defined(__CUDA_ARCH__)
+    return a * r_rcp(b);
+#else
+    return a / b;
+#endif
+}
+QZ_HD float r_sqrt(float x) {
+#if QZ_FAST && defined(__CUDA_ARCH__)
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#else
+    return sqrtf(x);
+#endif
+}
+QZ_HD float r_rsqrt(float x) {
+#if QZ_FAST && defined(__CUDA_ARCH__)
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#else
+    return 1.0f / sqrtf(x);
+#endif
+}
+// radiometric Spec4 division: 0 where the divisor is 0, like operator/
+QZ_HD Spec4 r_div(Spec4 a, float c) {
+#if QZ_FAST
+    if (c == 0.0f) return spec4(0.0f);
+    const float i = r_rcp(c);
+    return spec4(a.v[0] * i, a.v[1] * i, a.v[2] * i, a.v[3] * i);
+#else
+    return a / c;
+#endif
+}
+QZ_HD Spec4 r_div(Spec4 a, Spec4 b) {
+#if QZ_FAST
+    return spec4(b.v[0] == 0.0f ? 0.0f : r_div(a.v[0], b.v[0]), b.v[1] == 0.0f ? 0.0f : r_div(a.v[1], b.v[1]),
+                 b.v[2] == 0.0f ? 0.0f : r_div(a.v[2], b.v[2]), b.v[3] == 0.0f ? 0.0f : r_div(a.v[3], b.v[3]));
+#else
+    return a / b;
+#endif
+}
+// direction used for radiometric terms only (never stored in the path)
+QZ_HD V3 r_normalized(V3 a) {
+#if QZ_FAST
+    const float i = r_rsqrt(r_fma(a.z, a.z, r_fma(a.y, a.y, a.x * a.x)));
+    return v3(a.x * i, a.y * i, a.z * i);
+#else
+    return normalized(a);
+#endif
 }
 
 QZ_HD float u32_as_float(uint32_t u) {

@@ -1,0 +1,19 @@
+// Queue builder, sampler stage and film (wf_stage.cuh) behind the launch interface.
+#include "launch.h"
+#include "wf_stage.cuh"
+
+namespace qzl {
+using namespace qz;
+
+void bin(const Stage& s) {
+    k_bin<SQ_COUNT><<<s.bin_blocks, 256, 0, s.stream>>>(*static_cast<const WfBuffers*>(s.bufs));
+}
+void sample(const Stage& s) {
+    k_sample<<<s.lean_blocks * 2, 256, 0, s.stream>>>(*static_cast<const DScene*>(s.scene), *static_cast<const WfBuffers*>(s.bufs));
+}
+void film(const Stage& s, float* acc, bool first_pass, bool last_pass, uint32_t n_samples_total, float* color, float* normal,
+          float* albedo, int blocks) {
+    k_film<<<blocks, 256, 0, s.stream>>>(*static_cast<const WfBuffers*>(s.bufs), *static_cast<const PassParams*>(s.pass), acc, first_pass,
+                                         last_pass, n_samples_total, color, normal, albedo);
+}
+}  // namespace qzl

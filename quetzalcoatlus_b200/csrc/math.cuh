@@ -27,6 +27,62 @@ QZ_HD_CALL float qz_cosf(float x) {
     return cosf(x);
 #endif
 }
+// sinf and cosf of the same argument (every warp needs both): glibc's own algorithm.  glibc >= 2.28
+// computes sinf / cosf / sincosf (sysdeps/ieee754/flt-32/s_sinf.c, s_cosf.c, sincosf.h -- the ARM
+// optimized routines) in DOUBLE: quadrant n = round(x * 2/pi) by a scaled float-to-int conversion,
+// r = x - n * pi/2, then a degree-7 sine or degree-8 cosine polynomial in r, rounded to float once.
+// Restated here operation for operation, with the multiply-adds fused as in the FMA build of the functions
+// that glibc selects on every x86-64 CPU of the last decade (a build without FMA differs from it in about
+// one result in 1e8); IEEE double arithmetic gives the same double on the B200 as on x86-64, hence the
+// same float -- including the ~1.4 % of arguments where glibc's result is not the
+// correctly rounded one, which the earlier "sin() in double, rounded once" version got "wrong" by being
+// right.  (Checked bit for bit against glibc 2.39 on 2e8 arguments; tests/test_gpu_parity.py::
+// test_sincos_is_glibc.)  The oracle's g++ -O2 merges the reference's std::sin / std::cos pairs
+// (sampler.cpp:22-23,34,58-61) into sincosf, whose two results are these same two polynomials.
+// |x| >= 120 (never produced by the warps) falls back to the correctly rounded double functions.
+QZ_HD float qz_sincos_poly(double x, double x2, int n, bool negate_cos) {
+    if ((n & 1) == 0) {
+        const double x3 = x * x2;
+        const double s1 = fma(x2, -0x1.994eb3774cf24p-13, 0x1.1107605230bc4p-7);
+        const double x7 = x3 * x2;
+        const double s = fma(x3, -0x1.555545995a603p-3, x);
+        return (float)fma(x7, s1, s);
+    }
+    // cosine polynomial; glibc's second table entry (used when n & 2) holds the NEGATED coefficients, and
+    // since rounding is symmetric that is exactly the negated result
+    const double x4 = x2 * x2;
+    const double c2 = fma(x2, 0x1.99343027bf8c3p-16, -0x1.6c087e89a359dp-10);
+    const double c1 = fma(x2, -0x1.ffffffd0c621cp-2, 0x1p0);
+    const double x6 = x4 * x2;
+    const double c = fma(x4, 0x1.55553e1068f19p-5, c1);
+    const float r = (float)fma(x6, c2, c);
+    return negate_cos ? -r : r;
+}
+QZ_HD void qz_sincosf(float y, float& s, float& c) {
+#if defined(__CUDA_ARCH__)
+    const uint32_t top = (float_as_u32(y) >> 20) & 0x7ffu;
+    double x = (double)y;
+    if (top < 0x3f4u) {                       // |y| < 0.75 (abstop12(pi/4))
+        if (top < 0x398u) { s = y; c = 1.0f; return; }   // |y| < 2^-12
+        const double x2 = x * x;
+        s = qz_sincos_poly(x, x2, 0, false);
+        c = qz_sincos_poly(x, x2, 1, false);
+        return;
+    }
+    if (top >= 0x42fu) { s = qz_sinf(y); c = qz_cosf(y); return; }   // |y| >= 120, inf, nan
+    const double r = x * 0x1.45F306DC9C883p+23;
+    const int n = ((int)r + 0x800000) >> 24;
+    x = fma(-(double)n, 0x1.921FB54442D18p0, x);
+    const double sign = ((n & 3) == 1 || (n & 3) == 2) ? -1.0 : 1.0;
+    const bool neg = (n & 2) != 0;
+    const double xs = x * sign, x2 = x * x;
+    s = qz_sincos_poly(xs, x2, n, neg);
+    c = qz_sincos_poly(xs, x2, n ^ 1, neg);
+#else
+    s = sinf(y);
+    c = cosf(y);
+#endif
+}
 QZ_HD_CALL float qz_atan2f(float y, float x) {
 #if defined(__CUDA_ARCH__)
     return (float)atan2((double)y, (double)x);
@@ -50,5 +106,6 @@ QZ_HD_CALL float qz_acosf(float x) {
 
 // util.cpp:3-5
 QZ_HD float lerpf(float a, float b, float t) { return a + t * (b - a); }
+QZ_HD float r_lerp(float a, float b, float t) { return r_fma(t, b - a, a); }
 
 }  // namespace qz

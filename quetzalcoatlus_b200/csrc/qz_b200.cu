@@ -18,8 +18,9 @@
 #include <string>
 #include <vector>
 
+#include "launch.h"
 #include "scene_store.cuh"
-#include "wavefront.cuh"
+#include "wf_types.cuh"
 
 using namespace qz;
 
@@ -112,7 +113,7 @@ int device_tables(int dev, DeviceTables& out) {
     if (!t.sampler) {
         std::vector<SamplerDim> host(QZ_N_PRIMES);
         build_sampler_table(host.data());
-        float rho[16 * 8];
+        float rho[QZ_RHO_TAB_FLOATS];
         build_rho_table(rho);
         // records, then the prefix tables of every dimension (sampler.cuh), filled by a kernel
         const uint32_t n_prefix = plan_sampler_prefix(host.data(), QZ_N_PRIMES, QZ_PREFIX_CAP);
@@ -123,23 +124,41 @@ int device_tables(int dev, DeviceTables& out) {
             for (int d = QZ_N_PRIMES - 1; d >= 0; d--) { if (host[d].pre_pow) next = host[d].pre_offset; dim_start[d] = next; }
             dim_start[QZ_N_PRIMES] = n_prefix;
         }
-        QZ_CUDA(cudaMalloc(&t.sampler, host.size() * sizeof(SamplerDim) + (size_t)n_prefix * sizeof(uint16_t) + 16));
-        QZ_CUDA(cudaMemcpy(t.sampler, host.data(), host.size() * sizeof(SamplerDim), cudaMemcpyHostToDevice));
+        // built into locals and published only when every step has succeeded: a half-built entry would make every
+        // later call return QZ_OK with a null table
+        SamplerDim* d_sampler = nullptr;
         uint32_t* d_start = nullptr;
-        QZ_CUDA(cudaMalloc(&d_start, dim_start.size() * sizeof(uint32_t)));
-        QZ_CUDA(cudaMemcpy(d_start, dim_start.data(), dim_start.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
-        k_build_sampler_prefix<<<(n_prefix + 255) / 256, 256>>>(t.sampler, d_start, n_prefix);
-        QZ_CUDA(cudaGetLastError());
-        QZ_CUDA(cudaDeviceSynchronize());
-        cudaFree(d_start);
-        QZ_CUDA(cudaMalloc(&t.rho, sizeof(rho)));
-        QZ_CUDA(cudaMemcpy(t.rho, rho, sizeof(rho), cudaMemcpyHostToDevice));
+        float* d_rho = nullptr;
+        auto build = [&]() -> cudaError_t {
+            cudaError_t e;
+            if ((e = cudaMalloc(&d_sampler, host.size() * sizeof(SamplerDim) + (size_t)n_prefix * sizeof(uint16_t) + 16)) != cudaSuccess) return e;
+            if ((e = cudaMemcpy(d_sampler, host.data(), host.size() * sizeof(SamplerDim), cudaMemcpyHostToDevice)) != cudaSuccess) return e;
+            if ((e = cudaMalloc(&d_start, dim_start.size() * sizeof(uint32_t))) != cudaSuccess) return e;
+            if ((e = cudaMemcpy(d_start, dim_start.data(), dim_start.size() * sizeof(uint32_t), cudaMemcpyHostToDevice)) != cudaSuccess) return e;
+            k_build_sampler_prefix<<<(n_prefix + 255) / 256, 256>>>(d_sampler, d_start, n_prefix);
+            if ((e = cudaGetLastError()) != cudaSuccess) return e;
+            if ((e = cudaDeviceSynchronize()) != cudaSuccess) return e;
+            if ((e = cudaMalloc(&d_rho, sizeof(rho))) != cudaSuccess) return e;
+            return cudaMemcpy(d_rho, rho, sizeof(rho), cudaMemcpyHostToDevice);
+        };
+        const cudaError_t e = build();
+        if (d_start) cudaFree(d_start);
+        if (e != cudaSuccess) {
+            if (d_sampler) cudaFree(d_sampler);
+            if (d_rho) cudaFree(d_rho);
+            QZ_CUDA(e);
+        }
+        t.sampler = d_sampler;
+        t.rho = d_rho;
     }
     out = t;
     return QZ_OK;
 }
 
 thread_local int g_device = -1;
+thread_local uint32_t g_default_flags = 0;
+
+bool env_exact() { const char* e = std::getenv("QZ_EXACT"); return e && std::atoi(e) != 0; }
 
 int ensure_device() {
     if (g_device >= 0) {
@@ -162,20 +181,6 @@ DCamera make_camera(const qz_camera* c, const float* d_sensor) {
 }
 
 // ------------------------------------------------------------------ small kernels of the probes
-__global__ void k_trace_paths(DScene sc, DCamera cam, SamplerParams spar, uint32_t max_bounces, uint32_t n,
-                              const int32_t* xys, float* records) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    PathState ps;
-    PathAov aov;
-    Spec4 lambda0;
-    run_path<false>(sc, cam, spar, (uint32_t)xys[3 * i], (uint32_t)xys[3 * i + 1], (uint32_t)xys[3 * i + 2], max_bounces, ps,
-                    aov, lambda0, nullptr);
-    V3 rgb = to_sensor_rgb(cam, ps.L, ps.lambda, ps.pdf);
-    V3 argb = to_sensor_rgb(cam, aov.albedo, ps.lambda, ps.pdf);
-    write_trace_record(records + (size_t)i * 32, ps, aov, lambda0, rgb, argb);
-}
-
 __global__ void k_sampler_eval(const SamplerDim* table, SamplerParams spar, uint32_t n, const int32_t* q, float* out) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -207,6 +212,12 @@ __global__ void k_intersect(DScene sc, uint32_t n, const float* rays, float* out
         o[6] = (float)float_as_u32(rec[0].w);
         o[7] = (float)float_as_u32(rec[1].w);
     }
+}
+
+__global__ void k_math_probe(int op, uint32_t n, const float* in, float* out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (op == 0) qz_sincosf(in[i], out[2 * i], out[2 * i + 1]);
 }
 
 __global__ void k_eval_spectrum(DScene sc, int32_t id, uint32_t n, const float* lambdas, float* out) {
@@ -246,7 +257,7 @@ struct DevBuf {
 #define QZ_MAX_PIPELINES 4
 
 struct WorkMem {
-    DevBuf rec_hot, rec_side, qbufs[10], tags[3], counters, statsb, res_a, res_b, res_c, rowsb, sensor, acc;
+    DevBuf rec_hot, rec_side, qbufs[8], tags[3], counters, statsb, res_a, res_b, res_c, rowsb, sensor, acc;
     uint32_t pool = 0;
     uint64_t cells = 0, acc_pix = 0, rows = 0;
     uint32_t* h_counters = nullptr;  // pinned
@@ -279,6 +290,7 @@ struct qz_scene_t {
 extern "C" {
 
 const char* qz_last_error(void) { return g_error.c_str(); }
+uint32_t qz_set_default_flags(uint32_t flags) { const uint32_t old = g_default_flags; g_default_flags = flags; return old; }
 int qz_abi_version(void) { return QZ_ABI_VERSION; }
 
 int qz_init(int device) {
@@ -351,10 +363,12 @@ static int render_impl(qz_scene s, const qz_camera* camera, uint32_t n_samples, 
     const DScene& sc = s->store.view;
     const uint32_t W = camera->image_width, H = camera->image_height;
     if (!W || !H || !n_samples) return fail(QZ_ERR_INVALID, "empty image or zero samples");
-    if (max_bounces > 255) return fail(QZ_ERR_INVALID, "max_bounces > 255 is not supported");
+    if (max_bounces > 65535) return fail(QZ_ERR_INVALID, "max_bounces > 65535 is not supported (the path depth is a 16-bit field)");
     SamplerParams spar = make_sampler_params((int)W, (int)H);
     if ((uint64_t)n_samples * spar.stride >= (1ull << 31)) return fail(QZ_ERR_INVALID, "n_samples too large for the 32-bit Halton index");
-    const uint32_t flags = options ? options->flags : 0u;
+    const uint32_t flags = (options ? options->flags : 0u) | g_default_flags;
+    if (flags & (QZ_FLAG_LANE_TRAVERSAL | QZ_FLAG_OCTET_TRAVERSAL))
+        return fail(QZ_ERR_INVALID, "the first-generation traversal kernels (evidence arms of round 1) are no longer built");
 
     // rows owned by this call
     std::vector<uint32_t> rows;
@@ -387,8 +401,9 @@ static int render_impl(qz_scene s, const qz_camera* camera, uint32_t n_samples, 
 
     const bool count_trav = (flags & QZ_FLAG_COUNT_TRAVERSAL) != 0;
     const bool stage_timing = (flags & QZ_FLAG_STAGE_TIMING) != 0;
-    const bool lane_trav = (flags & QZ_FLAG_LANE_TRAVERSAL) != 0;  // first-generation per-lane kernels (evidence arm)
-    const bool oct_trav = (flags & QZ_FLAG_OCTET_TRAVERSAL) != 0;  // eight lanes per ray (evidence arm); default: phase-scheduled
+    // ARITHMETIC MODE (common.cuh): radiometric values fused / approximate by default; QZ_FLAG_EXACT_ARITHMETIC (or
+    // QZ_EXACT=1 in the environment) selects the kernels that keep the reference's arithmetic throughout
+    const bool exact = env_exact() || (flags & QZ_FLAG_EXACT_ARITHMETIC) != 0;
 
     // PIPELINES.  The pool is cut into P independent sub-pools, each with its own queues, tags and
     // counters and its own stream, all drawing new paths from one shared cursor.  Every stage kernel
@@ -407,7 +422,7 @@ static int render_impl(qz_scene s, const qz_camera* camera, uint32_t n_samples, 
 
     // ---- working memory (cached in the scene handle)
     WorkMem& wm = s->work;
-    DevBuf(&qbufs)[10] = wm.qbufs;
+    DevBuf(&qbufs)[SQ_COUNT] = wm.qbufs;
     DevBuf &counters = wm.counters, &statsb = wm.statsb, &res_a = wm.res_a, &res_b = wm.res_b, &res_c = wm.res_c,
            &rowsb = wm.rowsb, &sensor = wm.sensor, &acc = wm.acc;
     QZ_CUDA(wm.rec_hot.reserve((size_t)sub_pool * P * QZ_REC_BYTES));
@@ -442,8 +457,6 @@ static int render_impl(qz_scene s, const qz_camera* camera, uint32_t n_samples, 
         b.fam = wm.tags[1].as<uint8_t>() + (size_t)p * tag_stride;
         b.post = wm.tags[2].as<uint8_t>() + (size_t)p * tag_stride;
         for (int k = 0; k < SQ_COUNT; k++) b.q_shade[k] = qbufs[k].as<uint32_t>() + (size_t)p * q_stride;
-        b.q_shadow = qbufs[8].as<uint32_t>() + (size_t)p * q_stride;
-        b.q_done = qbufs[9].as<uint32_t>() + (size_t)p * q_stride;
         b.counters = counters.as<uint32_t>() + (size_t)p * C_WORDS;
         b.next_path = counters.as<uint32_t>() + C_NEXT_PATH;   // pipeline 0's block holds the shared cursor
         b.stats = statsb.as<unsigned long long>();
@@ -452,19 +465,16 @@ static int render_impl(qz_scene s, const qz_camera* camera, uint32_t n_samples, 
     }
 
     DCamera cam = make_camera(camera, sensor.as<float>());
-    // tiny scenes skip the BVH (k_closest_flat); counting runs and QZ_FLAG_FORCE_BVH keep the traversal kernels
+    // tiny scenes need no BVH (k_step_flat); counting runs and QZ_FLAG_FORCE_BVH keep the traversal kernels
     const bool flat = sc.n_prims <= QZ_FLAT_MAX_PRIMS && sc.n_prims > 0 && !count_trav && !(flags & QZ_FLAG_FORCE_BVH);
 
-    PassParams pp_cur{};   // the pass being rendered (captured by the iteration lambda)
+    PassParams pp_cur{};   // the pass being rendered
     int n_sm = 148;
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, s->device);
     static const int env_per_sm = [] { const char* e = std::getenv("QZ_BLOCKS_PER_SM"); int v = e ? std::atoi(e) : 0; return v; }();
     const int per_sm = env_per_sm > 0 ? env_per_sm : (P == 1 ? 8 : (P == 2 ? 4 : (P == 3 ? 3 : 2)));
-    const int trav_blocks = n_sm * per_sm;   // persistent CTAs of 4 warps
-    const int shade_blocks = n_sm * per_sm;
-    // the lean stages (sampler, flat intersection, albedo, finish, generate: 32-80 registers, 256-thread CTAs)
+    // the lean stages (sampler, flat step, albedo, finish, generate: 32-96 registers, 256-thread CTAs)
     static const int env_lean = [] { const char* e = std::getenv("QZ_LEAN_BLOCKS_PER_SM"); int v = e ? std::atoi(e) : 0; return v; }();
-    const int lean_blocks = n_sm * (env_lean > 0 ? env_lean : per_sm);
 
     if (!wm.ev_begin) {
         QZ_CUDA(cudaEventCreate(&wm.ev_begin)); QZ_CUDA(cudaEventCreate(&wm.ev_end));
@@ -481,6 +491,18 @@ static int render_impl(qz_scene s, const qz_camera* camera, uint32_t n_samples, 
     // with one pipeline everything runs on the caller's stream; otherwise the pipelines fork from it and join back
     cudaStream_t ps[QZ_MAX_PIPELINES];
     for (int p = 0; p < P; p++) ps[p] = P == 1 ? stream : wm.pipe_stream[p];
+
+    qzl::Stage stg[QZ_MAX_PIPELINES];
+    for (int p = 0; p < P; p++) {
+        qzl::Stage& g = stg[p];
+        g.scene = &sc; g.cam = &cam; g.bufs = &bufs[p]; g.pass = &pp_cur;
+        g.flags = flags; g.max_bounces = max_bounces;
+        g.lean_blocks = n_sm * (env_lean > 0 ? env_lean : per_sm);
+        g.shade_blocks = n_sm * per_sm;   // persistent CTAs of 4 warps
+        g.trav_blocks = n_sm * per_sm;
+        g.bin_blocks = (int)std::min<uint32_t>((sub_pool + 2047u) / 2048u, (uint32_t)n_sm * 8u);
+        g.stream = ps[p];
+    }
 
     // Stage timing: events are recorded asynchronously between the stages (no host sync inside
     // the pipeline) and read back once per pass, so the figures are device time per stage of the
@@ -506,79 +528,60 @@ static int render_impl(qz_scene s, const qz_camera* camera, uint32_t n_samples, 
         ev_used = 0;
         ev_target.clear();
     };
-    auto timed = [&](cudaStream_t q, float& acc_ms, auto&& launch) -> cudaError_t {
-        if (!stage_timing) { launch(); return cudaGetLastError(); }
+    auto timed = [&](cudaStream_t q, float& acc_ms, auto&& launch) {
+        if (!stage_timing) { launch(); return; }
         cudaEvent_t a = next_event(), c = next_event();
         cudaEventRecord(a, q);
         launch();
         cudaEventRecord(c, q);
         ev_target.push_back(&acc_ms);
         if (ev_used >= 8192) flush_events();
+    };
+
+    // one wavefront iteration of pipeline p (wf_types.cuh): 8 launches for flat scenes, 10 with the BVH
+    const int launches_per_iteration = flat ? 8 : 10;
+    auto enqueue_iteration = [&](int p) -> cudaError_t {
+        const qzl::Stage& g = stg[p];
+        cudaStream_t q = ps[p];
+        if (flat) {
+            timed(q, st.ms_closest, [&] { exact ? qzl::exact::step_flat(g) : qzl::fast::step_flat(g); });
+        } else {
+            timed(q, st.ms_shadow, [&] { qzl::trace_shadow(g, count_trav); });
+            timed(q, st.ms_other, [&] { exact ? qzl::exact::finish(g) : qzl::fast::finish(g); });
+            timed(q, st.ms_closest, [&] { qzl::trace_closest(g, count_trav); });
+        }
+        timed(q, st.ms_other, [&] { qzl::bin(g); });
+        timed(q, st.ms_sample, [&] { qzl::sample(g); });
+        timed(q, st.ms_shade, [&] {
+            exact ? qzl::exact::albedo(g) : qzl::fast::albedo(g);
+            for (int fam = 0; fam < 4; fam++) exact ? qzl::exact::shade(g, fam) : qzl::fast::shade(g, fam);
+        });
         return cudaGetLastError();
     };
 
-    const int bin_blocks = (int)std::min<uint32_t>((sub_pool + 2047u) / 2048u, (uint32_t)n_sm * 8u);
-    // one wavefront iteration of pipeline p
-    auto enqueue_iteration = [&](int p) -> cudaError_t {
-        const WfBuffers& b = bufs[p];
-        cudaStream_t q = ps[p];
-        cudaError_t e;
-        e = timed(q, st.ms_closest, [&] {
-            if (flat) k_closest_flat<<<lean_blocks, 256, 0, q>>>(sc, b, flags);
-            else if (lane_trav && count_trav) k_closest_hit<true><<<trav_blocks, 128, 0, q>>>(sc, b, flags);
-            else if (lane_trav) k_closest_hit<false><<<trav_blocks, 128, 0, q>>>(sc, b, flags);
-            else if (oct_trav && count_trav) k_trace_oct<false, true><<<trav_blocks, 128, 0, q>>>(sc, b, flags);
-            else if (oct_trav) k_trace_oct<false, false><<<trav_blocks, 128, 0, q>>>(sc, b, flags);
-            else if (count_trav) k_trace_lane<false, true><<<trav_blocks, 128, 0, q>>>(sc, b, flags);
-            else k_trace_lane<false, false><<<trav_blocks, 128, 0, q>>>(sc, b, flags);
-        });
-        if (e != cudaSuccess) return e;
-        e = timed(q, st.ms_other, [&] {
-            k_bin<SQ_COUNT, true><<<bin_blocks, 256, 0, q>>>(b.fam, nullptr, b.pool, b.counters + C_SHADE0, b, 0);
-        });
-        if (e != cudaSuccess) return e;
-        if (!(flags & QZ_FLAG_UNSORTED_SHADING)) {
-            e = timed(q, st.ms_sample, [&] { k_sample<<<lean_blocks * 2, 256, 0, q>>>(sc, b); });
-            if (e != cudaSuccess) return e;
-            e = timed(q, st.ms_shade, [&] { k_albedo_conductor<<<lean_blocks * 2, 256, 0, q>>>(sc, b, max_bounces); });
-            if (e != cudaSuccess) return e;
-        }
-        e = timed(q, st.ms_shade, [&] {
-            if (flags & QZ_FLAG_UNSORTED_SHADING) {
-                k_shade<KH_ANY, -1><<<shade_blocks, 128, 0, q>>>(sc, b, SQ_MISC, max_bounces);
-            } else {
-                k_shade<KH_ANY, 1><<<shade_blocks, 128, 0, q>>>(sc, b, SQ_FAMILIES + SQ_MISC, max_bounces);
-                k_shade<KH_DIFFUSE, 1><<<shade_blocks, 128, 0, q>>>(sc, b, SQ_FAMILIES + SQ_DIFFUSE, max_bounces);
-                k_shade<KH_CONDUCTOR, 1><<<shade_blocks, 128, 0, q>>>(sc, b, SQ_FAMILIES + SQ_CONDUCTOR, max_bounces);
-                k_shade<KH_DIELECTRIC, 1><<<shade_blocks, 128, 0, q>>>(sc, b, SQ_FAMILIES + SQ_DIELECTRIC, max_bounces);
-                k_shade<KH_ANY, 0><<<shade_blocks, 128, 0, q>>>(sc, b, SQ_MISC, max_bounces);
-                k_shade<KH_DIFFUSE, 0><<<shade_blocks, 128, 0, q>>>(sc, b, SQ_DIFFUSE, max_bounces);
-                k_shade<KH_CONDUCTOR, 0><<<shade_blocks, 128, 0, q>>>(sc, b, SQ_CONDUCTOR, max_bounces);
-                k_shade<KH_DIELECTRIC, 0><<<shade_blocks, 128, 0, q>>>(sc, b, SQ_DIELECTRIC, max_bounces);
-            }
-        });
-        if (e != cudaSuccess) return e;
-        e = timed(q, st.ms_other, [&] {
-            k_bin<2, false><<<bin_blocks, 256, 0, q>>>(b.post, b.fam, b.pool, b.counters + C_SHADOW, b, 1);
-        });
-        if (e != cudaSuccess) return e;
-        e = timed(q, st.ms_shadow, [&] {
-            if (flat) k_shadow_flat<<<lean_blocks, 256, 0, q>>>(sc, b);
-            else if (lane_trav && count_trav) k_shadow<true><<<trav_blocks, 128, 0, q>>>(sc, b);
-            else if (lane_trav) k_shadow<false><<<trav_blocks, 128, 0, q>>>(sc, b);
-            else if (oct_trav && count_trav) k_trace_oct<true, true><<<trav_blocks, 128, 0, q>>>(sc, b, flags);
-            else if (oct_trav) k_trace_oct<true, false><<<trav_blocks, 128, 0, q>>>(sc, b, flags);
-            else if (count_trav) k_trace_lane<true, true><<<trav_blocks, 128, 0, q>>>(sc, b, flags);
-            else k_trace_lane<true, false><<<trav_blocks, 128, 0, q>>>(sc, b, flags);
-        });
-        if (e != cudaSuccess) return e;
-        e = timed(q, st.ms_other, [&] {
-            k_finish<<<lean_blocks, 256, 0, q>>>(sc, cam, b, pp_cur);
-            k_next_iteration<<<1, 32, 0, q>>>(b);
-        });
-        st.kernel_launches += (flags & QZ_FLAG_UNSORTED_SHADING) ? 7 : 16;
-        return e;
+    // The iteration of a pipeline is the same launch sequence with the same arguments for a whole pass: it is
+    // captured once per pass into a CUDA graph and replayed (QZ_GRAPH=0 launches kernel by kernel).
+    static const bool env_graph = [] { const char* e = std::getenv("QZ_GRAPH"); return !e || std::atoi(e) != 0; }();
+    const bool use_graph = env_graph && !stage_timing;
+    cudaGraphExec_t gexec[QZ_MAX_PIPELINES] = {};
+    auto drop_graphs = [&]() {
+        for (int p = 0; p < QZ_MAX_PIPELINES; p++) if (gexec[p]) { cudaGraphExecDestroy(gexec[p]); gexec[p] = nullptr; }
     };
+    // on any failure: nothing of this call may still be running on the cached buffers when the caller comes back
+    auto quiesce = [&]() {
+        for (int p = 0; p < P; p++) cudaStreamSynchronize(ps[p]);
+        cudaStreamSynchronize(stream);
+        drop_graphs();
+    };
+#define QZ_RENDER_CUDA(call)                                                                 \
+    do {                                                                                     \
+        cudaError_t e_ = (call);                                                             \
+        if (e_ != cudaSuccess) {                                                             \
+            quiesce();                                                                       \
+            g_error = std::string(#call) + ": " + cudaGetErrorString(e_);                    \
+            return e_ == cudaErrorMemoryAllocation ? QZ_ERR_OOM : QZ_ERR_CUDA;               \
+        }                                                                                    \
+    } while (0)
 
     int rc = QZ_OK;
     for (uint32_t s_begin = 0; s_begin < n_samples && rc == QZ_OK; s_begin += s_pass) {
@@ -598,18 +601,33 @@ static int render_impl(qz_scene s, const qz_camera* camera, uint32_t n_samples, 
         uint32_t first[QZ_MAX_PIPELINES], handed = 0;
         for (int p = 0; p < P; p++) { first[p] = std::min<uint32_t>(sub_pool, pp.total - handed); handed += first[p]; }
         init[C_NEXT_PATH] = handed;
-        QZ_CUDA(cudaMemcpyAsync(counters.p, init, sizeof(uint32_t) * C_WORDS * P, cudaMemcpyHostToDevice, stream));
+        QZ_RENDER_CUDA(cudaMemcpyAsync(counters.p, init, sizeof(uint32_t) * C_WORDS * P, cudaMemcpyHostToDevice, stream));
         if (P > 1) {
-            QZ_CUDA(cudaEventRecord(wm.fork, stream));
-            for (int p = 0; p < P; p++) QZ_CUDA(cudaStreamWaitEvent(ps[p], wm.fork, 0));
+            QZ_RENDER_CUDA(cudaEventRecord(wm.fork, stream));
+            for (int p = 0; p < P; p++) QZ_RENDER_CUDA(cudaStreamWaitEvent(ps[p], wm.fork, 0));
         }
         uint32_t id0 = 0;
         for (int p = 0; p < P; p++) {
-            k_generate<<<lean_blocks, 256, 0, ps[p]>>>(sc, cam, bufs[p], pp, id0, first[p]);
+            exact ? qzl::exact::generate(stg[p], id0, first[p]) : qzl::fast::generate(stg[p], id0, first[p]);
             id0 += first[p];
             st.kernel_launches++;
         }
-        QZ_CUDA(cudaGetLastError());
+        QZ_RENDER_CUDA(cudaGetLastError());
+        if (use_graph) {
+            drop_graphs();
+            for (int p = 0; p < P; p++) {
+                if (!first[p]) continue;
+                cudaGraph_t graph = nullptr;
+                QZ_RENDER_CUDA(cudaStreamBeginCapture(ps[p], cudaStreamCaptureModeThreadLocal));
+                const cudaError_t e1 = enqueue_iteration(p);
+                const cudaError_t e2 = cudaStreamEndCapture(ps[p], &graph);
+                QZ_RENDER_CUDA(e1);
+                QZ_RENDER_CUDA(e2);
+                const cudaError_t e3 = cudaGraphInstantiate(&gexec[p], graph, 0);
+                cudaGraphDestroy(graph);
+                QZ_RENDER_CUDA(e3);
+            }
+        }
 
         bool live[QZ_MAX_PIPELINES];
         for (int p = 0; p < P; p++) live[p] = first[p] > 0;
@@ -619,7 +637,9 @@ static int render_impl(qz_scene s, const qz_camera* camera, uint32_t n_samples, 
             for (int p = 0; p < P; p++) {
                 if (!live[p]) continue;
                 any = true;
-                QZ_CUDA(enqueue_iteration(p));
+                if (use_graph) QZ_RENDER_CUDA(cudaGraphLaunch(gexec[p], ps[p]));
+                else QZ_RENDER_CUDA(enqueue_iteration(p));
+                st.kernel_launches += launches_per_iteration;
             }
             if (!any) break;
             st.iterations++;
@@ -628,29 +648,35 @@ static int render_impl(qz_scene s, const qz_camera* camera, uint32_t n_samples, 
             // while the host waits for one pipeline the others still have their four iterations queued
             if ((it & 3u) == 0) {
                 for (int p = 0; p < P; p++)
-                    if (live[p]) QZ_CUDA(cudaMemcpyAsync(wm.h_counters + (size_t)p * C_WORDS, bufs[p].counters, C_WORDS * 4, cudaMemcpyDeviceToHost, ps[p]));
+                    if (live[p]) QZ_RENDER_CUDA(cudaMemcpyAsync(wm.h_counters + (size_t)p * C_WORDS, bufs[p].counters, C_WORDS * 4, cudaMemcpyDeviceToHost, ps[p]));
                 for (int p = 0; p < P; p++) {
                     if (!live[p]) continue;
-                    QZ_CUDA(cudaStreamSynchronize(ps[p]));
+                    QZ_RENDER_CUDA(cudaStreamSynchronize(ps[p]));
                     if (wm.h_counters[(size_t)p * C_WORDS + C_ACTIVE] == 0) live[p] = false;
                 }
             }
             if (it > 1000000ull) { rc = fail(QZ_ERR_CUDA, "wavefront did not terminate"); break; }
         }
         if (rc != QZ_OK) break;
+        // (an iteration whose trace stage found no live slot has finished every path: the finish stage runs FIRST in an
+        // iteration, on the post tags the previous shading stage left)
         if (P > 1) {
             for (int p = 0; p < P; p++) {
-                QZ_CUDA(cudaEventRecord(wm.pipe_done[p], ps[p]));
-                QZ_CUDA(cudaStreamWaitEvent(stream, wm.pipe_done[p], 0));
+                QZ_RENDER_CUDA(cudaEventRecord(wm.pipe_done[p], ps[p]));
+                QZ_RENDER_CUDA(cudaStreamWaitEvent(stream, wm.pipe_done[p], 0));
             }
         }
         const bool first_pass = s_begin == 0, last_pass = s_begin + pp.s_count >= n_samples;
-        k_film<<<n_sm * 8, 256, 0, stream>>>(bufs[0], pp, acc.as<float>(), first_pass, last_pass, n_samples, d_color, d_normal, d_albedo);
+        qzl::Stage fs = stg[0];
+        fs.stream = stream;
+        qzl::film(fs, acc.as<float>(), first_pass, last_pass, n_samples, d_color, d_normal, d_albedo, n_sm * 8);
         st.kernel_launches++;
-        QZ_CUDA(cudaGetLastError());
+        QZ_RENDER_CUDA(cudaGetLastError());
     }
-    QZ_CUDA(cudaEventRecord(ev_end, stream));
-    QZ_CUDA(cudaEventSynchronize(ev_end));
+    if (rc != QZ_OK) { quiesce(); return rc; }
+    QZ_RENDER_CUDA(cudaEventRecord(ev_end, stream));
+    QZ_RENDER_CUDA(cudaEventSynchronize(ev_end));
+    drop_graphs();
     if (stage_timing) flush_events();
     QZ_CUDA(cudaEventElapsedTime(&st.ms_total, ev_begin, ev_end));
     unsigned long long h_stats[S_WORDS];
@@ -662,11 +688,12 @@ static int render_impl(qz_scene s, const qz_camera* camera, uint32_t n_samples, 
     st.node_visits = h_stats[S_NODES];
     st.prim_tests = h_stats[S_PRIMS];
     st.stack_overflows = (uint32_t)std::min<unsigned long long>(h_stats[S_OVERFLOW], 0xffffffffull);
-    if (rc == QZ_OK && st.stack_overflows)
-        rc = fail(QZ_ERR_CUDA, "BVH traversal stack overflow: the tree is deeper than the shared-memory stack (QZ_OCT_STACK)");
+    if (st.stack_overflows)
+        rc = fail(QZ_ERR_CUDA, "BVH traversal stack overflow: the tree is deeper than the per-lane stack (QZ_STACK entries, bvh.cuh)");
     if (rc == QZ_OK && h_stats[S_PATHS_DONE] != st.paths) rc = fail(QZ_ERR_CUDA, "internal error: finished path count does not match");
     if (stats_out) *stats_out = st;
     return rc;
+#undef QZ_RENDER_CUDA
 }
 
 int qz_render_device(qz_scene s, const qz_camera* camera, uint32_t n_samples, uint32_t max_bounces, const qz_region* region,
@@ -749,10 +776,17 @@ int qz_trace_paths(qz_scene s, const qz_camera* camera, uint32_t n_samples, uint
     QZ_CUDA(cudaMemcpy(sensor.p, camera->sensor_rgb, 3 * 471 * 4, cudaMemcpyHostToDevice));
     DCamera cam = make_camera(camera, sensor.as<float>());
     SamplerParams spar = make_sampler_params((int)cam.width, (int)cam.height);
-    k_trace_paths<<<(n + 63) / 64, 64>>>(s->store.view, cam, spar, max_bounces, n, dx.as<int32_t>(), dr.as<float>());
+    QZ_CUDA(cudaMemset(s->store.view.overflow, 0, sizeof(uint32_t)));
+    if (env_exact() || (g_default_flags & QZ_FLAG_EXACT_ARITHMETIC))
+        qzl::exact::trace_paths(&s->store.view, &cam, &spar, max_bounces, n, dx.as<int32_t>(), dr.as<float>());
+    else
+        qzl::fast::trace_paths(&s->store.view, &cam, &spar, max_bounces, n, dx.as<int32_t>(), dr.as<float>());
     QZ_CUDA(cudaGetLastError());
     QZ_CUDA(cudaDeviceSynchronize());
     QZ_CUDA(cudaMemcpy(records, dr.p, (size_t)n * 128, cudaMemcpyDeviceToHost));
+    uint32_t overflow = 0;
+    QZ_CUDA(cudaMemcpy(&overflow, s->store.view.overflow, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    if (overflow) return fail(QZ_ERR_CUDA, "BVH traversal stack overflow in the per-path replay (QZ_STACK entries, bvh.cuh)");
     return QZ_OK;
 }
 
@@ -784,9 +818,13 @@ int qz_intersect(qz_scene s, uint32_t n, const float* rays, float* out) {
     QZ_CUDA(dr.alloc((size_t)n * 24));
     QZ_CUDA(dout.alloc((size_t)n * 32));
     QZ_CUDA(cudaMemcpy(dr.p, rays, (size_t)n * 24, cudaMemcpyHostToDevice));
+    QZ_CUDA(cudaMemset(s->store.view.overflow, 0, sizeof(uint32_t)));
     k_intersect<<<(n + 127) / 128, 128>>>(s->store.view, n, dr.as<float>(), dout.as<float>());
     QZ_CUDA(cudaGetLastError());
     QZ_CUDA(cudaMemcpy(out, dout.p, (size_t)n * 32, cudaMemcpyDeviceToHost));
+    uint32_t overflow = 0;
+    QZ_CUDA(cudaMemcpy(&overflow, s->store.view.overflow, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    if (overflow) return fail(QZ_ERR_CUDA, "BVH traversal stack overflow in the intersection probe (QZ_STACK entries, bvh.cuh)");
     return QZ_OK;
 }
 
@@ -804,6 +842,21 @@ int qz_eval_spectrum(qz_scene s, int32_t id, uint32_t n, const float* lambdas, f
     k_eval_spectrum<<<(n + 127) / 128, 128>>>(s->store.view, id, n, dl.as<float>(), dout.as<float>());
     QZ_CUDA(cudaGetLastError());
     QZ_CUDA(cudaMemcpy(out, dout.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    return QZ_OK;
+}
+
+int qz_math_probe(int op, uint32_t n, const float* in, float* out) {
+    if (op != 0 || (!in && n) || (!out && n)) return fail(QZ_ERR_INVALID, "bad argument");
+    int rc = ensure_device();
+    if (rc) return rc;
+    if (!n) return QZ_OK;
+    DevBuf din, dout;
+    QZ_CUDA(din.alloc((size_t)n * 4));
+    QZ_CUDA(dout.alloc((size_t)n * 8));
+    QZ_CUDA(cudaMemcpy(din.p, in, (size_t)n * 4, cudaMemcpyHostToDevice));
+    k_math_probe<<<(n + 127) / 128, 128>>>(op, n, din.as<float>(), dout.as<float>());
+    QZ_CUDA(cudaGetLastError());
+    QZ_CUDA(cudaMemcpy(out, dout.p, (size_t)n * 8, cudaMemcpyDeviceToHost));
     return QZ_OK;
 }
 

@@ -168,24 +168,15 @@ struct SceneStore {
         view.sampler_table = d_sampler_table;
         view.rho_tab = d_rho_tab;
         view.leaf_prims = nullptr;
+        {
+            uint32_t* flag = ex.template alloc<uint32_t>(1);
+            ex.zero(flag, sizeof(uint32_t));
+            owned.push_back(flag);
+            view.overflow = flag;
+        }
         committed = true;
         return true;
     }
 };
-
-// per-path replay record (include/qz_b200.h: qz_trace_paths)
-QZ_HD void write_trace_record(float* rec, const PathState& ps, const PathAov& aov, const Spec4& lambda0, V3 rgb, V3 argb) {
-    for (int k = 0; k < 32; k++) rec[k] = 0.0f;
-    for (int k = 0; k < 4; k++) {
-        rec[k] = lambda0.v[k];
-        rec[4 + k] = ps.pdf.v[k];
-        rec[8 + k] = ps.L.v[k];
-        rec[16 + k] = aov.albedo.v[k];
-    }
-    rec[12] = aov.normal.x; rec[13] = aov.normal.y; rec[14] = aov.normal.z;
-    rec[15] = (float)ps.n_rays;
-    rec[20] = rgb.x; rec[21] = rgb.y; rec[22] = rgb.z;
-    rec[23] = argb.x; rec[24] = argb.y; rec[25] = argb.z;
-}
 
 }  // namespace qz

@@ -43,7 +43,7 @@ QZ_HD float power_heuristic(float f_pdf, float g_pdf) {
     float f = 1 * f_pdf;
     float g = 1 * g_pdf;
     if (is_inf(f * f)) return 1.0f;
-    return f * f / (f * f + g * g);
+    return r_div(f * f, r_fma(f, f, g * g));
 }
 
 // scene.cpp:27-39
@@ -74,8 +74,8 @@ QZ_HD Spec4 texture_value(const DScene& sc, int32_t tex_id, V2 uv, const Spec4& 
     if (y == t.height) y = t.height - 1;
     const float* px = sc.pool + t.offset + 3 * ((size_t)y * t.width + x);
     V3 c = rgb_to_sigmoid(sc, px[0], px[1], px[2]);
-    return spec4(sigmoid_poly(c.x, c.y, c.z, lambda.v[0]), sigmoid_poly(c.x, c.y, c.z, lambda.v[1]),
-                 sigmoid_poly(c.x, c.y, c.z, lambda.v[2]), sigmoid_poly(c.x, c.y, c.z, lambda.v[3]));
+    return spec4(sigmoid_poly<true>(c.x, c.y, c.z, lambda.v[0]), sigmoid_poly<true>(c.x, c.y, c.z, lambda.v[1]),
+                 sigmoid_poly<true>(c.x, c.y, c.z, lambda.v[2]), sigmoid_poly<true>(c.x, c.y, c.z, lambda.v[3]));
 }
 
 // material kind after resolving MixedMaterial with the bounce's material sample
@@ -232,8 +232,8 @@ QZ_HD void sample_lights(const DScene& sc, const SurfacePoint& sp, const Bsdf& f
     float pdf;
     if (l.kind == QZ_LIGHT_POINT) {
         V3 dv = lp - sp.point;
-        wi = normalized(dv);
-        spec = from_spectrum(sc, l.spectrum, lambda) * (l.scale / norm_squared(dv));
+        wi = r_normalized(dv);
+        spec = from_spectrum(sc, l.spectrum, lambda) * r_div(l.scale, norm_squared(dv));
         pdf = 1.0f;
         p_light = lp;
     } else {
@@ -248,7 +248,7 @@ QZ_HD void sample_lights(const DScene& sc, const SurfacePoint& sp, const Bsdf& f
         pdf = l.inv_area;
         V3 dv = p_light - sp.point;
         if (pdf == 0.0f || norm_squared(dv) == 0.0f) return;
-        wi = normalized(dv);
+        wi = r_normalized(dv);
         spec = light_emission(sc, l, n, -wi, lambda);
         if (is_zero(spec)) return;
     }
@@ -259,9 +259,9 @@ QZ_HD void sample_lights(const DScene& sc, const SurfacePoint& sp, const Bsdf& f
     if (l.kind != QZ_LIGHT_POINT) {
         float p_b = bsdf_pdf<KH>(f, sp.wo, wi);
         float w_l = power_heuristic(p_l, p_b);
-        result = spec * fv * (w_l / p_l);
+        result = spec * fv * r_div(w_l, p_l);
     } else {
-        result = spec * fv / p_l;
+        result = r_div(spec * fv, p_l);
     }
     has_shadow = true;
     p_light_out = p_light;
@@ -275,7 +275,8 @@ QZ_HD void sample_lights(const DScene& sc, const SurfacePoint& sp, const Bsdf& f
 // Radiance picked up AT the hit (emitter or background) is returned in `gain` (has_gain) rather
 // than added to ps.L: a bounce adds at most one such term, and the wavefront kernels only touch
 // the radiance buffer when there is one.  ps.L is neither read nor written here.
-template <int KH, int FIRST, class SRC>
+// ALBEDO_STAGE: the depth-0 albedo of (non-mixed) conductors is estimated by a separate kernel (k_albedo_conductor).
+template <int KH, int FIRST, bool ALBEDO_STAGE, class SRC>
 QZ_HD bool shade_bounce(const DScene& sc, PathState& ps, PathAov& aov, const Hit& hit, uint32_t max_bounces,
                         ShadowRequest& shadow, const SRC& src, Spec4& gain, bool& has_gain) {
     const bool first = FIRST < 0 ? ps.depth == 0 : FIRST != 0;
@@ -318,8 +319,8 @@ QZ_HD bool shade_bounce(const DScene& sc, PathState& ps, PathAov& aov, const Hit
     const int32_t mat = KH == KH_ANY ? resolve_material(sc, sp.material, mat_sample) : sp.material;
     Bsdf f = make_bsdf<KH>(sc, mat, sp, ps.lambda, ps.pdf);
 
-    // the wavefront's first-hit conductor kernel leaves the estimate to k_albedo_conductor (wavefront.cuh)
-    if (first && !(KH == KH_CONDUCTOR && FIRST == 1)) aov.albedo = bsdf_rho_hd<KH>(sc, f, sp.wo);
+    // the wavefront's conductor kernel leaves the estimate to k_albedo_conductor (wf_shade.cuh)
+    if (first && !(KH == KH_CONDUCTOR && ALBEDO_STAGE)) aov.albedo = bsdf_rho_hd<KH>(sc, f, sp.wo);
 
     if (!bsdf_is_specular<KH>(f)) {
         bool has_shadow;
@@ -348,7 +349,7 @@ QZ_HD bool shade_bounce(const DScene& sc, PathState& ps, PathAov& aov, const Hit
     BsdfSample bs = bsdf_sample<KH>(f, sp.wo, u1, u2);
     if (!bs.valid) return false;
 
-    ps.weight = ps.weight * (bs.spec * fabsf(dot(bs.wi, sp.normal)) / bs.pdf);
+    ps.weight = ps.weight * r_div(bs.spec * fabsf(dot(bs.wi, sp.normal)), bs.pdf);
     ps.p_b = bs.pdf;  // pdf_is_proportional is never set by any BxDF
     if (bs.specular) ps.flags |= QZ_FLAG_SPECULAR_BOUNCE; else ps.flags &= ~QZ_FLAG_SPECULAR_BOUNCE;
     if (bs.transmission) ps.ior_scale *= bs.ior;
@@ -363,7 +364,7 @@ QZ_HD bool shade_bounce(const DScene& sc, PathState& ps, PathAov& aov, const Hit
         float q = std_max(0.0f, 1.0f - max_component(rr));
         float roulette = src.one(R_RR, rr_dim);
         if (roulette < q) return false;
-        ps.weight = ps.weight / (1.0f - q);
+        ps.weight = r_div(ps.weight, 1.0f - q);
     }
     return !is_zero(ps.weight);
 }
@@ -406,7 +407,7 @@ QZ_HD void run_path(const DScene& sc, const DCamera& cam, const SamplerParams& s
         src.tab = sc.sampler_table; src.index = ps.smp.index;
         Spec4 gain;
         bool has_gain;
-        bool alive = shade_bounce<KH_ANY, -1>(sc, ps, aov, hit, max_bounces, sh, src, gain, has_gain);
+        bool alive = shade_bounce<KH_ANY, -1, false>(sc, ps, aov, hit, max_bounces, sh, src, gain, has_gain);
         if (has_gain) ps.L = ps.L + gain;
         if (ps.flags & QZ_FLAG_HAS_SHADOW) {
             Ray sr;
@@ -416,6 +417,21 @@ QZ_HD void run_path(const DScene& sc, const DCamera& cam, const SamplerParams& s
         }
         if (!alive) break;
     }
+}
+
+// per-path replay record (include/qz_b200.h: qz_trace_paths)
+QZ_HD void write_trace_record(float* rec, const PathState& ps, const PathAov& aov, const Spec4& lambda0, V3 rgb, V3 argb) {
+    for (int k = 0; k < 32; k++) rec[k] = 0.0f;
+    for (int k = 0; k < 4; k++) {
+        rec[k] = lambda0.v[k];
+        rec[4 + k] = ps.pdf.v[k];
+        rec[8 + k] = ps.L.v[k];
+        rec[16 + k] = aov.albedo.v[k];
+    }
+    rec[12] = aov.normal.x; rec[13] = aov.normal.y; rec[14] = aov.normal.z;
+    rec[15] = (float)ps.n_rays;
+    rec[20] = rgb.x; rec[21] = rgb.y; rec[22] = rgb.z;
+    rec[23] = argb.x; rec[24] = argb.y; rec[25] = argb.z;
 }
 
 }  // namespace qz

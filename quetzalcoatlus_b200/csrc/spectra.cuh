@@ -11,16 +11,29 @@
 
 namespace qz {
 
+// R = the value is RADIOMETRIC (common.cuh, ARITHMETIC MODES): evaluated with the r_* primitives, which are
+// the plain IEEE operations in the exact build.  R = false is the reference's arithmetic in both builds: the
+// index of refraction of a dielectric steers the refracted DIRECTION and is always evaluated that way.
+template <bool R> QZ_HD float t_div(float a, float b) { return R ? r_div(a, b) : a / b; }
+template <bool R> QZ_HD float t_fma(float a, float b, float c) { return R ? r_fma(a, b, c) : a * b + c; }
+
+template <bool R>
 QZ_HD float sigmoidf(float x) {
     if (is_inf(x)) return x > 0.0f ? 1.0f : 0.0f;
+    // (IEEE square root and division in the radiometric build as well: for a strongly negative x the result is the
+    // small difference 0.5 - 0.4999..., so an ulp of the quotient is 1e-4 of a dark reflectance -- the reference's
+    // value can only be matched by rounding the way it does)
     return 0.5f + 0.5f * x / (sqrtf(1.0f + x * x));
 }
 
+template <bool R>
 QZ_HD float sigmoid_poly(float c0, float c1, float c2, float lambda) {
-    return sigmoidf(c0 + c1 * lambda + c2 * lambda * lambda);
+    // (the polynomial too: saturated colours have coefficients in the thousands that cancel to an argument of order one)
+    return sigmoidf<R>(c0 + c1 * lambda + c2 * lambda * lambda);
 }
 
 // every kind except RGB_ILLUMINANT (which multiplies by another spectrum)
+template <bool R>
 QZ_HD float eval_spectrum_leaf(const DScene& sc, const qz_spectrum& s, float lambda) {
     {
         switch (s.kind) {
@@ -51,13 +64,15 @@ QZ_HD float eval_spectrum_leaf(const DScene& sc, const qz_spectrum& s, float lam
                 }
                 // l[count] and v[count] are the zero pads standing in for the reference's
                 // one-past-the-end read
-                float t = (lambda - l[first]) / (l[first + 1] - l[first]);
-                return v[first] * (1.0f - t) + v[first + 1] * t;
+                const float l0 = l[first], l1 = l[first + 1], v0 = v[first], v1 = v[first + 1];
+                float t = t_div<R>(lambda - l0, l1 - l0);
+                if (R && QZ_FAST) return r_fma(t, v1 - v0, v0);
+                return v0 * (1.0f - t) + v1 * t;
             }
             case QZ_SPEC_SIGMOID:
-                return sigmoid_poly(s.a, s.b, s.c, lambda);
+                return sigmoid_poly<R>(s.a, s.b, s.c, lambda);
             case QZ_SPEC_RGB_UNBOUNDED:
-                return s.scale * sigmoid_poly(s.a, s.b, s.c, lambda);
+                return s.scale * sigmoid_poly<R>(s.a, s.b, s.c, lambda);
             case QZ_SPEC_BLACKBODY: {
                 // spectrum.cpp:113-133; pow(lambda, 5) is a double pow, expm1f a float one
                 if (s.a <= 0.f) return s.b * 0.f;
@@ -73,27 +88,62 @@ QZ_HD float eval_spectrum_leaf(const DScene& sc, const qz_spectrum& s, float lam
     }
 }
 
-QZ_HD_CALL float eval_spectrum(const DScene& sc, int32_t id, float lambda) {
-    const qz_spectrum s = sc.spectra[id];
+QZ_HD qz_spectrum load_spectrum(const DScene& sc, int32_t id) {
+#if defined(__CUDA_ARCH__)
+    // one 32-byte record = two 16-byte loads through the read-only path
+    const uint4* p = reinterpret_cast<const uint4*>(sc.spectra + id);
+    const uint4 r0 = __ldg(p), r1 = __ldg(p + 1);
+    qz_spectrum s;
+    uint32_t* w = reinterpret_cast<uint32_t*>(&s);
+    w[0] = r0.x; w[1] = r0.y; w[2] = r0.z; w[3] = r0.w; w[4] = r1.x; w[5] = r1.y; w[6] = r1.z; w[7] = r1.w;
+    return s;
+#else
+    return sc.spectra[id];
+#endif
+}
+
+template <bool R>
+QZ_HD float eval_spectrum_rec(const DScene& sc, const qz_spectrum& s, float lambda) {
     if (s.kind == QZ_SPEC_RGB_ILLUMINANT) {
         if (s.aux < 0) return 0.0f;
         // m_scale * m_polynomial(lambda) * illuminant(lambda), left to right (rgb.cpp:191-196);
         // the illuminant is never itself an RGBIlluminantSpectrum (it is the colour space's D65)
-        float head = s.scale * sigmoid_poly(s.a, s.b, s.c, lambda);
-        const qz_spectrum ill = sc.spectra[s.aux];
-        return head * eval_spectrum_leaf(sc, ill, lambda);
+        float head = s.scale * sigmoid_poly<R>(s.a, s.b, s.c, lambda);
+        const qz_spectrum ill = load_spectrum(sc, s.aux);
+        return head * eval_spectrum_leaf<R>(sc, ill, lambda);
     }
-    return eval_spectrum_leaf(sc, s, lambda);
+    return eval_spectrum_leaf<R>(sc, s, lambda);
 }
 
-// SpectrumSample::from_spectrum (spectrum_sample.cpp:49-58)
-QZ_HD Spec4 from_spectrum(const DScene& sc, int32_t id, const Spec4& lambda) {
-    return spec4(eval_spectrum(sc, id, lambda.v[0]), eval_spectrum(sc, id, lambda.v[1]),
-                 eval_spectrum(sc, id, lambda.v[2]), eval_spectrum(sc, id, lambda.v[3]));
+// Spectrum::operator() in the reference's arithmetic (probes, index of refraction)
+QZ_HD_CALL float eval_spectrum(const DScene& sc, int32_t id, float lambda) {
+    return eval_spectrum_rec<false>(sc, load_spectrum(sc, id), lambda);
+}
+
+// SpectrumSample::from_spectrum (spectrum_sample.cpp:49-58), radiometric: the record (and an illuminant's
+// second record) is fetched ONCE for the four wavelengths, and the four evaluations are one instruction
+// stream the scheduler can interleave -- as four calls of eval_spectrum() they were four serial chains of
+// dependent loads, 12 % of a shading kernel's instructions for the record fetch alone.
+QZ_HD_CALL Spec4 from_spectrum(const DScene& sc, int32_t id, const Spec4& lambda) {
+    const qz_spectrum s = load_spectrum(sc, id);
+    if (s.kind == QZ_SPEC_RGB_ILLUMINANT) {
+        if (s.aux < 0) return spec4(0.0f);
+        const qz_spectrum ill = load_spectrum(sc, s.aux);
+        Spec4 r;
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            r.v[k] = (s.scale * sigmoid_poly<true>(s.a, s.b, s.c, lambda.v[k])) * eval_spectrum_leaf<true>(sc, ill, lambda.v[k]);
+        return r;
+    }
+    Spec4 r;
+#pragma unroll
+    for (int k = 0; k < 4; k++) r.v[k] = eval_spectrum_leaf<true>(sc, s, lambda.v[k]);
+    return r;
 }
 
 // RGBColorSpace::to_spectrum + RGBToSpectrumTable::operator() (rgb.cpp:50-57, 78-140);
-// returns (c0, c1, c2) of the sigmoid polynomial
+// returns (c0, c1, c2) of the sigmoid polynomial.  The reference's arithmetic in both builds: the
+// coefficients feed a polynomial whose terms cancel (see sigmoid_poly), so a relative 1e-7 here is 1e-4 there.
 QZ_HD_CALL V3 rgb_to_sigmoid(const DScene& sc, float r, float g, float b) {
     r = std_clamp(r, 0.0f, 1.0f); g = std_clamp(g, 0.0f, 1.0f); b = std_clamp(b, 0.0f, 1.0f);
     if (r == g && g == b) {
@@ -123,7 +173,7 @@ QZ_HD_CALL V3 rgb_to_sigmoid(const DScene& sc, float r, float g, float b) {
     for (uint32_t i = 0; i < 3; i++) {
 #define QZ_CO(a, bb, d) base[((zi + (d)) * 32 * 32 + (yi + (bb)) * 32 + (xi + (a))) * 3 + i]
         c[i] = lerpf(lerpf(lerpf(QZ_CO(0, 0, 0), QZ_CO(1, 0, 0), dx), lerpf(QZ_CO(0, 1, 0), QZ_CO(1, 1, 0), dx), dy),
-                     lerpf(lerpf(QZ_CO(0, 0, 1), QZ_CO(1, 0, 1), dx), lerpf(QZ_CO(0, 1, 1), QZ_CO(1, 1, 1), dx), dy), dz);
+                      lerpf(lerpf(QZ_CO(0, 0, 1), QZ_CO(1, 0, 1), dx), lerpf(QZ_CO(0, 1, 1), QZ_CO(1, 1, 1), dx), dy), dz);
 #undef QZ_CO
     }
     return v3(c[2], c[1], c[0]);
@@ -157,12 +207,15 @@ QZ_HD float sensor_curve(const float* curve, float lambda) {
 
 // PixelSensor::to_sensor_rgb (sensor.cpp:57-70) incl. the per-sample saturation clamp at 40
 QZ_HD V3 to_sensor_rgb(const DCamera& cam, const Spec4& L, const Spec4& lambda, const Spec4& pdf) {
-    Spec4 l = L / pdf;
+    Spec4 l = r_div(L, pdf);
     float rgb[3];
+    // the four curve indices are the same for the three curves
+    long idx[4];
+    for (int j = 0; j < 4; j++) idx[j] = lroundf(lambda.v[j] - 360.0f);
     for (int k = 0; k < 3; k++) {
         const float* curve = cam.sensor + k * 471;
-        Spec4 resp = spec4(sensor_curve(curve, lambda.v[0]), sensor_curve(curve, lambda.v[1]),
-                           sensor_curve(curve, lambda.v[2]), sensor_curve(curve, lambda.v[3]));
+        Spec4 resp;
+        for (int j = 0; j < 4; j++) resp.v[j] = (idx[j] < 0 || idx[j] >= 471) ? 0.0f : curve[idx[j]];
         rgb[k] = average(resp * l) * cam.imaging_ratio;
     }
     // std::max({x, y, z})
@@ -170,7 +223,7 @@ QZ_HD V3 to_sensor_rgb(const DCamera& cam, const Spec4& L, const Spec4& lambda, 
     if (m < rgb[1]) m = rgb[1];
     if (m < rgb[2]) m = rgb[2];
     if (m > 40.0f) {
-        float s = 40.0f / m;
+        float s = r_div(40.0f, m);
         rgb[0] *= s; rgb[1] *= s; rgb[2] *= s;
     }
     return v3(rgb[0], rgb[1], rgb[2]);

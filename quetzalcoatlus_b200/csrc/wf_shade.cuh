@@ -1,0 +1,369 @@
+// Arithmetic-bearing stages of the wavefront (wf_types.cuh).  This header is compiled twice -- csrc/k_shade_exact.cu
+// and csrc/k_shade_fast.cu, the two ARITHMETIC MODES of common.cuh -- and the host picks one set per render call.
+#pragma once
+
+#include "wf_types.cuh"
+
+namespace qz {
+
+__device__ __forceinline__ void store_state(const WfBuffers& b, uint32_t slot, const PathState& ps, uint32_t path_id) {
+    b.ray_o.set(slot, f4(ps.ray.o.x, ps.ray.o.y, ps.ray.o.z, ps.ior_scale));
+    b.ray_d.set(slot, f4(ps.ray.d.x, ps.ray.d.y, ps.ray.d.z, ps.p_b));
+    b.weight.set(slot, f4(ps.weight));
+    b.radiance.set(slot, f4(ps.L));
+    b.lpdf.set(slot, f4(ps.pdf));
+    b.misc.set(slot, pack_misc(path_id, ps));
+}
+
+// path id of the pass -> pixel and sample; initialises the slot (render.cpp:261-273)
+__device__ __forceinline__ void init_slot(const DScene& sc, const DCamera& cam, const WfBuffers& b, const PassParams& pp,
+                                          uint32_t slot, uint32_t path_id, float4& ray_o, float4& ray_d) {
+    const uint32_t pix = path_id % pp.n_pix;
+    const uint32_t s = pp.s_begin + path_id / pp.n_pix;
+    const uint32_t row = pp.owned_rows[pix / pp.width];
+    const uint32_t x = pix % pp.width;
+    const uint32_t y = pp.height - row - 1;
+    PathState ps;
+    PathAov aov;
+    start_path(sc, cam, pp.spar, x, y, s, ps, aov);
+    store_state(b, slot, ps, path_id);
+    b.lambda.set(slot, f4(ps.lambda));
+    b.aov_n.set(slot, f4(0.0f, 0.0f, 0.0f, 0.0f));
+    b.aov_a.set(slot, f4(0.0f, 0.0f, 0.0f, 0.0f));
+    ray_o = f4(ps.ray.o.x, ps.ray.o.y, ps.ray.o.z, ps.ior_scale);
+    ray_d = f4(ps.ray.d.x, ps.ray.d.y, ps.ray.d.z, ps.p_b);
+}
+
+// ------------------------------------------------------------------ kernels
+__global__ void __launch_bounds__(256) k_generate(DScene sc, DCamera cam, WfBuffers b, PassParams pp, uint32_t first_id, uint32_t n) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < b.pool; i += gridDim.x * blockDim.x) {
+        b.post[i] = 0;
+        if (i < n) {
+            float4 o, d;
+            init_slot(sc, cam, b, pp, i, first_id + i, o, d);
+            b.stage[i] = ST_TRACE_FIRST;
+        } else {
+            b.stage[i] = ST_EMPTY;
+        }
+    }
+}
+
+// Depth-0 albedo of conductors as its own stage.  The reference estimates the albedo AOV at the first
+// hit with 16 fixed BxDF samples (render.cpp:150-170, bxdf.hpp:46-56); for a rough conductor that is
+// 16 x (visible-normal sample, D, G, complex Fresnel at 4 wavelengths) -- about three times the rest
+// of the bounce, executed as one serial chain per thread inside a 128-register kernel.  Here SIXTEEN
+// LANES share a path, one sample each, in a lean kernel at high occupancy; the 16 terms are then
+// added in sample order by every lane of the group (shuffles), which is the reference's
+// summation order, so the value is unchanged bit for bit.
+__global__ void __launch_bounds__(256) k_albedo_conductor(DScene sc, WfBuffers b, uint32_t max_bounces) {
+    if (max_bounces == 0) return;  // the path loop breaks before the estimate (render.cpp:137): the AOV stays zero
+    const uint32_t count = b.counters[C_SHADE0 + SQ_FAMILIES + SQ_CONDUCTOR];
+    const uint32_t* queue = b.q_shade[SQ_FAMILIES + SQ_CONDUCTOR];
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int i = lane & 15;          // this lane's sample
+    const int gbase = lane & 16;      // first lane of the 16-lane group
+    const uint32_t n_groups = gridDim.x * blockDim.x / 16u;
+    const uint32_t rounds = (count + n_groups - 1u) / n_groups;
+    uint32_t e = (blockIdx.x * blockDim.x + threadIdx.x) / 16u;
+    for (uint32_t r = 0; r < rounds; r++, e += n_groups) {
+        const bool live = e < count;   // uniform within the group; the warp stays converged for the shuffles
+        Spec4 term = spec4(0.0f);
+        bool valid = false;
+        uint32_t slot = 0;
+        SurfacePoint sp;
+        qz_material mat;
+        float coeff = 0.0f;
+        if (live) {
+            slot = queue[e];
+            const float4 o = b.ray_o.get(slot), d = b.ray_d.get(slot), ha = b.hit_a.get(slot), hb = b.hit_b.get(slot);
+            Ray ray;
+            ray.o = v3(o.x, o.y, o.z); ray.d = v3(d.x, d.y, d.z);
+            Hit hit;
+            hit.t = ha.x; hit.u = ha.y; hit.v = ha.z; hit.prim_id = __float_as_uint(ha.w);
+            hit.ng = v3(hb.x, hb.y, hb.z); hit.geom_id = __float_as_uint(hb.w); hit.prim = hit.geom_id; hit.key = 0;
+            const Spec4 lambda = s4(b.lambda.get(slot));
+            sp = make_surface_point(sc, ray, hit);
+            // Material::bsdf for a conductor (material.cpp:16-20) is eight spectrum lookups (eta and k at four
+            // wavelengths): lane j of the group does lookup j, the group exchanges them below
+            mat = sc.materials[sp.material];
+            const int j = i & 7;
+            const float lam = j & 2 ? (j & 1 ? lambda.v[3] : lambda.v[2]) : (j & 1 ? lambda.v[1] : lambda.v[0]);
+            coeff = eval_spectrum_rec<true>(sc, load_spectrum(sc, j < 4 ? mat.a : mat.b), lam);
+        }
+        Bsdf f;
+        f.kind = BX_CONDUCTOR; f.ior = 1.0f;
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            f.a.v[c] = __shfl_sync(full, coeff, gbase + c);
+            f.b.v[c] = __shfl_sync(full, coeff, gbase + 4 + c);
+        }
+        if (live) {
+            f.rough.ax = mat.alpha_x; f.rough.ay = mat.alpha_y;
+            make_basis(sp.normal, f.u0, f.u1, f.u2);
+            const V3 wo = to_local(f, sp.wo);
+            const float* t = sc.rho_tab + i * 8;
+            const BsdfSample smp = bxdf_sample<KH_CONDUCTOR>(f, wo, t[0], v2(t[1], t[2]), true, v3(t[6], t[7], 0.0f));
+            valid = smp.valid;
+            if (valid) term = r_div(smp.spec * fabsf(smp.wi.z), smp.pdf);
+        }
+        Spec4 acc = spec4(0.0f);
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+            const bool ok = __shfl_sync(full, (int)valid, gbase + j) != 0;
+            Spec4 v;
+#pragma unroll
+            for (int c = 0; c < 4; c++) v.v[c] = __shfl_sync(full, term.v[c], gbase + j);
+            if (ok) acc = acc + v;
+        }
+        if (live && i == 0) b.aov_a.set(slot, f4(acc / 16.0f));
+    }
+}
+
+#ifndef QZ_SHADE_MIN_BLOCKS_LIGHT
+#define QZ_SHADE_MIN_BLOCKS_LIGHT 5   /* diffuse / dielectric shade kernels: 96 registers */
+#endif
+#ifndef QZ_SHADE_MIN_BLOCKS_HEAVY
+#define QZ_SHADE_MIN_BLOCKS_HEAVY 4   /* conductor / run-time-dispatch shade kernels */
+#endif
+
+// One bounce for every path of one material family: its first-hit queue, then its later-bounce queue, as one index
+// space (a warp straddles the boundary at most once per kernel, so `first` is warp-uniform in practice).  Only
+// what the family can change is loaded and stored: the radiance buffer is touched only when the hit itself adds
+// radiance (emitters and misses live in the run-time-dispatch queue), the AOVs only at first hits.
+template <int KH>
+__global__ void __launch_bounds__(128, (KH == KH_DIFFUSE || KH == KH_DIELECTRIC) ? QZ_SHADE_MIN_BLOCKS_LIGHT : QZ_SHADE_MIN_BLOCKS_HEAVY)
+k_shade(DScene sc, WfBuffers b, uint32_t max_bounces) {
+    constexpr int FAM = KH == KH_DIFFUSE ? SQ_DIFFUSE : (KH == KH_CONDUCTOR ? SQ_CONDUCTOR : (KH == KH_DIELECTRIC ? SQ_DIELECTRIC : SQ_MISC));
+    const uint32_t n_first = b.counters[C_SHADE0 + SQ_FAMILIES + FAM];
+    const uint32_t count = n_first + b.counters[C_SHADE0 + FAM];
+    const uint32_t* q_first = b.q_shade[SQ_FAMILIES + FAM];
+    const uint32_t* q_later = b.q_shade[FAM];
+    auto entry = [&](uint32_t i) -> uint32_t { return i < n_first ? q_first[i] : q_later[i - n_first]; };
+    // A bounce is: read one record, many dependent instructions, write it back -- nothing in it overlaps the
+    // read.  So the read of the thread's NEXT path is started a whole bounce early: its queue entry is loaded two
+    // trips ahead, its record lines prefetched one trip ahead.
+    const uint32_t stride = gridDim.x * blockDim.x;
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t slot_cur = i < count ? entry(i) : 0u;
+    uint32_t slot_next = i + stride < count ? entry(i + stride) : 0u;
+    for (; i < count; i += stride) {
+        const uint32_t slot = slot_cur;
+        const uint32_t slot_after = (i + 2u * stride < count && i + 2u * stride >= i) ? entry(i + 2u * stride) : 0u;
+        if (i + stride < count) {
+            prefetch_line(b.ray_o.at(slot_next));
+            if (KH != KH_ANY) prefetch_line(b.samples.at(slot_next));
+        }
+        slot_cur = slot_next;
+        slot_next = slot_after;
+        const bool first = i < n_first;
+        PathState ps;
+        const float4 o = b.ray_o.get(slot), d = b.ray_d.get(slot);
+        ps.ray.o = v3(o.x, o.y, o.z); ps.ior_scale = o.w;
+        ps.ray.d = v3(d.x, d.y, d.z); ps.p_b = d.w;
+        ps.weight = s4(b.weight.get(slot));
+        ps.lambda = s4(b.lambda.get(slot));
+        // only a dispersive dielectric changes the wavelength pdf (terminate_secondary): the other families neither load nor store it
+        constexpr bool TOUCHES_PDF = KH == KH_DIELECTRIC || KH == KH_ANY;
+        ps.pdf = TOUCHES_PDF ? s4(b.lpdf.get(slot)) : spec4(0.0f);
+        ps.L = spec4(0.0f);
+        const uint4 m = b.misc.get(slot);
+        unpack_misc(m, ps);
+        ps.n_rays += 1;  // + the closest-hit query that produced this hit
+        const float4 ha = b.hit_a.get(slot), hb = b.hit_b.get(slot);
+        Hit hit;
+        hit.t = ha.x; hit.u = ha.y; hit.v = ha.z; hit.prim_id = __float_as_uint(ha.w);
+        hit.ng = v3(hb.x, hb.y, hb.z);
+        hit.geom_id = __float_as_uint(hb.w);
+        hit.prim = hit.geom_id;  // only compared against QZ_NO_HIT from here on
+        hit.key = 0;
+        PathAov aov;
+        aov.normal = v3(0.0f, 0.0f, 0.0f);
+        aov.albedo = spec4(0.0f);
+        ShadowRequest sh;
+        Spec4 gain;
+        bool has_gain, alive;
+        if (KH == KH_ANY) {
+            SamplesOnTheFly src;
+            src.tab = sc.sampler_table; src.index = ps.smp.index;
+            alive = shade_bounce<KH, -1, true>(sc, ps, aov, hit, max_bounces, sh, src, gain, has_gain);
+        } else {
+            const float4* sv = b.samples.at(slot);
+            const float4 s0 = __ldcg(sv), s1 = __ldcg(sv + 1);
+            SamplesPrecomputed src;
+            src.v[0] = s0.x; src.v[1] = s0.y; src.v[2] = s0.z; src.v[3] = s0.w;
+            src.v[4] = s1.x; src.v[5] = s1.y; src.v[6] = s1.z; src.v[7] = s1.w;
+            alive = shade_bounce<KH, -1, true>(sc, ps, aov, hit, max_bounces, sh, src, gain, has_gain);
+        }
+        if (has_gain) b.radiance.set(slot, f4(s4(b.radiance.get(slot)) + gain));
+        if (first) {
+            // depth is still 0 after an emitter pass-through, so these may be written more than
+            // once per path; the last write (the first real surface) wins, as in the reference
+            if (hit.prim != QZ_NO_HIT) b.aov_n.set(slot, f4(aov.normal.x, aov.normal.y, aov.normal.z, 0.0f));
+            // (conductors: the albedo comes from k_albedo_conductor)
+            if (KH != KH_CONDUCTOR && (ps.depth != 0 || !alive)) b.aov_a.set(slot, f4(aov.albedo));
+        }
+        uint32_t post = alive ? 0u : QZ_POST_DONE;
+        if (ps.flags & QZ_FLAG_HAS_SHADOW) {
+            ps.n_rays++;
+            b.sh_o.set(slot, f4(sh.o.x, sh.o.y, sh.o.z, 0.0f));
+            b.sh_d.set(slot, f4(sh.d.x, sh.d.y, sh.d.z, 0.0f));
+            b.sh_c.set(slot, f4(sh.contrib));
+            post |= QZ_POST_SHADOW;
+        }
+        if (alive) {
+            b.ray_o.set(slot, f4(ps.ray.o.x, ps.ray.o.y, ps.ray.o.z, ps.ior_scale));
+            b.ray_d.set(slot, f4(ps.ray.d.x, ps.ray.d.y, ps.ray.d.z, ps.p_b));
+            // weight and lambda share a sector: writing both keeps it a full-sector store
+            b.weight.set(slot, f4(ps.weight));
+            b.lambda.set(slot, f4(ps.lambda));
+        }
+        if (TOUCHES_PDF) b.lpdf.set(slot, f4(ps.pdf));
+        b.misc.set(slot, pack_misc(m.x, ps));
+        b.post[slot] = (uint8_t)post;
+        b.stage[slot] = alive ? (ps.depth == 0 ? ST_TRACE_FIRST : ST_TRACE) : ST_EMPTY;
+    }
+}
+
+// A finished path: sensor conversion into its result cell (sensor.cpp:57-70), then the next pixel-sample of the
+// pass in the same slot.  Returns the slot's new stage tag; a regenerated path's ray comes back in (ray_o, ray_d).
+__device__ __forceinline__ uint8_t finish_and_regenerate(const DScene& sc, const DCamera& cam, const WfBuffers& b, const PassParams& pp,
+                                                         uint32_t slot, const Spec4& L, float4& ray_o, float4& ray_d) {
+    const uint32_t path_id = b.misc.get(slot).x;
+    const Spec4 lambda = s4(b.lambda.get(slot)), pdf = s4(b.lpdf.get(slot));
+    const float4 n = b.aov_n.get(slot);
+    const V3 rgb = to_sensor_rgb(cam, L, lambda, pdf);
+    const V3 argb = to_sensor_rgb(cam, s4(b.aov_a.get(slot)), lambda, pdf);
+    __stcs(b.res_a + path_id, f4(rgb.x, rgb.y, rgb.z, n.x));
+    __stcs(b.res_b + path_id, f4(argb.x, argb.y, argb.z, n.y));
+    __stcs(b.res_c + path_id, n.z);
+    // regenerate
+    const unsigned peers = __activemask();
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(peers) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(b.next_path, (uint32_t)__popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    const uint32_t next_id = base + __popc(peers & ((1u << lane) - 1u));
+    if (next_id >= pp.total) return ST_EMPTY;
+    init_slot(sc, cam, b, pp, slot, next_id, ray_o, ray_d);
+    return ST_TRACE_FIRST;
+}
+
+// BVH scenes: the finish stage between the two traversal kernels.  Walks the slots densely, consumes the post tags.
+__global__ void __launch_bounds__(256) k_finish(DScene sc, DCamera cam, WfBuffers b, PassParams pp) {
+    if (blockIdx.x == 0 && threadIdx.x < SQ_COUNT) b.counters[C_SHADE0 + threadIdx.x] = 0;   // consumed by the shading stage; k_bin refills them
+    uint32_t n_done = 0;
+    for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < b.pool; slot += gridDim.x * blockDim.x) {
+        const uint8_t po = b.post[slot];
+        if (!po) continue;
+        if (po & QZ_POST_DONE) {
+            float4 o, d;
+            const uint8_t st = finish_and_regenerate(sc, cam, b, pp, slot, s4(b.radiance.get(slot)), o, d);
+            if (st != ST_EMPTY) b.stage[slot] = st;
+            n_done++;
+        }
+        b.post[slot] = 0;
+    }
+    stat_add(&b.stats[S_PATHS_DONE], n_done);
+}
+
+// Flat scenes (<= QZ_FLAT_MAX_PRIMS primitives: every shipped analytic scene): no BVH and no separate shadow /
+// finish / closest-hit kernels.  ONE pass over the slots does, per slot, what its tags ask for:
+//   post & SHADOW : the next-event shadow test of the last bounce (scene.cpp:136-143), radiance += contribution;
+//   post & DONE   : finish the path and start the next pixel-sample of the pass in the slot;
+//   stage != EMPTY: closest hit of the slot's ray (scene.cpp:61-117) and the family tag for k_bin.
+// The primitive records are staged once per CTA in shared memory together with each triangle's edges and normal
+// (make_flat_prim: the expressions tri_test uses), and every lane walks the same list in lockstep -- no stack, no
+// divergence inside a test, broadcast shared-memory reads.  The answer is the brute-force minimum under the (t, key)
+// order, i.e. exactly what the BVH traversal is defined to return.  Against the three kernels it replaces, a
+// slot's record is visited once instead of up to three times and a finished path's radiance never leaves the
+// registers between the shadow test and the sensor.
+__global__ void __launch_bounds__(128, 4) k_step_flat(DScene sc, DCamera cam, WfBuffers b, PassParams pp, uint32_t flags) {
+    __shared__ FlatPrim s_prims[QZ_FLAT_MAX_PRIMS];
+    const uint32_t n_prims = sc.n_prims;
+    for (uint32_t i = threadIdx.x; i < n_prims; i += blockDim.x)
+        s_prims[i] = make_flat_prim(sc.prims[4 * i], sc.prims[4 * i + 1], sc.prims[4 * i + 2], sc.prims[4 * i + 3]);
+    if (blockIdx.x == 0 && threadIdx.x < SQ_COUNT) b.counters[C_SHADE0 + threadIdx.x] = 0;   // consumed by the shading stage; k_bin refills them
+    __syncthreads();
+    uint32_t n_closest = 0, n_shadow = 0, n_done = 0;
+    for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < b.pool; slot += gridDim.x * blockDim.x) {
+        uint8_t st = b.stage[slot];
+        const uint8_t po = b.post[slot];
+        float4 ro, rd;
+        bool have_ray = false;
+        if (po) {
+            Spec4 L;
+            bool have_L = false;
+            if (po & QZ_POST_SHADOW) {
+                n_shadow++;
+                const float4 o = b.sh_o.get(slot), d = b.sh_d.get(slot);
+                const V3 O = v3(o.x, o.y, o.z), D = v3(d.x, d.y, d.z);
+                const float rd2 = 1.0f / dot(D, D);   // the ray's share of every sphere test
+                Hit best;
+                best.t = INFINITY; best.u = 0.0f; best.v = 0.0f; best.prim = QZ_NO_HIT; best.key = 0xffffffffu;
+                best.ng = v3(0.0f, 0.0f, 0.0f); best.geom_id = QZ_NO_HIT; best.prim_id = 0;
+                // occluded iff the closest hit has t <= 1 (scene.cpp:136-143)
+#pragma unroll 1
+                for (uint32_t p = 0; p < n_prims; p++)
+                    flat_prim_test(sc, s_prims[p], p, O, D, rd2, QZ_TNEAR, INFINITY, best);
+                if (!(best.prim != QZ_NO_HIT && best.t <= 1.0f)) {
+                    L = s4(b.radiance.get(slot)) + s4(b.sh_c.get(slot));
+                    have_L = true;
+                    if (!(po & QZ_POST_DONE)) b.radiance.set(slot, f4(L));
+                }
+            }
+            if (po & QZ_POST_DONE) {
+                if (!have_L) L = s4(b.radiance.get(slot));
+                st = finish_and_regenerate(sc, cam, b, pp, slot, L, ro, rd);
+                if (st != ST_EMPTY) { b.stage[slot] = st; have_ray = true; }
+                n_done++;
+            }
+            b.post[slot] = 0;
+        }
+        if (st == ST_EMPTY) { b.fam[slot] = QZ_FAM_NONE; continue; }
+        if (!have_ray) { ro = b.ray_o.get(slot); rd = b.ray_d.get(slot); }
+        n_closest++;
+        const V3 O = v3(ro.x, ro.y, ro.z), D = v3(rd.x, rd.y, rd.z);
+        const float rd2 = 1.0f / dot(D, D);
+        Hit best;
+        best.t = INFINITY; best.u = 0.0f; best.v = 0.0f; best.prim = QZ_NO_HIT; best.key = 0xffffffffu;
+        best.ng = v3(0.0f, 0.0f, 0.0f); best.geom_id = QZ_NO_HIT; best.prim_id = 0;
+#pragma unroll 1
+        for (uint32_t p = 0; p < n_prims; p++)
+            flat_prim_test(sc, s_prims[p], p, O, D, rd2, QZ_TNEAR, INFINITY, best);
+        b.hit_a.set(slot, f4(best.t, best.u, best.v, __uint_as_float(best.prim_id)));
+        b.hit_b.set(slot, f4(best.ng.x, best.ng.y, best.ng.z, __uint_as_float(best.geom_id)));
+        const bool unsorted = (flags & QZ_FLAG_UNSORTED_SHADING) != 0;
+        int fam = SQ_MISC;
+        if (!unsorted && best.geom_id != QZ_NO_HIT) {
+            const int32_t mat = sc.geoms[best.geom_id].material;
+            if (mat >= 0) {
+                const uint32_t kind = sc.materials[mat].kind;
+                fam = kind == QZ_MAT_DIFFUSE ? SQ_DIFFUSE : (kind == QZ_MAT_CONDUCTOR ? SQ_CONDUCTOR
+                      : ((kind == QZ_MAT_DIELECTRIC || kind == QZ_MAT_THIN_DIELECTRIC) ? SQ_DIELECTRIC : SQ_MISC));
+            }
+        }
+        b.fam[slot] = (uint8_t)(fam + (st == ST_TRACE_FIRST && !unsorted ? SQ_FAMILIES : 0));
+    }
+    stat_add(&b.stats[S_RAYS_CLOSEST], n_closest);
+    stat_add(&b.stats[S_RAYS_SHADOW], n_shadow);
+    stat_add(&b.stats[S_PATHS_DONE], n_done);
+}
+
+// per-path replay (qz_trace_paths): a whole path in one thread, no wavefront
+__global__ void k_trace_paths(DScene sc, DCamera cam, SamplerParams spar, uint32_t max_bounces, uint32_t n,
+                              const int32_t* xys, float* records) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    PathState ps;
+    PathAov aov;
+    Spec4 lambda0;
+    run_path<false>(sc, cam, spar, (uint32_t)xys[3 * i], (uint32_t)xys[3 * i + 1], (uint32_t)xys[3 * i + 2], max_bounces, ps,
+                    aov, lambda0, nullptr);
+    V3 rgb = to_sensor_rgb(cam, ps.L, ps.lambda, ps.pdf);
+    V3 argb = to_sensor_rgb(cam, aov.albedo, ps.lambda, ps.pdf);
+    write_trace_record(records + (size_t)i * 32, ps, aov, lambda0, rgb, argb);
+}
+
+}  // namespace qz

@@ -85,8 +85,9 @@ QZ_FLAG_UNSORTED_SHADING = 1
 QZ_FLAG_COUNT_TRAVERSAL = 2
 QZ_FLAG_STAGE_TIMING = 4
 QZ_FLAG_FORCE_BVH = 8
-QZ_FLAG_LANE_TRAVERSAL = 16
+QZ_FLAG_LANE_TRAVERSAL = 16   # round-1 evidence arms: rejected with QZ_ERR_INVALID
 QZ_FLAG_OCTET_TRAVERSAL = 32
+QZ_FLAG_EXACT_ARITHMETIC = 64
 
 
 @dataclass
@@ -224,6 +225,39 @@ class Harness:
 
     def _fn(self, name: str):
         return getattr(self.lib, self.prefix + name)
+
+    def math_probe(self, op: int, x) -> np.ndarray:
+        """qz_math_probe of the C ABI: op 0 -> (sinf, cosf) per argument."""
+        a = _f32(x).ravel()
+        out = np.zeros((len(a), 2), np.float32)
+        rc = self.lib.qz_math_probe(op, len(a), a.ctypes.data_as(_c_float_p), out.ctypes.data_as(_c_float_p))
+        if rc != 0:
+            raise RuntimeError(f"qz_math_probe failed with code {rc}")
+        return out
+
+    def set_default_flags(self, flags: int) -> int:
+        """QZ_FLAG_* bits OR-ed into every later render / trace_paths call of this thread (product library only;
+        the oracle and the host emulation have one arithmetic).  Returns the previous value."""
+        fn = getattr(self.lib, "qz_set_default_flags", None)
+        if fn is None:
+            return 0
+        fn.restype = ctypes.c_uint32
+        return int(fn(ctypes.c_uint32(flags)))
+
+    def arithmetic(self, exact: bool):
+        """Context manager: run the enclosed calls in the reference's arithmetic (exact=True) or in the default
+        radiometric mode (include/qz_b200.h: QZ_FLAG_EXACT_ARITHMETIC)."""
+        import contextlib
+
+        @contextlib.contextmanager
+        def scope():
+            old = self.set_default_flags(QZ_FLAG_EXACT_ARITHMETIC if exact else 0)
+            try:
+                yield self
+            finally:
+                self.set_default_flags(old)
+
+        return scope()
 
     def impl(self) -> str:
         return self._fn("impl")().decode()

@@ -55,11 +55,12 @@ def qz() -> Harness:
 
 @pytest.fixture(scope="session")
 def small_mesh(tmp_path_factory) -> str:
-    """A ~20k-triangle instance of the synthetic obj_viewer mesh (tools/gen_mesh.py)."""
+    """A 4000-triangle instance of the synthetic obj_viewer mesh (tools/gen_mesh.py: the bulky "dragon" body that fills
+    a third of the obj_viewer frame; the full 1M-triangle instance is pinned by tests/golden/paths_obj_viewer_1m.npz)."""
     sys.path.insert(0, str(ROOT / "tools"))
     import gen_mesh
 
-    path = tmp_path_factory.mktemp("mesh") / "knot_small.obj"
-    pos, nrm, tris = gen_mesh.knot_mesh(4000)
+    path = tmp_path_factory.mktemp("mesh") / "dragon_small.obj"
+    pos, nrm, tris = gen_mesh.dragon_mesh(4000)
     gen_mesh.write_obj(str(path), pos, nrm, tris)
     return str(path)

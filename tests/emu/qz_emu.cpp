@@ -39,7 +39,7 @@ SeqExec g_exec;
 // with a small cap -- enough to run the prefixed evaluation path through every CPU parity test
 std::vector<SamplerDim> g_sampler_storage;
 SamplerDim* g_sampler_table = nullptr;
-float g_rho_tab[16 * 8];
+float g_rho_tab[QZ_RHO_TAB_FLOATS];
 bool g_tables_ready = false;
 
 void ensure_tables() {
@@ -78,6 +78,7 @@ struct qz_scene_t {
 extern "C" {
 
 const char* qz_last_error(void) { return g_error.c_str(); }
+uint32_t qz_set_default_flags(uint32_t) { return 0; }
 int qz_abi_version(void) { return QZ_ABI_VERSION; }
 int qz_init(int) { ensure_tables(); return QZ_OK; }
 int qz_device_name(char* buf, size_t n) { std::snprintf(buf, n, "host emulation (tests only)"); return QZ_OK; }
@@ -191,6 +192,12 @@ int qz_eval_spectrum(qz_scene s, int32_t id, uint32_t n, const float* lambdas, f
     if (id < 0) id = sc.bg_spectrum;
     if (id < 0) { g_error = "no such spectrum"; return QZ_ERR_INVALID; }
     for (uint32_t i = 0; i < n; i++) out[i] = eval_spectrum(sc, id, lambdas[i]);
+    return QZ_OK;
+}
+
+int qz_math_probe(int op, uint32_t n, const float* in, float* out) {
+    if (op != 0) return QZ_ERR_INVALID;
+    for (uint32_t i = 0; i < n; i++) qz_sincosf(in[i], out[2 * i], out[2 * i + 1]);
     return QZ_OK;
 }
 

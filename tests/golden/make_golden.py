@@ -23,7 +23,29 @@ from quetzalcoatlus_b200.harness import Harness  # noqa: E402
 OUT = Path(__file__).resolve().parent
 
 
+def obj_viewer_1m(orc) -> None:
+    """One-off (the reference's regex OBJ loader needs ~25 minutes for the 1M-triangle text): replayed paths of the
+    obj_viewer configuration on the FULL synthetic mesh, plus the checksum of the OBJ text they belong to."""
+    import hashlib
+
+    sys.path.insert(0, str(ROOT / "tools"))
+    import gen_mesh
+
+    path = gen_mesh.ensure_obj("/tmp", 1_000_000)
+    digest = hashlib.sha256(open(path, "rb").read()).hexdigest()
+    with orc.build_scene("obj_viewer", obj_path=path, obj_material="alluminum", obj_light="point") as sc:
+        xys = pixel_samples(sc, 4096, seed=1_000_003)
+        rec = sc.trace_paths(xys)
+        r = sc.render(1)
+    np.savez_compressed(OUT / "paths_obj_viewer_1m.npz", xys=xys, records=rec, obj_sha256=np.array(digest),
+                        cpu_seconds_1spp=np.array(r.seconds), cpu_threads=np.array(r.n_threads), cpu_rays_1spp=np.array(r.rays))
+    print("paths obj_viewer_1m", digest, r.seconds)
+
+
 def main() -> None:
+    if "--obj1m" in sys.argv:
+        obj_viewer_1m(Harness(ROOT / "oracle" / "_ref" / "liboracle_ref.so", "orc_"))
+        return
     orc = Harness(ROOT / "oracle" / "_ref" / "liboracle_ref.so", "orc_")
     rng = np.random.default_rng(2026)
     q = np.stack([rng.integers(0, 1920, 4096), rng.integers(0, 1080, 4096), rng.integers(0, 256, 4096), rng.integers(0, 1000, 4096)], 1)

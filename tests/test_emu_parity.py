@@ -108,3 +108,24 @@ def test_bounce_limits_bit_exact(emu, oracle, max_bounces):
         with emu.build_scene(name) as se, oracle.build_scene(name) as so:
             xys = pixel_samples(so, 800, seed=8)
             assert bits_equal(se.trace_paths(xys, max_bounces=max_bounces), so.trace_paths(xys, max_bounces=max_bounces)).all(), name
+
+
+FAST_EMU_LIB = Path(__file__).resolve().parent / "emu" / "_build" / "libqz_emu_fast_harness.so"
+
+
+@pytest.mark.parametrize("name", ANALYTIC_SCENES)
+def test_fast_arithmetic_build_stays_within_tolerance(emu, oracle, name):
+    """The radiometric ("fast") build of the device headers (csrc/common.cuh, ARITHMETIC MODES), compiled for the host:
+    geometry and discrete decisions identical to the oracle's (ray counts, wavelengths, first-hit normals bit for
+    bit), radiance within 1e-5 relative -- ten times tighter than the north-star tolerance.  (The host stands in for
+    the MUFU approximations with exact operations; the GPU tests measure those.)"""
+    from common import NORMAL, RAYS, path_agreement
+    from quetzalcoatlus_b200.harness import Harness
+
+    fast = Harness(FAST_EMU_LIB, "qzh_")
+    with fast.build_scene(name) as sf, oracle.build_scene(name) as so:
+        xys = pixel_samples(so, 3000, seed=33)
+        got, want = sf.trace_paths(xys), so.trace_paths(xys)
+    assert (got[:, RAYS] == want[:, RAYS]).all()
+    assert bits_equal(got[:, :4], want[:, :4]).all() and bits_equal(got[:, NORMAL], want[:, NORMAL]).all()
+    assert path_agreement(want, got, 1e-5).all()

@@ -46,6 +46,45 @@ def knot_mesh(n_tri: int):
     return pos.reshape(-1, 3), nrm.reshape(-1, 3), tris
 
 
+def dragon_mesh(n_tri: int):
+    """The obj_viewer stand-in: a bulky closed body that fills the obj_viewer frame the way the reference's dragon
+    render does (examples/xyz_dragon_obj.png: a quarter to a third of the pixels).  A latitude-longitude grid over a
+    displaced ellipsoid -- overlapping scale rows, a dorsal ridge of spikes, fine noise -- closed by two pole fans:
+    nu rings x nv segments -> nu*nv + 2 vertices, 2*nv*(nu - 1) + 2*nv triangles."""
+    nv = max(8, int(round(np.sqrt(n_tri / 2.0))))
+    nu = max(4, n_tri // (2 * nv))
+    eps = np.pi / (2.0 * nu)
+    th = np.linspace(eps, np.pi - eps, nu)            # polar angle from +x (the body's long axis)
+    ph = np.linspace(0.0, 2.0 * np.pi, nv, endpoint=False)
+    tt, pp = np.meshgrid(th, ph, indexing="ij")
+
+    def surface(t, p):
+        scales = 0.045 * np.abs(np.sin(19.0 * t + 0.5 * np.sin(14.0 * p))) * np.abs(np.sin(14.0 * p))
+        ridge = 0.32 * np.exp(-((p - 0.5 * np.pi) / 0.22) ** 2) * (0.55 + 0.45 * np.sin(23.0 * t)) * np.sin(t) ** 2
+        bulge = 0.10 * np.sin(3.0 * t) * np.cos(2.0 * p) + 0.06 * np.sin(5.0 * t + 1.3) * np.sin(3.0 * p + 0.4)
+        fine = 0.012 * np.sin(61.0 * t + 11.0 * p) + 0.008 * np.sin(97.0 * p - 29.0 * t)
+        r = 1.0 + scales + ridge + bulge + fine
+        d = np.stack([np.cos(t), np.sin(t) * np.sin(p), np.sin(t) * np.cos(p)], -1)
+        return d * r[..., None] * np.array([2.85, 1.9, 1.95]) + np.array([0.0, 2.2, 0.0])
+
+    pos = surface(tt, pp)
+    h = 1e-4
+    dt = surface(tt + h, pp) - surface(tt - h, pp)
+    dp = surface(tt, pp + h) - surface(tt, pp - h)
+    nrm = np.cross(dp, dt)
+    nrm /= np.maximum(np.linalg.norm(nrm, axis=2, keepdims=True), 1e-12)
+    poles = np.stack([surface(np.array(0.0), np.array(0.0)), surface(np.array(np.pi), np.array(0.0))])
+    pole_n = np.array([[1.0, 0.0, 0.0], [-1.0, 0.0, 0.0]])
+    idx = np.arange(nu)[:, None] * nv + np.arange(nv)[None, :]
+    a, b = idx[:-1], idx[1:]
+    c, d = np.roll(b, -1, 1), np.roll(a, -1, 1)
+    tris = [np.stack([a, b, c], -1).reshape(-1, 3), np.stack([a, c, d], -1).reshape(-1, 3)]
+    p0, p1 = nu * nv, nu * nv + 1
+    tris.append(np.stack([np.full(nv, p0), idx[0], np.roll(idx[0], -1)], -1))
+    tris.append(np.stack([np.full(nv, p1), np.roll(idx[-1], -1), idx[-1]], -1))
+    return np.concatenate([pos.reshape(-1, 3), poles]), np.concatenate([nrm.reshape(-1, 3), pole_n]), np.concatenate(tris, 0)
+
+
 def write_obj(path: str, pos, nrm, tris) -> None:
     with open(path, "w") as f:
         f.write("# synthetic torus-knot mesh (tools/gen_mesh.py)\n")
@@ -55,12 +94,25 @@ def write_obj(path: str, pos, nrm, tris) -> None:
         f.write("".join("f %d//%d %d//%d %d//%d\n" % (a, a, b, b, c, c) for a, b, c in t1))
 
 
+def ensure_obj(directory: str, n_tri: int = 1_000_000, shape: str = "dragon") -> str:
+    """Path of the cached OBJ text of `shape` with ~n_tri triangles (written on first use)."""
+    import os
+
+    path = os.path.join(directory, f"qz_{shape}_{n_tri}.obj")
+    if not os.path.exists(path):
+        pos, nrm, tris = (knot_mesh if shape == "knot" else dragon_mesh)(n_tri)
+        write_obj(path + ".tmp", pos, nrm, tris)
+        os.replace(path + ".tmp", path)
+    return path
+
+
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("out")
     ap.add_argument("--triangles", type=int, default=1_000_000)
+    ap.add_argument("--shape", choices=["dragon", "knot"], default="dragon")
     args = ap.parse_args()
-    pos, nrm, tris = knot_mesh(args.triangles)
+    pos, nrm, tris = (knot_mesh if args.shape == "knot" else dragon_mesh)(args.triangles)
     write_obj(args.out, pos, nrm, tris)
     print(f"{args.out}: {len(pos)} vertices, {len(tris)} triangles")
 
