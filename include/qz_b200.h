@@ -244,6 +244,18 @@ int qz_render_device(qz_scene scene, const qz_camera* camera, uint32_t n_samples
                      const qz_region* region, const qz_render_options* options,
                      float* d_color, float* d_normal, float* d_albedo, void* cuda_stream, qz_stats* stats);
 
+/* AOV hand-off to a GPU denoiser (RenderResult::denoise, image.cpp:47-95, copies the three planes into OIDN buffers):
+ * DEVICE pointers of the colour / normal / albedo planes of the last qz_render() on this handle (H*W*3 floats each;
+ * a plane that was not requested is NULL), valid until the next render or qz_scene_destroy().                    */
+int qz_film_device(qz_scene scene, float** d_color, float** d_normal, float** d_albedo, uint32_t* width, uint32_t* height);
+
+/* Image::save's tone path (image.cpp:7-19) as a kernel over a film plane: bgr255[3i + k] = 255 * powf(rgb[3i + 2 - k],
+ * gamma) -- the BGR float image the reference hands to cv::imwrite -- and/or bgr8 = that value saturated to 8 bits
+ * (round to nearest even, clamp to 0..255: OpenCV's conversion of a CV_32F matrix for an 8-bit file).  Either output
+ * may be NULL.  qz_tone_device takes DEVICE pointers and enqueues on `cuda_stream`; qz_tone takes host buffers.      */
+int qz_tone_device(const float* d_rgb, uint32_t n_pixels, float gamma, float* d_bgr255, uint8_t* d_bgr8, void* cuda_stream);
+int qz_tone(const float* rgb, uint32_t n_pixels, float gamma, float* bgr255, uint8_t* bgr8);
+
 /* Per-path replay (the parity harness; the reference equivalent is the loop body
  * render.cpp:268-277 around sample_pixel(), render.cpp:91): n x (x, y, s) with y the
  * sampler/camera y (= H-1-row); 32 floats per path:

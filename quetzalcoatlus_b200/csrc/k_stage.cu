@@ -16,4 +16,7 @@ void film(const Stage& s, float* acc, bool first_pass, bool last_pass, uint32_t 
     k_film<<<blocks, 256, 0, s.stream>>>(*static_cast<const WfBuffers*>(s.bufs), *static_cast<const PassParams*>(s.pass), acc, first_pass,
                                          last_pass, n_samples_total, color, normal, albedo);
 }
+void tone(const float* rgb, uint32_t n_pixels, float gamma, float* bgr255, uint8_t* bgr8, int blocks, cudaStream_t stream) {
+    k_tone<<<blocks, 256, 0, stream>>>(rgb, n_pixels, gamma, bgr255, bgr8);
+}
 }  // namespace qzl

@@ -28,6 +28,8 @@ void bin(const Stage& s);
 void sample(const Stage& s);
 void film(const Stage& s, float* acc, bool first_pass, bool last_pass, uint32_t n_samples_total, float* color, float* normal, float* albedo, int blocks);
 
+void tone(const float* rgb, uint32_t n_pixels, float gamma, float* bgr255, uint8_t* bgr8, int blocks, cudaStream_t stream);
+
 // one set per arithmetic mode
 #define QZL_MODE_API                                                                                          \
     void generate(const Stage& s, uint32_t first_id, uint32_t n);                                           \

@@ -108,4 +108,17 @@ QZ_HD_CALL float qz_acosf(float x) {
 QZ_HD float lerpf(float a, float b, float t) { return a + t * (b - a); }
 QZ_HD float r_lerp(float a, float b, float t) { return r_fma(t, b - a, a); }
 
+// Image::save's tone path, one channel (image.cpp:10-15): 255 * powf(c, gamma).  powf is evaluated in double and rounded
+// once (glibc's powf does the same internally); gamma == 1 returns c itself, as powf(c, 1) does.
+QZ_HD float tone_value(float c, float gamma) {
+    const float p = gamma == 1.0f ? c : (float)pow((double)c, (double)gamma);
+    return 255.0f * p;
+}
+// OpenCV's saturate_cast<uchar>(float) (what cv::imwrite applies to a CV_32F matrix for an 8-bit file): round to
+// nearest even, clamp to 0..255; NaN gives 0
+QZ_HD uint8_t tone_u8(float v) {
+    const float r = rintf(v);
+    return (uint8_t)(r >= 255.0f ? 255.0f : (r > 0.0f ? r : 0.0f));
+}
+
 }  // namespace qz

@@ -262,6 +262,8 @@ struct WorkMem {
     uint64_t cells = 0, acc_pix = 0, rows = 0;
     uint32_t* h_counters = nullptr;  // pinned
     DevBuf film[3];                  // device film planes of the host-buffer entry (qz_render)
+    bool film_valid[3] = {false, false, false};
+    uint32_t film_w = 0, film_h = 0;
     float* h_film = nullptr;         // pinned staging for pageable caller buffers
     size_t h_film_bytes = 0;
     std::vector<cudaEvent_t> stage_events;
@@ -488,9 +490,10 @@ static int render_impl(qz_scene s, const qz_camera* camera, uint32_t n_samples, 
     }
     cudaEvent_t ev_begin = wm.ev_begin, ev_end = wm.ev_end;
     QZ_CUDA(cudaEventRecord(ev_begin, stream));
-    // with one pipeline everything runs on the caller's stream; otherwise the pipelines fork from it and join back
+    // the pipelines run on the handle's own streams, forked from the caller's stream and joined back into it (also a
+    // single pipeline: the iteration is captured into a CUDA graph, which the legacy default stream does not allow)
     cudaStream_t ps[QZ_MAX_PIPELINES];
-    for (int p = 0; p < P; p++) ps[p] = P == 1 ? stream : wm.pipe_stream[p];
+    for (int p = 0; p < P; p++) ps[p] = wm.pipe_stream[p];
 
     qzl::Stage stg[QZ_MAX_PIPELINES];
     for (int p = 0; p < P; p++) {
@@ -519,6 +522,7 @@ static int render_impl(qz_scene s, const qz_camera* camera, uint32_t n_samples, 
         return evpool[ev_used++];
     };
     auto flush_events = [&]() {
+        for (int p = 0; p < P; p++) cudaStreamSynchronize(ps[p]);
         cudaStreamSynchronize(stream);
         for (size_t i = 0; i + 1 < ev_used; i += 2) {
             float ms = 0.0f;
@@ -601,11 +605,10 @@ static int render_impl(qz_scene s, const qz_camera* camera, uint32_t n_samples, 
         uint32_t first[QZ_MAX_PIPELINES], handed = 0;
         for (int p = 0; p < P; p++) { first[p] = std::min<uint32_t>(sub_pool, pp.total - handed); handed += first[p]; }
         init[C_NEXT_PATH] = handed;
+        for (int p = 0; p < P; p++) init[(size_t)p * C_WORDS + C_WORK0] = first[p];   // k_generate seeds queue 0 with the slots it fills
         QZ_RENDER_CUDA(cudaMemcpyAsync(counters.p, init, sizeof(uint32_t) * C_WORDS * P, cudaMemcpyHostToDevice, stream));
-        if (P > 1) {
-            QZ_RENDER_CUDA(cudaEventRecord(wm.fork, stream));
-            for (int p = 0; p < P; p++) QZ_RENDER_CUDA(cudaStreamWaitEvent(ps[p], wm.fork, 0));
-        }
+        QZ_RENDER_CUDA(cudaEventRecord(wm.fork, stream));
+        for (int p = 0; p < P; p++) QZ_RENDER_CUDA(cudaStreamWaitEvent(ps[p], wm.fork, 0));
         uint32_t id0 = 0;
         for (int p = 0; p < P; p++) {
             exact ? qzl::exact::generate(stg[p], id0, first[p]) : qzl::fast::generate(stg[p], id0, first[p]);
@@ -660,11 +663,9 @@ static int render_impl(qz_scene s, const qz_camera* camera, uint32_t n_samples, 
         if (rc != QZ_OK) break;
         // (an iteration whose trace stage found no live slot has finished every path: the finish stage runs FIRST in an
         // iteration, on the post tags the previous shading stage left)
-        if (P > 1) {
-            for (int p = 0; p < P; p++) {
-                QZ_RENDER_CUDA(cudaEventRecord(wm.pipe_done[p], ps[p]));
-                QZ_RENDER_CUDA(cudaStreamWaitEvent(stream, wm.pipe_done[p], 0));
-            }
+        for (int p = 0; p < P; p++) {
+            QZ_RENDER_CUDA(cudaEventRecord(wm.pipe_done[p], ps[p]));
+            QZ_RENDER_CUDA(cudaStreamWaitEvent(stream, wm.pipe_done[p], 0));
         }
         const bool first_pass = s_begin == 0, last_pass = s_begin + pp.s_count >= n_samples;
         qzl::Stage fs = stg[0];
@@ -743,9 +744,12 @@ int qz_render(qz_scene s, const qz_camera* camera, uint32_t n_samples, uint32_t 
         for (int k = 0; k < 3; k++)
             if (host[k]) QZ_CUDA(cudaMemcpy(dev[k]->p, host[k], n * 4, cudaMemcpyHostToDevice));
     }
+    wm.film_valid[0] = wm.film_valid[1] = wm.film_valid[2] = false;
     int rc = render_impl(s, camera, n_samples, max_bounces, region, options, dc.as<float>(), normal ? dn.as<float>() : nullptr,
                          albedo ? da.as<float>() : nullptr, nullptr, stats);
     if (rc != QZ_OK) return rc;
+    wm.film_valid[0] = true; wm.film_valid[1] = normal != nullptr; wm.film_valid[2] = albedo != nullptr;
+    wm.film_w = camera->image_width; wm.film_h = camera->image_height;
     for (int k = 0; k < 3; k++) {
         if (!host[k]) continue;
         if (pinned[k]) {
@@ -757,6 +761,51 @@ int qz_render(qz_scene s, const qz_camera* camera, uint32_t n_samples, uint32_t 
         }
     }
     QZ_CUDA(cudaStreamSynchronize(nullptr));
+    return QZ_OK;
+}
+
+// ------------------------------------------------------------------ output step (image.cpp)
+int qz_film_device(qz_scene s, float** d_color, float** d_normal, float** d_albedo, uint32_t* width, uint32_t* height) {
+    if (!s) return fail(QZ_ERR_INVALID, "null argument");
+    WorkMem& wm = s->work;
+    if (!wm.film_valid[0]) return fail(QZ_ERR_INVALID, "no film on the device: qz_render() has not completed on this handle");
+    if (d_color) *d_color = wm.film[0].as<float>();
+    if (d_normal) *d_normal = wm.film_valid[1] ? wm.film[1].as<float>() : nullptr;
+    if (d_albedo) *d_albedo = wm.film_valid[2] ? wm.film[2].as<float>() : nullptr;
+    if (width) *width = wm.film_w;
+    if (height) *height = wm.film_h;
+    return QZ_OK;
+}
+
+int qz_tone_device(const float* d_rgb, uint32_t n_pixels, float gamma, float* d_bgr255, uint8_t* d_bgr8, void* cuda_stream) {
+    if ((!d_rgb && n_pixels) || (!d_bgr255 && !d_bgr8)) return fail(QZ_ERR_INVALID, "null argument");
+    if (n_pixels > 0xffffffffu / 3u) return fail(QZ_ERR_INVALID, "image too large");
+    int rc = ensure_device();
+    if (rc) return rc;
+    if (!n_pixels) return QZ_OK;
+    int n_sm = 148;
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, g_device);
+    const int blocks = (int)std::min<uint64_t>(((uint64_t)n_pixels * 3 + 255) / 256, (uint64_t)n_sm * 8);
+    qzl::tone(d_rgb, n_pixels, gamma, d_bgr255, d_bgr8, blocks, static_cast<cudaStream_t>(cuda_stream));
+    QZ_CUDA(cudaGetLastError());
+    return QZ_OK;
+}
+
+int qz_tone(const float* rgb, uint32_t n_pixels, float gamma, float* bgr255, uint8_t* bgr8) {
+    if ((!rgb && n_pixels) || (!bgr255 && !bgr8)) return fail(QZ_ERR_INVALID, "null argument");
+    int rc = ensure_device();
+    if (rc) return rc;
+    if (!n_pixels) return QZ_OK;
+    const size_t n = (size_t)n_pixels * 3;
+    DevBuf din, dout, d8;
+    QZ_CUDA(din.alloc(n * 4));
+    if (bgr255) QZ_CUDA(dout.alloc(n * 4));
+    if (bgr8) QZ_CUDA(d8.alloc(n));
+    QZ_CUDA(cudaMemcpy(din.p, rgb, n * 4, cudaMemcpyHostToDevice));
+    rc = qz_tone_device(din.as<float>(), n_pixels, gamma, bgr255 ? dout.as<float>() : nullptr, bgr8 ? d8.as<uint8_t>() : nullptr, nullptr);
+    if (rc) return rc;
+    if (bgr255) QZ_CUDA(cudaMemcpy(bgr255, dout.p, n * 4, cudaMemcpyDeviceToHost));
+    if (bgr8) QZ_CUDA(cudaMemcpy(bgr8, d8.p, n, cudaMemcpyDeviceToHost));
     return QZ_OK;
 }
 

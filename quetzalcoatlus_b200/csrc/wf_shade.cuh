@@ -36,12 +36,15 @@ __device__ __forceinline__ void init_slot(const DScene& sc, const DCamera& cam, 
 
 // ------------------------------------------------------------------ kernels
 __global__ void __launch_bounds__(256) k_generate(DScene sc, DCamera cam, WfBuffers b, PassParams pp, uint32_t first_id, uint32_t n) {
+    // (the work list of the first iteration -- slots 0 .. n-1 in queue 0 -- gets its length from the host's counter block)
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < b.pool; i += gridDim.x * blockDim.x) {
         b.post[i] = 0;
+        b.fam[i] = QZ_FAM_NONE;
         if (i < n) {
             float4 o, d;
             init_slot(sc, cam, b, pp, i, first_id + i, o, d);
             b.stage[i] = ST_TRACE_FIRST;
+            b.q_shade[0][i] = i;
         } else {
             b.stage[i] = ST_EMPTY;
         }
@@ -250,11 +253,15 @@ __device__ __forceinline__ uint8_t finish_and_regenerate(const DScene& sc, const
     return ST_TRACE_FIRST;
 }
 
-// BVH scenes: the finish stage between the two traversal kernels.  Walks the slots densely, consumes the post tags.
+// BVH scenes: the finish stage between the two traversal kernels.  Walks the work list, consumes the post tags.
 __global__ void __launch_bounds__(256) k_finish(DScene sc, DCamera cam, WfBuffers b, PassParams pp) {
     if (blockIdx.x == 0 && threadIdx.x < SQ_COUNT) b.counters[C_SHADE0 + threadIdx.x] = 0;   // consumed by the shading stage; k_bin refills them
+    WorkList wl;
+    wl.load(b.counters);
+    const uint32_t n_work = wl.total();
     uint32_t n_done = 0;
-    for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < b.pool; slot += gridDim.x * blockDim.x) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_work; i += gridDim.x * blockDim.x) {
+        const uint32_t slot = wl.slot(b.q_shade, i);
         const uint8_t po = b.post[slot];
         if (!po) continue;
         if (po & QZ_POST_DONE) {
@@ -273,6 +280,7 @@ __global__ void __launch_bounds__(256) k_finish(DScene sc, DCamera cam, WfBuffer
 //   post & SHADOW : the next-event shadow test of the last bounce (scene.cpp:136-143), radiance += contribution;
 //   post & DONE   : finish the path and start the next pixel-sample of the pass in the slot;
 //   stage != EMPTY: closest hit of the slot's ray (scene.cpp:61-117) and the family tag for k_bin.
+// The pass runs over the WORK LIST (wf_types.cuh), not over the pool.
 // The primitive records are staged once per CTA in shared memory together with each triangle's edges and normal
 // (make_flat_prim: the expressions tri_test uses), and every lane walks the same list in lockstep -- no stack, no
 // divergence inside a test, broadcast shared-memory reads.  The answer is the brute-force minimum under the (t, key)
@@ -285,9 +293,13 @@ __global__ void __launch_bounds__(128, 4) k_step_flat(DScene sc, DCamera cam, Wf
     for (uint32_t i = threadIdx.x; i < n_prims; i += blockDim.x)
         s_prims[i] = make_flat_prim(sc.prims[4 * i], sc.prims[4 * i + 1], sc.prims[4 * i + 2], sc.prims[4 * i + 3]);
     if (blockIdx.x == 0 && threadIdx.x < SQ_COUNT) b.counters[C_SHADE0 + threadIdx.x] = 0;   // consumed by the shading stage; k_bin refills them
+    __shared__ WorkList wl;
+    if (threadIdx.x == 0) wl.load(b.counters);
     __syncthreads();
+    const uint32_t n_work = wl.total();
     uint32_t n_closest = 0, n_shadow = 0, n_done = 0;
-    for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < b.pool; slot += gridDim.x * blockDim.x) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_work; i += gridDim.x * blockDim.x) {
+        const uint32_t slot = wl.slot(b.q_shade, i);
         uint8_t st = b.stage[slot];
         const uint8_t po = b.post[slot];
         float4 ro, rd;

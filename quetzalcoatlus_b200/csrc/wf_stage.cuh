@@ -108,6 +108,8 @@ __global__ void __launch_bounds__(256) k_sample(DScene sc, WfBuffers b) {
         for (int q = 0; q < SQ_COUNT; q++) shade += b.counters[C_SHADE0 + q];
         atomicAdd(&b.stats[S_SHADE], (unsigned long long)shade);
         b.counters[C_ACTIVE] = shade;
+        // the queues of this iteration are the next iteration's work list (wf_types.cuh, WorkList)
+        for (int q = 0; q < SQ_COUNT; q++) b.counters[C_WORK0 + q] = b.counters[C_SHADE0 + q];
         b.counters[C_CURSOR_TRACE] = 0;
         b.counters[C_CURSOR_SHADOW] = 0;
     }
@@ -191,6 +193,22 @@ __global__ void __launch_bounds__(256) k_film(WfBuffers b, PassParams pp, float*
                 if (albedo) albedo[o + k] = a[k] / inv;
             }
         }
+    }
+}
+
+// Image::save's tone path on the device film (image.cpp:7-19): 255 * powf(c, gamma) per channel with the channel order
+// reversed (the BGR float image the reference hands to cv::imwrite), and optionally that image saturated to 8 bits the
+// way OpenCV stores a CV_32F matrix into an 8-bit file (saturate_cast<uchar>: round to nearest even, clamp to 0..255).
+// The per-channel arithmetic is tone_value / tone_u8 (math.cuh).
+__global__ void __launch_bounds__(256) k_tone(const float* __restrict__ rgb, uint32_t n_pixels, float gamma, float* __restrict__ bgr255,
+                                               uint8_t* __restrict__ bgr8) {
+    const uint32_t n = n_pixels * 3u;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t pix = i / 3u, ch = i - 3u * pix;
+        const float c = rgb[3u * pix + (2u - ch)];
+        const float v = tone_value(c, gamma);
+        if (bgr255) bgr255[i] = v;
+        if (bgr8) bgr8[i] = tone_u8(v);
     }
 }
 

@@ -22,7 +22,8 @@
 // still hit different banks); only deeper excursions spill to the per-lane local-memory array behind it.  An
 // 8-wide tree over a million triangles is ~7 levels deep and a lane rarely holds more than a dozen entries, so the
 // local array -- 1 KB per lane that used to be the stack and competed with nodes and primitives for L1 -- is
-// untouched on almost every ray.  The slots are walked densely; the per-slot tag says which carry a ray.
+// untouched on almost every ray.  The kernel draws from the iteration's work list (wf_types.cuh); the per-slot tag
+// says which of its slots carry a ray for this stage.
 #pragma once
 
 #include "wf_types.cuh"
@@ -71,7 +72,10 @@ enum LaneState { LS_IDLE = 0, LS_NODE = 1, LS_PRIM = 2, LS_DONE = 3 };
 template <bool ANY_HIT, bool COUNT>
 __global__ void __launch_bounds__(128, QZ_TRACE_MIN_BLOCKS) k_trace_lane(DScene sc, WfBuffers b, uint32_t flags) {
     __shared__ uint2 s_stack[QZ_SMEM_STACK][128];
-    const uint32_t count = b.pool;
+    __shared__ WorkList wl;
+    if (threadIdx.x == 0) wl.load(b.counters);
+    __syncthreads();
+    const uint32_t count = wl.total();
     uint32_t* cursor = &b.counters[ANY_HIT ? C_CURSOR_SHADOW : C_CURSOR_TRACE];
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -136,8 +140,9 @@ __global__ void __launch_bounds__(128, QZ_TRACE_MIN_BLOCKS) k_trace_lane(DScene 
                 if (lane == 0) base = atomicAdd(cursor, (uint32_t)__popc(idle));
                 base = __shfl_sync(full, base, 0);
                 if (state == LS_IDLE) {
-                    const uint32_t idx = base + __popc(idle & ((1u << lane) - 1u));
-                    if (idx < count) {
+                    const uint32_t widx = base + __popc(idle & ((1u << lane) - 1u));
+                    if (widx < count) {
+                        const uint32_t idx = wl.slot(b.q_shade, widx);
                         float4 ro, rd;
                         bool live;
                         if (ANY_HIT) {

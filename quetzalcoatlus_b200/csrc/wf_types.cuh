@@ -50,7 +50,8 @@ enum Counter {
     C_SHADE0 = 2,                         // .. C_SHADE0 + SQ_COUNT - 1: queue lengths of this iteration
     C_CURSOR_TRACE = 12, C_CURSOR_SHADOW = 13,   // work cursors of the persistent traversal kernels
     C_NEXT_PATH = 14,                     // (pipeline 0's block only) next path id of the pass to hand out
-    C_WORDS = 16
+    C_WORK0 = 16,                         // .. C_WORK0 + SQ_COUNT - 1: queue lengths of the PREVIOUS iteration = this iteration's work list
+    C_WORDS = 32
 };
 // 64-bit statistics block (shared by all pipelines, atomics)
 enum Stat { S_RAYS_CLOSEST = 0, S_RAYS_SHADOW = 1, S_SHADE = 2, S_NODES = 3, S_PRIMS = 4, S_PATHS_DONE = 5, S_OVERFLOW = 6, S_WORDS = 8 };
@@ -104,6 +105,29 @@ struct PassParams {
 };
 
 #if defined(__CUDACC__)
+// WORK LIST of the intersection / finish stages.  Everything those stages have to do in an iteration was left by the
+// shading stage of the previous one (a shadow request, a finished path whose slot takes the next pixel-sample, a
+// continued ray), so their work list IS the previous iteration's shade queues, one after the other -- compact, in slot
+// order within a family, and already there.  (The first version walked every slot of the pool and looked at its tag:
+// in the tail of a pass, when a few long paths are left in a pool of millions, a warp found 2 live slots among its 32
+// and the stage cost as much as with a full pool -- profiles/r02_summary.md.)  k_generate seeds the list with the
+// slots it filled; k_sample's bookkeeping thread publishes the lengths (C_WORK0) after k_bin has built the queues.
+struct WorkList {
+    uint32_t start[SQ_COUNT + 1];
+    __device__ __forceinline__ void load(const uint32_t* counters) {
+        start[0] = 0;
+#pragma unroll
+        for (int q = 0; q < SQ_COUNT; q++) start[q + 1] = start[q] + counters[C_WORK0 + q];
+    }
+    __device__ __forceinline__ uint32_t total() const { return start[SQ_COUNT]; }
+    __device__ __forceinline__ uint32_t slot(uint32_t* const* queues, uint32_t i) const {
+        int q = 0;
+#pragma unroll
+        for (int k = 1; k < SQ_COUNT; k++) q += (i >= start[k]) ? 1 : 0;
+        return __ldcg(queues[q] + (i - start[q]));
+    }
+};
+
 // start fetching the 128-byte line that holds p
 __device__ __forceinline__ void prefetch_line(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void prefetch_line_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }

@@ -278,6 +278,18 @@ class Harness:
             raise RuntimeError(f"{self.prefix}sampler_eval failed with code {rc}")
         return out
 
+    def tone(self, rgb, gamma: float = 1.0):
+        """Image::save's tone path (image.cpp:7-19): (n, 3) RGB floats -> (255 * powf(c, gamma) as BGR floats, the same as
+        8-bit BGR)."""
+        a = _f32(rgb).reshape(-1, 3)
+        f = np.zeros_like(a)
+        u8 = np.zeros(a.shape, np.uint8)
+        rc = self._fn("tone")(a.ctypes.data_as(_c_float_p), len(a), ctypes.c_float(gamma), f.ctypes.data_as(_c_float_p),
+                              u8.ctypes.data_as(ctypes.c_void_p))
+        if rc != 0:
+            raise RuntimeError(f"{self.prefix}tone failed with code {rc}")
+        return f, u8
+
     def eval_spectrum(self, name: str, lambdas) -> np.ndarray:
         lam = _f32(lambdas).ravel()
         out = np.zeros(len(lam), np.float32)

@@ -154,4 +154,9 @@ int qzh_intersect(void* h, int n, const float* rays, float* out) {
 
 void qzh_force_brute_force(int) {}
 
+// Image::save's tone path (image.cpp:7-19) through the C ABI
+int qzh_tone(const float* rgb, int n_pixels, float gamma, float* bgr255, unsigned char* bgr8) {
+    return qz_tone(rgb, (uint32_t)n_pixels, gamma, bgr255, bgr8);
+}
+
 }  // extern "C"

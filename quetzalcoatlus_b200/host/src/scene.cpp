@@ -461,16 +461,17 @@ static void write_image(const std::string& filename, const std::vector<float>& b
     }
     bool ppm = filename.size() >= 4 && filename.compare(filename.size() - 4, 4, ".ppm") == 0;
     if (ppm) {
-        // 8-bit: x255 with the gamma exponent applied the way the reference does (image.cpp:10-15)
-        std::fprintf(f, "P6\n%zu %zu\n255\n", w, h);
-        std::vector<unsigned char> row(w * 3);
-        for (size_t y = 0; y < h; y++) {
-            for (size_t i = 0; i < w * 3; i++) {
-                float v = 255.0f * powf(buf[y * w * 3 + i], gamma);
-                row[i] = (unsigned char)(v < 0.0f ? 0.0f : (v > 255.0f ? 255.0f : v));
-            }
-            std::fwrite(row.data(), 1, row.size(), f);
+        // 8-bit: the tone path of image.cpp:10-15 (x255, powf gamma, BGR) runs as a kernel (qz_tone); a PPM stores RGB,
+        // so the channel swap the reference does for OpenCV is undone when the rows are written
+        std::vector<unsigned char> bgr(w * h * 3);
+        if (qz_tone(buf.data(), uint32_t(w * h), gamma, nullptr, bgr.data()) != QZ_OK) {
+            std::cerr << "error: save failed: " << qz_last_error() << std::endl;
+            std::fclose(f);
+            return;
         }
+        std::fprintf(f, "P6\n%zu %zu\n255\n", w, h);
+        for (size_t i = 0; i < w * h; i++) std::swap(bgr[3 * i], bgr[3 * i + 2]);
+        std::fwrite(bgr.data(), 1, bgr.size(), f);
     } else {
         std::fprintf(f, "PF\n%zu %zu\n-1.0\n", w, h);
         for (size_t row = h; row-- > 0;) std::fwrite(buf.data() + row * w * 3, sizeof(float), w * 3, f);

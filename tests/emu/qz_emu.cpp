@@ -201,6 +201,17 @@ int qz_math_probe(int op, uint32_t n, const float* in, float* out) {
     return QZ_OK;
 }
 
+int qz_film_device(qz_scene, float**, float**, float**, uint32_t*, uint32_t*) { g_error = "host emulation: no device film"; return QZ_ERR_NO_DEVICE; }
+int qz_tone_device(const float*, uint32_t, float, float*, uint8_t*, void*) { g_error = "host emulation: no device"; return QZ_ERR_NO_DEVICE; }
+int qz_tone(const float* rgb, uint32_t n_pixels, float gamma, float* bgr255, uint8_t* bgr8) {
+    for (uint64_t i = 0; i < (uint64_t)n_pixels * 3; i++) {
+        const float v = tone_value(rgb[3 * (i / 3) + (2 - i % 3)], gamma);
+        if (bgr255) bgr255[i] = v;
+        if (bgr8) bgr8[i] = tone_u8(v);
+    }
+    return QZ_OK;
+}
+
 int qz_sensor_eval(const qz_camera* camera, uint32_t n, const float* in, float* out) {
     DCamera cam = make_camera(camera);
     for (uint32_t i = 0; i < n; i++) {

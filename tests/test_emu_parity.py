@@ -129,3 +129,25 @@ def test_fast_arithmetic_build_stays_within_tolerance(emu, oracle, name):
     assert (got[:, RAYS] == want[:, RAYS]).all()
     assert bits_equal(got[:, :4], want[:, :4]).all() and bits_equal(got[:, NORMAL], want[:, NORMAL]).all()
     assert path_agreement(want, got, 1e-5).all()
+
+
+def _tone_inputs():
+    rng = np.random.default_rng(11)
+    rgb = np.concatenate([rng.uniform(0.0, 1.2, (20000, 3)), rng.uniform(0.0, 40.0, (2000, 3)),
+                          [[0.0, 1.0, 0.5], [1.0 / 255, 2.0 / 255, 0.5 / 255], [-0.25, 0.0, 1e-30]]]).astype(np.float32)
+    return rgb
+
+
+@pytest.mark.parametrize("gamma", [1.0, 0.45454547, 2.2])
+def test_tone_path_restatement(emu, oracle, gamma):
+    """Image::save's arithmetic (image.cpp:10-15) as restated in csrc/math.cuh (tone_value / tone_u8) against the oracle's
+    libm expression: bit-exact for the default gamma of 1, within one ulp otherwise (double pow rounded once vs glibc powf)."""
+    rgb = _tone_inputs()
+    got_f, got_u8 = emu.tone(rgb, gamma)
+    want_f, want_u8 = oracle.tone(rgb, gamma)
+    if gamma == 1.0:
+        assert bits_equal(got_f, want_f).all() and (got_u8 == want_u8).all()
+    else:
+        ok = np.isnan(want_f) & np.isnan(got_f) | (np.abs(got_f - want_f) <= np.spacing(np.abs(want_f)))
+        assert ok.all()
+        assert (np.abs(got_u8.astype(int) - want_u8.astype(int)) <= 1).all() and (got_u8 != want_u8).mean() < 1e-3

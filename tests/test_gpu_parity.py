@@ -387,6 +387,54 @@ def test_obj_viewer_1m_against_golden(qz):
             assert bits_equal(got[:, :4], g["records"][:, :4]).all()
 
 
+@pytest.mark.parametrize("gamma", [1.0, 0.45454547, 2.2])
+def test_tone_path_against_oracle(qz, oracle, gamma):
+    """SURVEY 8.f-3: Image::save's tone path (image.cpp:10-15: x255, powf gamma, BGR) as a kernel, through the C ABI
+    (qz_tone), against the oracle's libm expression: bit-exact at the default gamma of 1, within one ulp otherwise
+    (device double pow rounded once vs glibc powf), 8-bit output equal except at rounding knife edges."""
+    rng = np.random.default_rng(11)
+    rgb = np.concatenate([rng.uniform(0.0, 1.2, (200000, 3)), rng.uniform(0.0, 40.0, (2000, 3)),
+                          [[0.0, 1.0, 0.5], [1.0 / 255, 2.0 / 255, 0.5 / 255], [-0.25, 0.0, 1e-30]]]).astype(np.float32)
+    got_f, got_u8 = qz.tone(rgb, gamma)
+    want_f, want_u8 = oracle.tone(rgb, gamma)
+    if gamma == 1.0:
+        assert bits_equal(got_f, want_f).all() and (got_u8 == want_u8).all()
+    else:
+        ok = np.isnan(want_f) & np.isnan(got_f) | (np.abs(got_f - want_f) <= np.spacing(np.abs(want_f)))
+        print(f"tone gamma {gamma}: {(got_f != want_f).mean():.2e} of values differ from glibc powf (by one ulp)")
+        assert ok.all()
+        assert (np.abs(got_u8.astype(int) - want_u8.astype(int)) <= 1).all() and (got_u8 != want_u8).mean() < 1e-3
+
+
+def test_film_stays_on_the_device_for_a_denoiser(qz):
+    """AOV hand-off (RenderResult::denoise, image.cpp:47-95): after render() the three planes are still on the device
+    (qz_film_device) and equal what render() returned; the tone kernel runs on them in place (qz_tone_device)."""
+    import ctypes
+
+    import torch
+
+    lib = qz.lib
+    with qz.build_scene("cornell_box", 48, 40) as sc:
+        out = sc.render(spp=2, max_bounces=4)
+        ptrs = [ctypes.c_void_p() for _ in range(3)]
+        w, h = ctypes.c_uint32(), ctypes.c_uint32()
+        rc = lib.qz_film_device(ctypes.c_void_p(sc.c_scene_handle()), ctypes.byref(ptrs[0]), ctypes.byref(ptrs[1]), ctypes.byref(ptrs[2]),
+                                ctypes.byref(w), ctypes.byref(h))
+        assert rc == 0 and (w.value, h.value) == (48, 40) and all(p.value for p in ptrs)
+        n = 48 * 40
+        planes = []
+        for p in ptrs:
+            host = np.zeros((40, 48, 3), np.float32)
+            assert torch.cuda.cudart().cudaMemcpy(host.ctypes.data, p.value, n * 12, 2) == 0   # device -> host
+            planes.append(host)
+        assert bits_equal(planes[0], out.color).all() and bits_equal(planes[1], out.normal).all() and bits_equal(planes[2], out.albedo).all()
+        bgr8 = torch.zeros(n * 3, dtype=torch.uint8, device="cuda")
+        assert lib.qz_tone_device(ptrs[0], n, ctypes.c_float(1.0), None, ctypes.c_void_p(bgr8.data_ptr()), None) == 0
+        torch.cuda.synchronize()
+        want = np.clip(np.rint(255.0 * out.color[..., ::-1].astype(np.float32)), 0, 255).astype(np.uint8)
+        assert (bgr8.cpu().numpy().reshape(40, 48, 3) == want).all()
+
+
 def test_error_conventions(qz):
     import ctypes
 

@@ -40,6 +40,20 @@ def test_reference_color_test_output(oracle):
         assert want.strip() in lines, f"color_test no longer prints {want!r}"
 
 
+def test_shipped_rgb_to_spectrum_table_is_what_the_reference_optimiser_writes(tmp_path):
+    """data/coeffs_SRGB_32.dat must be byte for byte what rgb_to_spectrum_opt.cpp:788-898 produces.
+    The reference's color_test, built from unmodified sources, runs the optimiser when its working directory holds
+    no cached table (get_coeffs, :873-898) and writes the file there."""
+    exe = ROOT / "oracle" / "_ref" / "color_test"
+    if not exe.exists():
+        pytest.skip("oracle/_ref/color_test not built")
+    subprocess.run([str(exe)], cwd=tmp_path, capture_output=True, text=True, check=True, timeout=600)
+    fresh = (tmp_path / "coeffs_SRGB_32.dat").read_bytes()
+    shipped = (ROOT / "quetzalcoatlus_b200" / "data" / "coeffs_SRGB_32.dat").read_bytes()
+    assert len(fresh) == (32 + 3 * 32 ** 3 * 3) * 4
+    assert fresh == shipped
+
+
 @pytest.mark.parametrize("fixture", ["sampler_kat.npz", "sampler_kat_800.npz"])
 def test_oracle_reproduces_sampler_fixture(oracle, fixture):
     g = np.load(GOLDEN / fixture)
