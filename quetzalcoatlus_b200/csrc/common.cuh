@@ -67,14 +67,28 @@ QZ_HD V3 operator+(V3 a, V3 b) { return v3(a.x + b.x, a.y + b.y, a.z + b.z); }
 QZ_HD V3 operator-(V3 a, V3 b) { return v3(a.x - b.x, a.y - b.y, a.z - b.z); }
 QZ_HD V3 operator-(V3 a) { return v3(-a.x, -a.y, -a.z); }
 QZ_HD V3 operator*(V3 a, float s) { return v3(a.x * s, a.y * s, a.z * s); }
-QZ_HD V3 operator/(V3 a, float s) { return v3(a.x / s, a.y / s, a.z / s); }
+// IEEE a / b.  On the device a ZERO NUMERATOR sends the division into its out-of-line slow path (FCHK flags it), ~30
+// instructions and a divergent call -- and the components of an axis-aligned normal are zeros: normalising the
+// geometric normal of a wall and building its frame took that path four times per bounce, a tenth of the diffuse
+// shading kernel's instructions (profiles/r02_summary.md).  0 / b for an ordinary b is a zero with the signs xor-ed;
+// everything else is the division itself.
+QZ_HD float div_zn(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    const bool z = a == 0.0f && b != 0.0f && b == b;
+    const float q = (z ? 1.0f : a) / b;
+    return z ? __uint_as_float(__float_as_uint(a) ^ (__float_as_uint(b) & 0x80000000u)) : q;
+#else
+    return a / b;
+#endif
+}
+QZ_HD V3 operator/(V3 a, float s) { return v3(div_zn(a.x, s), div_zn(a.y, s), div_zn(a.z, s)); }
 // vec.cpp:116-126: (x*x' + y*y') + z*z'
 QZ_HD float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 QZ_HD V3 cross(V3 a, V3 b) { return v3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
 QZ_HD float norm_squared(V3 a) { return a.x * a.x + a.y * a.y + a.z * a.z; }
 QZ_HD float norm(V3 a) { return sqrtf(a.x * a.x + a.y * a.y + a.z * a.z); }
 // vec.cpp:99-102: divide each component by the norm (no reciprocal)
-QZ_HD V3 normalized(V3 a) { float n = norm(a); return v3(a.x / n, a.y / n, a.z / n); }
+QZ_HD V3 normalized(V3 a) { float n = norm(a); return v3(div_zn(a.x, n), div_zn(a.y, n), div_zn(a.z, n)); }
 
 struct V2 {
     float x, y;

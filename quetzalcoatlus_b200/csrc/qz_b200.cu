@@ -257,7 +257,7 @@ struct DevBuf {
 #define QZ_MAX_PIPELINES 4
 
 struct WorkMem {
-    DevBuf rec_hot, rec_side, qbufs[8], tags[3], counters, statsb, res_a, res_b, res_c, rowsb, sensor, acc;
+    DevBuf rec_hot, rec_side, qbufs[8], tags[3], counters, statsb, res_a, res_b, res_c, rowsb, sensor, acc, memo;
     uint32_t pool = 0;
     uint64_t cells = 0, acc_pix = 0, rows = 0;
     uint32_t* h_counters = nullptr;  // pinned
@@ -362,7 +362,9 @@ int qz_scene_commit(qz_scene s, const qz_scene_tables* t) {
 static int render_impl(qz_scene s, const qz_camera* camera, uint32_t n_samples, uint32_t max_bounces, const qz_region* region,
                        const qz_render_options* options, float* d_color, float* d_normal, float* d_albedo,
                        cudaStream_t stream, qz_stats* stats_out) {
-    const DScene& sc = s->store.view;
+    // the kernels receive a per-call copy of the scene view: it carries the pass's sample memo (sampler.cuh)
+    DScene sc = s->store.view;
+    sc.memo = SampleMemo{nullptr, 0, 0, 0};
     const uint32_t W = camera->image_width, H = camera->image_height;
     if (!W || !H || !n_samples) return fail(QZ_ERR_INVALID, "empty image or zero samples");
     if (max_bounces > 65535) return fail(QZ_ERR_INVALID, "max_bounces > 65535 is not supported (the path depth is a 16-bit field)");
@@ -438,6 +440,21 @@ static int render_impl(qz_scene s, const qz_camera* camera, uint32_t n_samples, 
     QZ_CUDA(res_c.reserve(cells * 4));
     QZ_CUDA(rowsb.reserve(rows.size() * 4));
     QZ_CUDA(sensor.reserve(3 * 471 * 4));
+    // SAMPLE MEMO (sampler.cuh): worth its memset when several pixels share a Halton index, i.e. when the call owns
+    // several times more pixels than there are (x mod 128, y mod 128) classes.  Rows: the jitter, the wavelength draw
+    // and eight bounces' worth of dimensions (later bounces evaluate directly), within a 2 GB budget.
+    static const int env_memo = [] { const char* e = std::getenv("QZ_MEMO"); return e ? std::atoi(e) : 1; }();
+    uint32_t memo_dims = 0;
+    const uint64_t memo_n = (uint64_t)s_pass * spar.stride;
+    {
+        const uint64_t classes = (uint64_t)std::min<uint32_t>(W, QZ_MAX_HALTON_RESOLUTION) * std::min<uint32_t>(H, QZ_MAX_HALTON_RESOLUTION);
+        if (env_memo && n_pix64 >= 4 * classes && memo_n < (1ull << 31)) {
+            const uint64_t fit = (2ull << 30) / (memo_n * 4);
+            memo_dims = (uint32_t)std::min<uint64_t>(3 + 8 * 8, fit);
+            if (memo_dims < 3 + 8) memo_dims = 0;
+        }
+    }
+    if (memo_dims) QZ_CUDA(wm.memo.reserve((size_t)memo_dims * memo_n * 4));
     const bool multi_pass = s_pass < n_samples;
     if (multi_pass) QZ_CUDA(acc.reserve((size_t)n_pix * 9 * 4));
     QZ_CUDA(cudaMemcpyAsync(rowsb.p, rows.data(), rows.size() * 4, cudaMemcpyHostToDevice, stream));
@@ -599,6 +616,13 @@ static int render_impl(qz_scene s, const qz_camera* camera, uint32_t n_samples, 
         pp.width = W; pp.height = H;
         pp.spar = spar;
         pp_cur = pp;
+        if (memo_dims) {
+            sc.memo.tab = wm.memo.as<uint32_t>();
+            sc.memo.dims = memo_dims;
+            sc.memo.n = pp.s_count * spar.stride;
+            sc.memo.index0 = s_begin * spar.stride;
+            QZ_RENDER_CUDA(cudaMemsetAsync(sc.memo.tab, 0xff, (size_t)memo_dims * sc.memo.n * 4, stream));
+        }
 
         // initial fill: pipeline p starts with the next `first[p]` path ids; the shared cursor continues behind them
         uint32_t init[C_WORDS * QZ_MAX_PIPELINES] = {0};

@@ -197,6 +197,62 @@ QZ_HD float sample_dimension(const SamplerDim* __restrict__ table, const Sampler
     return owen_scrambled_radical_inv(rec, sampler_prefix_array(table), smp.index);
 }
 
+// SAMPLE MEMO.  The value of a dimension depends on nothing but (dimension, Halton index), and the index depends on
+// the pixel only through (x mod 128, y mod 128) (sampler_start): in an 800 x 800 image 39 pixels share every index of
+// a sample number, in a 4K image 506.  The wavefront therefore keeps, per render pass, a table value[dim][index -
+// index0] over the pass's index range (32-bit float patterns, all-ones = not yet computed; a valid value is < 1):
+// the first path that needs an entry runs the digit loops and stores the result, every later one loads it.  Entries
+// only ever change from "empty" to the one value the reference's arithmetic gives, so races are harmless and the
+// samples are the reference's bit for bit.  Rows 0 and 1 hold the two pixel-jitter radical inverses.  tab == nullptr
+// (per-path replay, host emulation, small images without reuse) evaluates directly.
+#define QZ_MEMO_EMPTY 0xffffffffu
+struct SampleMemo {
+    uint32_t* tab;
+    uint32_t dims;     // rows
+    uint32_t n;        // entries per row
+    uint32_t index0;   // first Halton index of the pass
+};
+QZ_HD uint32_t* memo_slot(const SampleMemo& m, uint32_t dim, uint32_t index) {
+    if (!m.tab || dim >= m.dims) return nullptr;
+    const uint32_t i = index - m.index0;
+    if (i >= m.n) return nullptr;
+    return m.tab + (size_t)dim * m.n + i;
+}
+QZ_HD uint32_t memo_load(const uint32_t* p) {
+#if defined(__CUDA_ARCH__)
+    return p ? __ldcg(p) : QZ_MEMO_EMPTY;   // L2: the table is shared by all SMs and written while it is read
+#else
+    return p ? *p : QZ_MEMO_EMPTY;
+#endif
+}
+QZ_HD void memo_store(uint32_t* p, float v) {
+#if defined(__CUDA_ARCH__)
+    if (p) __stcg(p, __float_as_uint(v));
+#else
+    if (p) *p = float_as_u32(v);
+#endif
+}
+QZ_HD float sample_dimension_memo(const SamplerDim* __restrict__ table, const SampleMemo& m, uint32_t index, uint32_t dim) {
+    uint32_t* p = memo_slot(m, dim, index);
+    const uint32_t bits = memo_load(p);
+    if (bits != QZ_MEMO_EMPTY) return u32_as_float(bits);
+    Sampler smp; smp.index = index; smp.dim = 0;
+    const float v = sample_dimension(table, smp, dim);
+    memo_store(p, v);
+    return v;
+}
+QZ_HD V2 sampler_pixel_jitter_memo(const SamplerParams& sp, const SampleMemo& m, const Sampler& smp) {
+    uint32_t* p0 = memo_slot(m, 0, smp.index);
+    uint32_t* p1 = memo_slot(m, 1, smp.index);
+    const uint32_t b0 = memo_load(p0), b1 = memo_load(p1);
+    V2 j;
+    if (b0 != QZ_MEMO_EMPTY) j.x = u32_as_float(b0);
+    else { j.x = radical_inv(2, smp.index >> sp.exp0); memo_store(p0, j.x); }
+    if (b1 != QZ_MEMO_EMPTY) j.y = u32_as_float(b1);
+    else { j.y = radical_inv(3, smp.index / sp.scale1); memo_store(p1, j.y); }
+    return j;
+}
+
 // two independent dimensions evaluated in one loop: the digit chains of the two dimensions do
 // not depend on each other, so interleaving them doubles the instruction-level parallelism of
 // what is otherwise one long dependent integer chain per digit

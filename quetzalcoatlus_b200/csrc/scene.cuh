@@ -35,6 +35,7 @@ struct DScene {
     const uint32_t* leaf_prims; // primitive indices in leaf order
     const SamplerDim* sampler_table;
     const float* rho_tab;       // depth-0 albedo sample tables (see bxdf.cuh)
+    SampleMemo memo;            // per-pass table of sampler values (sampler.cuh); tab == nullptr: none
     uint32_t* overflow;         // set to 1 by the per-thread traversal (bvh.cuh) when its stack overflowed
     uint32_t n_lights;
     uint32_t n_prims;

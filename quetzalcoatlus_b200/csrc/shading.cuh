@@ -170,11 +170,12 @@ enum SampleRole { R_MAT = 0, R_PICK = 1, R_LIGHT = 2 /* and 3 */, R_BSDF = 4 /* 
 struct SamplesOnTheFly {
     const SamplerDim* tab;
     uint32_t index;
-    QZ_HD float one(int, uint32_t dim) const {
-        Sampler s; s.index = index; s.dim = 0;
-        return sample_dimension(tab, s, dim);
+    SampleMemo memo;   // the wavefront's table of values already computed this pass (sampler.cuh); none in the replay
+    QZ_HD float one(int, uint32_t dim) const { return sample_dimension_memo(tab, memo, index, dim); }
+    QZ_HD V2 two(int, uint32_t dim) const {
+        if (memo.tab) return v2(sample_dimension_memo(tab, memo, index, dim), sample_dimension_memo(tab, memo, index, dim + 1));
+        return owen_scrambled_radical_inv_pair(load_dim(tab, dim), load_dim(tab, dim + 1), sampler_prefix_array(tab), index);
     }
-    QZ_HD V2 two(int, uint32_t dim) const { return owen_scrambled_radical_inv_pair(load_dim(tab, dim), load_dim(tab, dim + 1), sampler_prefix_array(tab), index); }
 };
 
 struct SamplesPrecomputed {
@@ -373,12 +374,12 @@ QZ_HD bool shade_bounce(const DScene& sc, PathState& ps, PathAov& aov, const Hit
 QZ_HD void start_path(const DScene& sc, const DCamera& cam, const SamplerParams& spar, uint32_t x, uint32_t y, uint32_t s,
                       PathState& ps, PathAov& aov) {
     ps.smp = sampler_start(spar, x, y, s);
-    V2 jitter = sampler_pixel_jitter(spar, ps.smp);
+    V2 jitter = sampler_pixel_jitter_memo(spar, sc.memo, ps.smp);
     float u = (float)x + jitter.x;
     float v = (float)y + jitter.y;
     ps.ray.o = cam.pos;
     ps.ray.d = cam.bottom_left + cam.du * u + cam.dv * v - cam.pos;
-    float ul = sample_1d(sc.sampler_table, ps.smp);
+    float ul = sample_dimension_memo(sc.sampler_table, sc.memo, ps.smp.index, sample_1d_skip(ps.smp));
     sample_wavelengths(ul, ps.lambda, ps.pdf);
     ps.weight = spec4(1.0f);
     ps.L = spec4(0.0f);
@@ -404,7 +405,7 @@ QZ_HD void run_path(const DScene& sc, const DCamera& cam, const SamplerParams& s
         ps.n_rays++;
         ShadowRequest sh;
         SamplesOnTheFly src;
-        src.tab = sc.sampler_table; src.index = ps.smp.index;
+        src.tab = sc.sampler_table; src.index = ps.smp.index; src.memo = sc.memo;
         Spec4 gain;
         bool has_gain;
         bool alive = shade_bounce<KH_ANY, -1, false>(sc, ps, aov, hit, max_bounces, sh, src, gain, has_gain);

@@ -32,16 +32,40 @@ QZ_HD float sigmoid_poly(float c0, float c1, float c2, float lambda) {
     return sigmoidf<R>(c0 + c1 * lambda + c2 * lambda * lambda);
 }
 
+// The three tables a spectrum evaluation reads.  The out-of-line evaluators below take this BY VALUE (six registers),
+// not the scene by reference: a reference parameter of a real call forced every shading kernel to keep a copy of the
+// whole DScene in local memory (a 200-byte frame per thread that, at 640 threads per SM, competed with the scene
+// tables for L1) and the callee to reach the tables through it.
+struct SpecView {
+    const qz_spectrum* spectra;
+    const float* pool;
+    const uint8_t* pw_accel;
+};
+QZ_HD SpecView spec_view(const DScene& sc) { SpecView v; v.spectra = sc.spectra; v.pool = sc.pool; v.pw_accel = sc.pw_accel; return v; }
+
+// lroundf(x) for |x| < 2^22 (wavelength offsets): round half away from zero.  x - trunc(x) is exact, so this is the
+// same integer; CUDA's lroundf is a 64-bit software sequence (5 % of the sensor stage's instructions).
+QZ_HD int lround_small(float x) {
+    const float t = truncf(x);
+    const float r = x - t;
+    int i = (int)t;
+    if (r >= 0.5f) i++;
+    if (r <= -0.5f) i--;
+    return i;
+}
+
 // every kind except RGB_ILLUMINANT (which multiplies by another spectrum)
 template <bool R>
-QZ_HD float eval_spectrum_leaf(const DScene& sc, const qz_spectrum& s, float lambda) {
+QZ_HD float eval_spectrum_leaf(const SpecView& sc, const qz_spectrum& s, float lambda) {
     {
         switch (s.kind) {
             case QZ_SPEC_CONSTANT:
                 return s.a;
             case QZ_SPEC_DENSE: {
-                long idx = lroundf(lambda - (float)s.aux);
-                if (idx < 0 || idx >= (long)s.count) return 0.0f;
+                const float off = lambda - (float)s.aux;
+                if (!(off > -4194304.0f && off < 4194304.0f)) return 0.0f;   // (also NaN) far outside any table
+                const int idx = lround_small(off);
+                if (idx < 0 || idx >= (int)s.count) return 0.0f;
                 return sc.pool[s.offset + idx];
             }
             case QZ_SPEC_PIECEWISE: {
@@ -88,7 +112,7 @@ QZ_HD float eval_spectrum_leaf(const DScene& sc, const qz_spectrum& s, float lam
     }
 }
 
-QZ_HD qz_spectrum load_spectrum(const DScene& sc, int32_t id) {
+QZ_HD qz_spectrum load_spectrum(const SpecView& sc, int32_t id) {
 #if defined(__CUDA_ARCH__)
     // one 32-byte record = two 16-byte loads through the read-only path
     const uint4* p = reinterpret_cast<const uint4*>(sc.spectra + id);
@@ -102,8 +126,10 @@ QZ_HD qz_spectrum load_spectrum(const DScene& sc, int32_t id) {
 #endif
 }
 
+QZ_HD qz_spectrum load_spectrum(const DScene& sc, int32_t id) { return load_spectrum(spec_view(sc), id); }
+
 template <bool R>
-QZ_HD float eval_spectrum_rec(const DScene& sc, const qz_spectrum& s, float lambda) {
+QZ_HD float eval_spectrum_rec(const SpecView& sc, const qz_spectrum& s, float lambda) {
     if (s.kind == QZ_SPEC_RGB_ILLUMINANT) {
         if (s.aux < 0) return 0.0f;
         // m_scale * m_polynomial(lambda) * illuminant(lambda), left to right (rgb.cpp:191-196);
@@ -115,16 +141,27 @@ QZ_HD float eval_spectrum_rec(const DScene& sc, const qz_spectrum& s, float lamb
     return eval_spectrum_leaf<R>(sc, s, lambda);
 }
 
+template <bool R>
+QZ_HD float eval_spectrum_rec(const DScene& sc, const qz_spectrum& s, float lambda) { return eval_spectrum_rec<R>(spec_view(sc), s, lambda); }
+
 // Spectrum::operator() in the reference's arithmetic (probes, index of refraction)
-QZ_HD_CALL float eval_spectrum(const DScene& sc, int32_t id, float lambda) {
+QZ_HD_CALL float eval_spectrum_call(SpecView sc, int32_t id, float lambda) {
     return eval_spectrum_rec<false>(sc, load_spectrum(sc, id), lambda);
 }
+QZ_HD float eval_spectrum(const DScene& sc, int32_t id, float lambda) { return eval_spectrum_call(spec_view(sc), id, lambda); }
 
 // SpectrumSample::from_spectrum (spectrum_sample.cpp:49-58), radiometric: the record (and an illuminant's
 // second record) is fetched ONCE for the four wavelengths, and the four evaluations are one instruction
 // stream the scheduler can interleave -- as four calls of eval_spectrum() they were four serial chains of
 // dependent loads, 12 % of a shading kernel's instructions for the record fetch alone.
-QZ_HD_CALL Spec4 from_spectrum(const DScene& sc, int32_t id, const Spec4& lambda) {
+// (arguments and result of the real call travel in registers: scalars in, one 16-byte vector out)
+struct SpecRet { float x, y, z, w; };
+QZ_HD_CALL SpecRet from_spectrum_call(SpecView sc, int32_t id, float la, float lb, float lc, float ld);
+QZ_HD Spec4 from_spectrum(const DScene& sc, int32_t id, const Spec4& lambda) {
+    const SpecRet r = from_spectrum_call(spec_view(sc), id, lambda.v[0], lambda.v[1], lambda.v[2], lambda.v[3]);
+    return spec4(r.x, r.y, r.z, r.w);
+}
+QZ_HD Spec4 from_spectrum_body(const SpecView& sc, int32_t id, const Spec4& lambda) {
     const qz_spectrum s = load_spectrum(sc, id);
     if (s.kind == QZ_SPEC_RGB_ILLUMINANT) {
         if (s.aux < 0) return spec4(0.0f);
@@ -140,11 +177,22 @@ QZ_HD_CALL Spec4 from_spectrum(const DScene& sc, int32_t id, const Spec4& lambda
     for (int k = 0; k < 4; k++) r.v[k] = eval_spectrum_leaf<true>(sc, s, lambda.v[k]);
     return r;
 }
+QZ_HD_CALL SpecRet from_spectrum_call(SpecView sc, int32_t id, float la, float lb, float lc, float ld) {
+    const Spec4 r = from_spectrum_body(sc, id, spec4(la, lb, lc, ld));
+    SpecRet o; o.x = r.v[0]; o.y = r.v[1]; o.z = r.v[2]; o.w = r.v[3];
+    return o;
+}
 
 // RGBColorSpace::to_spectrum + RGBToSpectrumTable::operator() (rgb.cpp:50-57, 78-140);
 // returns (c0, c1, c2) of the sigmoid polynomial.  The reference's arithmetic in both builds: the
 // coefficients feed a polynomial whose terms cancel (see sigmoid_poly), so a relative 1e-7 here is 1e-4 there.
-QZ_HD_CALL V3 rgb_to_sigmoid(const DScene& sc, float r, float g, float b) {
+struct LutView { const float* lut_z; const float* lut_coeffs; };
+QZ_HD_CALL V3 rgb_to_sigmoid_call(LutView sc, float r, float g, float b);
+QZ_HD V3 rgb_to_sigmoid(const DScene& sc, float r, float g, float b) {
+    LutView v; v.lut_z = sc.lut_z; v.lut_coeffs = sc.lut_coeffs;
+    return rgb_to_sigmoid_call(v, r, g, b);
+}
+QZ_HD_CALL V3 rgb_to_sigmoid_call(LutView sc, float r, float g, float b) {
     r = std_clamp(r, 0.0f, 1.0f); g = std_clamp(g, 0.0f, 1.0f); b = std_clamp(b, 0.0f, 1.0f);
     if (r == g && g == b) {
         return v3(0.0f, 0.0f, (r - 0.5f) / sqrtf(std_max(0.0f, r * (1.0f - r))));
@@ -200,7 +248,7 @@ QZ_HD void terminate_secondary(Spec4& pdf) {
 
 // DenselySampledSpectrum lookup of one sensor curve (lambda_min 360, 471 samples)
 QZ_HD float sensor_curve(const float* curve, float lambda) {
-    long idx = lroundf(lambda - 360.0f);
+    const int idx = lround_small(lambda - 360.0f);
     if (idx < 0 || idx >= 471) return 0.0f;
     return curve[idx];
 }
@@ -210,8 +258,8 @@ QZ_HD V3 to_sensor_rgb(const DCamera& cam, const Spec4& L, const Spec4& lambda, 
     Spec4 l = r_div(L, pdf);
     float rgb[3];
     // the four curve indices are the same for the three curves
-    long idx[4];
-    for (int j = 0; j < 4; j++) idx[j] = lroundf(lambda.v[j] - 360.0f);
+    int idx[4];
+    for (int j = 0; j < 4; j++) idx[j] = lround_small(lambda.v[j] - 360.0f);   // wavelengths lie in [360, 830]
     for (int k = 0; k < 3; k++) {
         const float* curve = cam.sensor + k * 471;
         Spec4 resp;

@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(256) k_albedo_conductor(DScene sc, WfBuffers b
 }
 
 #ifndef QZ_SHADE_MIN_BLOCKS_LIGHT
-#define QZ_SHADE_MIN_BLOCKS_LIGHT 5   /* diffuse / dielectric shade kernels: 96 registers */
+#define QZ_SHADE_MIN_BLOCKS_LIGHT 4   /* diffuse / dielectric shade kernels: 128 registers (5 blocks = 96 registers spills: -12 % on the stage) */
 #endif
 #ifndef QZ_SHADE_MIN_BLOCKS_HEAVY
 #define QZ_SHADE_MIN_BLOCKS_HEAVY 4   /* conductor / run-time-dispatch shade kernels */
@@ -188,7 +188,7 @@ k_shade(DScene sc, WfBuffers b, uint32_t max_bounces) {
         bool has_gain, alive;
         if (KH == KH_ANY) {
             SamplesOnTheFly src;
-            src.tab = sc.sampler_table; src.index = ps.smp.index;
+            src.tab = sc.sampler_table; src.index = ps.smp.index; src.memo = sc.memo;
             alive = shade_bounce<KH, -1, true>(sc, ps, aov, hit, max_bounces, sh, src, gain, has_gain);
         } else {
             const float4* sv = b.samples.at(slot);
@@ -276,87 +276,144 @@ __global__ void __launch_bounds__(256) k_finish(DScene sc, DCamera cam, WfBuffer
 }
 
 // Flat scenes (<= QZ_FLAT_MAX_PRIMS primitives: every shipped analytic scene): no BVH and no separate shadow /
-// finish / closest-hit kernels.  ONE pass over the slots does, per slot, what its tags ask for:
+// finish / closest-hit kernels.  ONE kernel does, per slot of the work list (wf_types.cuh), what its tags ask for:
 //   post & SHADOW : the next-event shadow test of the last bounce (scene.cpp:136-143), radiance += contribution;
 //   post & DONE   : finish the path and start the next pixel-sample of the pass in the slot;
 //   stage != EMPTY: closest hit of the slot's ray (scene.cpp:61-117) and the family tag for k_bin.
-// The pass runs over the WORK LIST (wf_types.cuh), not over the pool.
 // The primitive records are staged once per CTA in shared memory together with each triangle's edges and normal
 // (make_flat_prim: the expressions tri_test uses), and every lane walks the same list in lockstep -- no stack, no
 // divergence inside a test, broadcast shared-memory reads.  The answer is the brute-force minimum under the (t, key)
-// order, i.e. exactly what the BVH traversal is defined to return.  Against the three kernels it replaces, a
-// slot's record is visited once instead of up to three times and a finished path's radiance never leaves the
-// registers between the shadow test and the sensor.
+// order, i.e. exactly what the BVH traversal is defined to return.
+//
+// A CTA works on TILES of QZ_FLAT_TILE consecutive work-list entries (drawn from an atomic cursor) in three dense
+// phases, because the three jobs are needed by different subsets of the lanes:
+//   1. shadow tests; slots whose path is finished are collected in a shared-memory list;
+//   2. that list, densely: sensor conversion, result cell, new path -- the sampler's integer chains of a new path
+//      (Halton index, pixel jitter, the wavelength draw) used to run inside the per-slot pass with a third of the
+//      lanes (10 of 32 per instruction, a quarter of the kernel's instructions: profiles/r02_summary.md);
+//   3. closest hit for every slot of the tile that carries a ray.
+// Shadow rays ask "is there any hit with t <= 1" (the closest hit has t <= 1 iff some hit has): emitter primitives are
+// staged first and a lane leaves the loop at its first occluder, so the rays that end on the light's own geometry
+// (all of them for an axis-aligned emitter) test one primitive instead of all.
+#ifndef QZ_FLAT_TILE
+#define QZ_FLAT_TILE 1024
+#endif
+
+// any valid hit with t <= 1?  The validity conditions are tri_test_pre's; T / absDen <= 1 iff T <= absDen (round to
+// nearest cannot carry a quotient > 1 down to 1: that needs ulp(absDen) / absDen == 2^-24 exactly), so no division.
+__device__ __forceinline__ bool tri_occludes(V3 O, V3 D, float tnear, V3 v0, V3 e1, V3 e2, V3 ng) {
+    const V3 C = v0 - O;
+    const V3 R = cross(C, D);
+    const float den = dot(ng, D);
+    const float absDen = fabsf(den);
+    const uint32_t s = float_as_u32(den) & 0x80000000u;
+    const float U = xor_sign(dot(R, e2), s);
+    const float V = xor_sign(dot(R, e1), s);
+    if (!(den != 0.0f) || !(U >= 0.0f) || !(V >= 0.0f) || !(U + V <= absDen)) return false;
+    const float T = xor_sign(dot(ng, C), s);
+    return absDen * tnear < T && T <= absDen;
+}
+__device__ __forceinline__ bool flat_prim_occludes(const FlatPrim& f, V3 O, V3 D, float rd2) {
+    const uint32_t kind = prim_kind(float_as_u32(f.e1a.w));
+    if (kind == QZ_PRIM_SPHERE) {
+        PrimHit h;
+        return sphere_test_rd2(O, D, rd2, QZ_TNEAR, INFINITY, xyz(f.a), f.b.x, h) && h.t <= 1.0f;
+    }
+    if (tri_occludes(O, D, QZ_TNEAR, xyz(f.a), xyz(f.e1a), xyz(f.e2a), xyz(f.nga))) return true;
+    return kind != QZ_PRIM_TRIANGLE && f.c.w != 0.0f &&
+           tri_occludes(O, D, QZ_TNEAR, xyz(f.c), xyz(f.e1b), xyz(f.e2b), v3(f.nga.w, f.e1b.w, f.e2b.w));
+}
+
 __global__ void __launch_bounds__(128, 4) k_step_flat(DScene sc, DCamera cam, WfBuffers b, PassParams pp, uint32_t flags) {
     __shared__ FlatPrim s_prims[QZ_FLAT_MAX_PRIMS];
-    const uint32_t n_prims = sc.n_prims;
-    for (uint32_t i = threadIdx.x; i < n_prims; i += blockDim.x)
-        s_prims[i] = make_flat_prim(sc.prims[4 * i], sc.prims[4 * i + 1], sc.prims[4 * i + 2], sc.prims[4 * i + 3]);
-    if (blockIdx.x == 0 && threadIdx.x < SQ_COUNT) b.counters[C_SHADE0 + threadIdx.x] = 0;   // consumed by the shading stage; k_bin refills them
+    __shared__ uint8_t s_emit[QZ_FLAT_MAX_PRIMS];
+    __shared__ uint32_t s_slot[QZ_FLAT_TILE], s_done[QZ_FLAT_TILE];
+    __shared__ uint32_t s_ndone, s_tile;
     __shared__ WorkList wl;
+    const uint32_t n_prims = sc.n_prims;
+    // stage the primitives, emitter geometry first (stable partition; the closest hit does not depend on the order)
+    for (uint32_t i = threadIdx.x; i < n_prims; i += blockDim.x)
+        s_emit[i] = sc.geoms[float_as_u32(sc.prims[4 * i].w)].light >= 0 ? 1 : 0;
     if (threadIdx.x == 0) wl.load(b.counters);
+    if (blockIdx.x == 0 && threadIdx.x < SQ_COUNT) b.counters[C_SHADE0 + threadIdx.x] = 0;   // consumed by the shading stage; k_bin refills them
     __syncthreads();
+    for (uint32_t i = threadIdx.x; i < n_prims; i += blockDim.x) {
+        uint32_t before_same = 0, n_emit = 0;
+        for (uint32_t j = 0; j < n_prims; j++) {
+            n_emit += s_emit[j];
+            if (j < i && s_emit[j] == s_emit[i]) before_same++;
+        }
+        const uint32_t pos = s_emit[i] ? before_same : n_emit + before_same;
+        s_prims[pos] = make_flat_prim(sc.prims[4 * i], sc.prims[4 * i + 1], sc.prims[4 * i + 2], sc.prims[4 * i + 3]);
+    }
     const uint32_t n_work = wl.total();
     uint32_t n_closest = 0, n_shadow = 0, n_done = 0;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_work; i += gridDim.x * blockDim.x) {
-        const uint32_t slot = wl.slot(b.q_shade, i);
-        uint8_t st = b.stage[slot];
-        const uint8_t po = b.post[slot];
-        float4 ro, rd;
-        bool have_ray = false;
-        if (po) {
-            Spec4 L;
-            bool have_L = false;
+    for (;;) {
+        __syncthreads();   // (first trip: the staged primitives; later trips: everyone is done with the previous tile's lists)
+        if (threadIdx.x == 0) { s_tile = atomicAdd(&b.counters[C_CURSOR_TRACE], 1u); s_ndone = 0; }
+        __syncthreads();
+        const uint32_t tile = s_tile * (uint32_t)QZ_FLAT_TILE;
+        if (tile >= n_work) break;
+        const uint32_t tile_n = min((uint32_t)QZ_FLAT_TILE, n_work - tile);
+        // ---- phase 1: shadow tests, collect the finished paths
+        for (uint32_t k = threadIdx.x; k < tile_n; k += blockDim.x) {
+            const uint32_t slot = wl.slot(b.q_shade, tile + k);
+            s_slot[k] = slot;
+            const uint8_t po = b.post[slot];
+            if (!po) continue;
             if (po & QZ_POST_SHADOW) {
                 n_shadow++;
                 const float4 o = b.sh_o.get(slot), d = b.sh_d.get(slot);
                 const V3 O = v3(o.x, o.y, o.z), D = v3(d.x, d.y, d.z);
                 const float rd2 = 1.0f / dot(D, D);   // the ray's share of every sphere test
-                Hit best;
-                best.t = INFINITY; best.u = 0.0f; best.v = 0.0f; best.prim = QZ_NO_HIT; best.key = 0xffffffffu;
-                best.ng = v3(0.0f, 0.0f, 0.0f); best.geom_id = QZ_NO_HIT; best.prim_id = 0;
-                // occluded iff the closest hit has t <= 1 (scene.cpp:136-143)
+                bool occl = false;
 #pragma unroll 1
-                for (uint32_t p = 0; p < n_prims; p++)
-                    flat_prim_test(sc, s_prims[p], p, O, D, rd2, QZ_TNEAR, INFINITY, best);
-                if (!(best.prim != QZ_NO_HIT && best.t <= 1.0f)) {
-                    L = s4(b.radiance.get(slot)) + s4(b.sh_c.get(slot));
-                    have_L = true;
-                    if (!(po & QZ_POST_DONE)) b.radiance.set(slot, f4(L));
-                }
+                for (uint32_t p = 0; p < n_prims && !occl; p++) occl = flat_prim_occludes(s_prims[p], O, D, rd2);
+                if (!occl) b.radiance.set(slot, f4(s4(b.radiance.get(slot)) + s4(b.sh_c.get(slot))));
             }
-            if (po & QZ_POST_DONE) {
-                if (!have_L) L = s4(b.radiance.get(slot));
-                st = finish_and_regenerate(sc, cam, b, pp, slot, L, ro, rd);
-                if (st != ST_EMPTY) { b.stage[slot] = st; have_ray = true; }
-                n_done++;
-            }
+            if (po & QZ_POST_DONE) s_done[atomicAdd(&s_ndone, 1u)] = slot;
             b.post[slot] = 0;
         }
-        if (st == ST_EMPTY) { b.fam[slot] = QZ_FAM_NONE; continue; }
-        if (!have_ray) { ro = b.ray_o.get(slot); rd = b.ray_d.get(slot); }
-        n_closest++;
-        const V3 O = v3(ro.x, ro.y, ro.z), D = v3(rd.x, rd.y, rd.z);
-        const float rd2 = 1.0f / dot(D, D);
-        Hit best;
-        best.t = INFINITY; best.u = 0.0f; best.v = 0.0f; best.prim = QZ_NO_HIT; best.key = 0xffffffffu;
-        best.ng = v3(0.0f, 0.0f, 0.0f); best.geom_id = QZ_NO_HIT; best.prim_id = 0;
-#pragma unroll 1
-        for (uint32_t p = 0; p < n_prims; p++)
-            flat_prim_test(sc, s_prims[p], p, O, D, rd2, QZ_TNEAR, INFINITY, best);
-        b.hit_a.set(slot, f4(best.t, best.u, best.v, __uint_as_float(best.prim_id)));
-        b.hit_b.set(slot, f4(best.ng.x, best.ng.y, best.ng.z, __uint_as_float(best.geom_id)));
-        const bool unsorted = (flags & QZ_FLAG_UNSORTED_SHADING) != 0;
-        int fam = SQ_MISC;
-        if (!unsorted && best.geom_id != QZ_NO_HIT) {
-            const int32_t mat = sc.geoms[best.geom_id].material;
-            if (mat >= 0) {
-                const uint32_t kind = sc.materials[mat].kind;
-                fam = kind == QZ_MAT_DIFFUSE ? SQ_DIFFUSE : (kind == QZ_MAT_CONDUCTOR ? SQ_CONDUCTOR
-                      : ((kind == QZ_MAT_DIELECTRIC || kind == QZ_MAT_THIN_DIELECTRIC) ? SQ_DIELECTRIC : SQ_MISC));
-            }
+        __syncthreads();
+        // ---- phase 2: finished paths -> result cell, next pixel-sample of the pass in the slot
+        const uint32_t nd = s_ndone;
+        for (uint32_t k = threadIdx.x; k < nd; k += blockDim.x) {
+            const uint32_t slot = s_done[k];
+            float4 ro, rd;
+            const uint8_t st = finish_and_regenerate(sc, cam, b, pp, slot, s4(b.radiance.get(slot)), ro, rd);
+            if (st != ST_EMPTY) b.stage[slot] = st;
+            n_done++;
         }
-        b.fam[slot] = (uint8_t)(fam + (st == ST_TRACE_FIRST && !unsorted ? SQ_FAMILIES : 0));
+        __syncthreads();
+        // ---- phase 3: closest hit of every slot of the tile that carries a ray
+        for (uint32_t k = threadIdx.x; k < tile_n; k += blockDim.x) {
+            const uint32_t slot = s_slot[k];
+            const uint8_t st = b.stage[slot];
+            if (st == ST_EMPTY) { b.fam[slot] = QZ_FAM_NONE; continue; }
+            const float4 ro = b.ray_o.get(slot), rd = b.ray_d.get(slot);
+            n_closest++;
+            const V3 O = v3(ro.x, ro.y, ro.z), D = v3(rd.x, rd.y, rd.z);
+            const float rd2 = 1.0f / dot(D, D);
+            Hit best;
+            best.t = INFINITY; best.u = 0.0f; best.v = 0.0f; best.prim = QZ_NO_HIT; best.key = 0xffffffffu;
+            best.ng = v3(0.0f, 0.0f, 0.0f); best.geom_id = QZ_NO_HIT; best.prim_id = 0;
+#pragma unroll 1
+            for (uint32_t p = 0; p < n_prims; p++)
+                flat_prim_test(sc, s_prims[p], p, O, D, rd2, QZ_TNEAR, INFINITY, best);
+            b.hit_a.set(slot, f4(best.t, best.u, best.v, __uint_as_float(best.prim_id)));
+            b.hit_b.set(slot, f4(best.ng.x, best.ng.y, best.ng.z, __uint_as_float(best.geom_id)));
+            const bool unsorted = (flags & QZ_FLAG_UNSORTED_SHADING) != 0;
+            int fam = SQ_MISC;
+            if (!unsorted && best.geom_id != QZ_NO_HIT) {
+                const int32_t mat = sc.geoms[best.geom_id].material;
+                if (mat >= 0) {
+                    const uint32_t kind = sc.materials[mat].kind;
+                    fam = kind == QZ_MAT_DIFFUSE ? SQ_DIFFUSE : (kind == QZ_MAT_CONDUCTOR ? SQ_CONDUCTOR
+                          : ((kind == QZ_MAT_DIELECTRIC || kind == QZ_MAT_THIN_DIELECTRIC) ? SQ_DIELECTRIC : SQ_MISC));
+                }
+            }
+            b.fam[slot] = (uint8_t)(fam + (st == ST_TRACE_FIRST && !unsorted ? SQ_FAMILIES : 0));
+        }
     }
     stat_add(&b.stats[S_RAYS_CLOSEST], n_closest);
     stat_add(&b.stats[S_RAYS_SHADOW], n_shadow);

@@ -131,19 +131,30 @@ __global__ void __launch_bounds__(256) k_sample(DScene sc, WfBuffers b) {
         uint32_t dims[R_COUNT];
         bounce_dims(misc.z & 0xffffu, nee, has_lights, dims);
         const uint32_t roles = queue_roles(q, sc.n_lights);
+        // the roles' values: first from the pass's memo table (all loads in flight together), then the digit loops for
+        // the entries nobody has computed yet -- one copy of the loops in the instruction stream, the role's dimension and
+        // result register are selected
+        float v[R_COUNT];
+        uint32_t missing = 0;
+#pragma unroll
+        for (int k = 0; k < R_COUNT; k++) {
+            v[k] = 0.0f;
+            if ((roles >> k) & 1u) {
+                const uint32_t bits = memo_load(memo_slot(sc.memo, dims[k], misc.y));
+                if (bits != QZ_MEMO_EMPTY) v[k] = __uint_as_float(bits);
+                else missing |= 1u << k;
+            }
+        }
         Sampler smp;
         smp.index = misc.y; smp.dim = 0;
-        float v[R_COUNT];
-#pragma unroll
-        for (int k = 0; k < R_COUNT; k++) v[k] = 0.0f;
-        // one copy of the digit loops in the instruction stream; the role's dimension and result register are selected
 #pragma unroll 1
-        for (uint32_t m = roles; m; m &= m - 1u) {
+        for (uint32_t m = missing; m; m &= m - 1u) {
             const int r = __ffs(m) - 1;
             uint32_t dim = dims[0];
 #pragma unroll
             for (int k = 1; k < R_COUNT; k++) dim = k == r ? dims[k] : dim;
             const float val = sample_dimension(sc.sampler_table, smp, dim);
+            memo_store(memo_slot(sc.memo, dim, misc.y), val);
 #pragma unroll
             for (int k = 0; k < R_COUNT; k++) v[k] = k == r ? val : v[k];
         }

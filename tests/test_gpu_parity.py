@@ -400,8 +400,9 @@ def test_tone_path_against_oracle(qz, oracle, gamma):
     if gamma == 1.0:
         assert bits_equal(got_f, want_f).all() and (got_u8 == want_u8).all()
     else:
-        ok = np.isnan(want_f) & np.isnan(got_f) | (np.abs(got_f - want_f) <= np.spacing(np.abs(want_f)))
-        print(f"tone gamma {gamma}: {(got_f != want_f).mean():.2e} of values differ from glibc powf (by one ulp)")
+        # one ulp of powf, then the rounding of the x255 product: two ulps of the result
+        ok = np.isnan(want_f) & np.isnan(got_f) | (np.abs(got_f - want_f) <= 2 * np.spacing(np.abs(want_f)))
+        print(f"tone gamma {gamma}: {(got_f != want_f).mean():.2e} of values differ from glibc powf (by one ulp of the power)")
         assert ok.all()
         assert (np.abs(got_u8.astype(int) - want_u8.astype(int)) <= 1).all() and (got_u8 != want_u8).mean() < 1e-3
 
@@ -412,6 +413,7 @@ def test_film_stays_on_the_device_for_a_denoiser(qz):
     import ctypes
 
     import torch
+    from cuda.bindings import runtime as cudart
 
     lib = qz.lib
     with qz.build_scene("cornell_box", 48, 40) as sc:
@@ -425,7 +427,8 @@ def test_film_stays_on_the_device_for_a_denoiser(qz):
         planes = []
         for p in ptrs:
             host = np.zeros((40, 48, 3), np.float32)
-            assert torch.cuda.cudart().cudaMemcpy(host.ctypes.data, p.value, n * 12, 2) == 0   # device -> host
+            (err,) = cudart.cudaMemcpy(host.ctypes.data, p.value, n * 12, cudart.cudaMemcpyKind.cudaMemcpyDeviceToHost)
+            assert int(err) == 0
             planes.append(host)
         assert bits_equal(planes[0], out.color).all() and bits_equal(planes[1], out.normal).all() and bits_equal(planes[2], out.albedo).all()
         bgr8 = torch.zeros(n * 3, dtype=torch.uint8, device="cuda")
