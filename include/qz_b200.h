@@ -223,6 +223,15 @@ int qz_device_name(char* buf, size_t n);
  * the previous value.                                                                                     */
 uint32_t qz_set_default_flags(uint32_t flags);
 
+/* Multi-GPU behind render() (the reference fans render() out over host threads, render.cpp:339-382; here over GPUs):
+ * scenes committed by this thread after qz_set_device_count(n), n > 1, are replicated on the n device ordinals starting
+ * at the thread's device (tables uploaded, BVH built on each), and qz_render() then renders interleaved row strips on all
+ * of them, one host thread per device; each device's film kernel writes its rows straight into the first device's film
+ * planes through NVLink peer memory, so there is no separate collective and no host bounce, and the film is
+ * bit-identical to a one-GPU render.  n = 0 (the default) takes the count from the environment variable QZ_DEVICES
+ * (so an unmodified application of the reference's API can be switched over from outside).  Returns the previous value. */
+int qz_set_device_count(int n);
+
 /* Scene::Scene / ~Scene (scene.hpp:44-49) */
 int qz_scene_create(qz_scene* out);
 int qz_scene_destroy(qz_scene scene);
@@ -230,6 +239,11 @@ int qz_scene_destroy(qz_scene scene);
 /* Scene::commit (scene.cpp:22-25): uploads the tables and builds the wide BVH on the GPU
  * (replaces rtcCommitScene).                                                              */
 int qz_scene_commit(qz_scene scene, const qz_scene_tables* tables);
+
+/* Device time of the BVH build of the last qz_scene_commit() on this handle (CUDA events around the build kernels:
+ * primitive boxes, Morton keys, radix sort, LBVH topology + fit, collapse to 8-wide nodes, leaf gather) -- the
+ * counterpart of rtcCommitScene's build, reported as a secondary metric.                        */
+int qz_scene_build_ms(qz_scene scene, float* ms);
 
 /* render() (render.hpp:8-13, render.cpp:321-397) with HOST output buffers: H*W*3 floats
  * each, RGB interleaved, row 0 = top (image.hpp:26-45).  Any of normal/albedo may be NULL. */

@@ -12,10 +12,12 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <chrono>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "launch.h"
@@ -287,7 +289,38 @@ struct qz_scene_t {
     int device = 0;
     DeviceTables tables;
     WorkMem work;
+    float build_ms = 0.0f;   // table upload + BVH build of the last commit
+    // MULTI-GPU behind render(): with QZ_DEVICES = N > 1 the handle owns N - 1 replicas of the committed scene on the
+    // following device ordinals (tables uploaded and BVH built on each); qz_render() then renders interleaved row
+    // strips on all N devices at once, one host thread per device (the reference fans render() out over host threads,
+    // render.cpp:339-382).
+    std::vector<qz_scene_t*> replicas;
 };
+
+namespace {
+thread_local int g_device_count = 0;   // qz_set_device_count(); 0 = take QZ_DEVICES from the environment
+int env_devices() {
+    if (g_device_count > 0) return g_device_count;
+    static const int n = [] { const char* e = std::getenv("QZ_DEVICES"); int v = e ? std::atoi(e) : 1; return v < 1 ? 1 : v; }();
+    return n;
+}
+void destroy_replicas(qz_scene_t* s) {
+    for (qz_scene_t* r : s->replicas) {
+        cudaSetDevice(r->device);
+        CudaExec ex;
+        r->store.release(ex);
+        delete r;
+    }
+    s->replicas.clear();
+    cudaSetDevice(s->device);
+}
+// rows per interleaved strip: the largest height <= 8 that gives every device the same number of rows
+uint32_t balanced_strip_rows(uint32_t height, uint32_t n) {
+    for (uint32_t rows = 8; rows >= 1; rows--)
+        if (height % rows == 0 && (height / rows) % n == 0) return rows;
+    return 1;
+}
+}  // namespace
 
 extern "C" {
 
@@ -335,6 +368,7 @@ int qz_scene_create(qz_scene* out) {
 
 int qz_scene_destroy(qz_scene s) {
     if (!s) return QZ_OK;
+    destroy_replicas(s);
     cudaSetDevice(s->device);
     CudaExec ex;
     s->store.release(ex);
@@ -348,13 +382,65 @@ int qz_scene_commit(qz_scene s, const qz_scene_tables* t) {
     std::string why = SceneStore<CudaExec>::validate(*t);
     if (!why.empty()) return fail(QZ_ERR_INVALID, "invalid scene tables: " + why);
     CudaExec ex;
+    // (the build is bracketed on the host around a synchronised device: uploads of the tables are included, the host-side
+    // flattening is not)
+    cudaDeviceSynchronize();
+    const auto t0 = std::chrono::steady_clock::now();
     bool ok = s->store.commit(ex, *t, s->tables.sampler, s->tables.rho);
     ex.note(cudaDeviceSynchronize());
+    s->build_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
     if (!ok || ex.err != cudaSuccess) {
         s->store.committed = false;
         return fail(ex.err == cudaErrorMemoryAllocation ? QZ_ERR_OOM : QZ_ERR_CUDA,
                     std::string("scene commit failed: ") + cudaGetErrorString(ex.err));
     }
+    // replicas for the in-library multi-GPU render (QZ_DEVICES)
+    destroy_replicas(s);
+    const int n_dev = env_devices();
+    if (n_dev > 1) {
+        int count = 0;
+        QZ_CUDA(cudaGetDeviceCount(&count));
+        if (s->device + n_dev > count)
+            return fail(QZ_ERR_INVALID, "QZ_DEVICES asks for more devices than are visible from device " + std::to_string(s->device));
+        for (int d = 1; d < n_dev; d++) {
+            const int dev = s->device + d;
+            int can = 0;
+            QZ_CUDA(cudaDeviceCanAccessPeer(&can, dev, s->device));
+            if (!can) { destroy_replicas(s); return fail(QZ_ERR_CUDA, "QZ_DEVICES: device " + std::to_string(dev) + " has no peer access to device " + std::to_string(s->device) + " (the film is written over NVLink peer memory)"); }
+            QZ_CUDA(cudaSetDevice(dev));
+            cudaError_t pe = cudaDeviceEnablePeerAccess(s->device, 0);
+            if (pe == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); pe = cudaSuccess; }
+            QZ_CUDA(pe);
+            qz_scene_t* r = new qz_scene_t();
+            r->device = dev;
+            s->replicas.push_back(r);
+            int rc = device_tables(dev, r->tables);
+            if (rc) { destroy_replicas(s); return rc; }
+            CudaExec rex;
+            const bool rok = r->store.commit(rex, *t, r->tables.sampler, r->tables.rho);
+            rex.note(cudaDeviceSynchronize());
+            if (!rok || rex.err != cudaSuccess) {
+                const std::string why_r = cudaGetErrorString(rex.err);
+                destroy_replicas(s);
+                return fail(rex.err == cudaErrorMemoryAllocation ? QZ_ERR_OOM : QZ_ERR_CUDA, "scene commit failed on device " + std::to_string(dev) + ": " + why_r);
+            }
+        }
+        QZ_CUDA(cudaSetDevice(s->device));
+    }
+    return QZ_OK;
+}
+
+int qz_set_device_count(int n) {
+    if (n < 0) return fail(QZ_ERR_INVALID, "negative device count");
+    const int old = g_device_count;
+    g_device_count = n;
+    return old;
+}
+
+int qz_scene_build_ms(qz_scene s, float* ms) {
+    if (!s || !ms) return fail(QZ_ERR_INVALID, "null argument");
+    if (!s->store.committed) return fail(QZ_ERR_NOT_COMMITTED, "Scene must be committed before rendering.");
+    *ms = s->build_ms;
     return QZ_OK;
 }
 
@@ -622,6 +708,10 @@ static int render_impl(qz_scene s, const qz_camera* camera, uint32_t n_samples, 
             sc.memo.n = pp.s_count * spar.stride;
             sc.memo.index0 = s_begin * spar.stride;
             QZ_RENDER_CUDA(cudaMemsetAsync(sc.memo.tab, 0xff, (size_t)memo_dims * sc.memo.n * 4, stream));
+            qzl::memo_fill(sc.sampler_table, &spar, &sc.memo, std::min<uint32_t>(W, QZ_MAX_HALTON_RESOLUTION), std::min<uint32_t>(H, QZ_MAX_HALTON_RESOLUTION),
+                           s_begin, pp.s_count, n_sm * 8, stream);
+            st.kernel_launches++;
+            QZ_RENDER_CUDA(cudaGetLastError());
         }
 
         // initial fill: pipeline p starts with the next `first[p]` path ids; the shared cursor continues behind them
@@ -769,8 +859,51 @@ int qz_render(qz_scene s, const qz_camera* camera, uint32_t n_samples, uint32_t 
             if (host[k]) QZ_CUDA(cudaMemcpy(dev[k]->p, host[k], n * 4, cudaMemcpyHostToDevice));
     }
     wm.film_valid[0] = wm.film_valid[1] = wm.film_valid[2] = false;
-    int rc = render_impl(s, camera, n_samples, max_bounces, region, options, dc.as<float>(), normal ? dn.as<float>() : nullptr,
+    int rc = QZ_OK;
+    if (!s->replicas.empty() && !sharded) {
+        // MULTI-GPU: device d renders the strips (row / strip_rows) % N == d, all samples of its pixels, and its film
+        // kernel writes the finished rows STRAIGHT INTO THIS DEVICE'S FILM PLANES through NVLink peer memory -- the
+        // film accumulation and the gather are one kernel, there is no separate collective and no host bounce.  Every
+        // pixel is owned by exactly one device and keeps its sample order: the film is bit-identical to a 1-GPU render.
+        const uint32_t n_dev = 1u + (uint32_t)s->replicas.size();
+        const uint32_t strip = balanced_strip_rows(camera->image_height, n_dev);
+        std::vector<int> rcs(n_dev, QZ_OK);
+        std::vector<std::string> errs(n_dev);
+        std::vector<qz_stats> sts(n_dev);
+        const uint32_t caller_flags = g_default_flags;
+        float* const pc = dc.as<float>();
+        float* const pn = normal ? dn.as<float>() : nullptr;
+        float* const pa = albedo ? da.as<float>() : nullptr;
+        auto work = [&](uint32_t d) {
+            qz_scene_t* sd = d == 0 ? s : s->replicas[d - 1];
+            qz_region reg{strip, n_dev, d};
+            if (cudaSetDevice(sd->device) != cudaSuccess) { rcs[d] = QZ_ERR_CUDA; errs[d] = "cudaSetDevice failed"; return; }
+            g_default_flags = caller_flags;
+            rcs[d] = render_impl(sd, camera, n_samples, max_bounces, &reg, options, pc, pn, pa, nullptr, &sts[d]);
+            if (rcs[d] != QZ_OK) errs[d] = g_error;
+        };
+        std::vector<std::thread> threads;
+        for (uint32_t d = 1; d < n_dev; d++) threads.emplace_back(work, d);
+        work(0);
+        for (auto& th : threads) th.join();
+        QZ_CUDA(cudaSetDevice(s->device));
+        for (uint32_t d = 0; d < n_dev; d++)
+            if (rcs[d] != QZ_OK) return fail(rcs[d], "device " + std::to_string(d) + ": " + errs[d]);
+        if (stats) {
+            qz_stats total = sts[0];
+            for (uint32_t d = 1; d < n_dev; d++) {
+                total.paths += sts[d].paths; total.rays_closest += sts[d].rays_closest; total.rays_shadow += sts[d].rays_shadow;
+                total.shade_calls += sts[d].shade_calls; total.kernel_launches += sts[d].kernel_launches;
+                total.node_visits += sts[d].node_visits; total.prim_tests += sts[d].prim_tests;
+                total.iterations = std::max(total.iterations, sts[d].iterations);
+                total.ms_total = std::max(total.ms_total, sts[d].ms_total);
+            }
+            *stats = total;
+        }
+    } else {
+        rc = render_impl(s, camera, n_samples, max_bounces, region, options, dc.as<float>(), normal ? dn.as<float>() : nullptr,
                          albedo ? da.as<float>() : nullptr, nullptr, stats);
+    }
     if (rc != QZ_OK) return rc;
     wm.film_valid[0] = true; wm.film_valid[1] = normal != nullptr; wm.film_valid[2] = albedo != nullptr;
     wm.film_w = camera->image_width; wm.film_h = camera->image_height;

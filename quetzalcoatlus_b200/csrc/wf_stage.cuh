@@ -164,6 +164,30 @@ __global__ void __launch_bounds__(256) k_sample(DScene sc, WfBuffers b) {
     }
 }
 
+// Fills the pass's sample memo (sampler.cuh) ahead of the wavefront: every row (dimension), every sample number of the
+// pass, every (x mod 128, y mod 128) class of the image.  A warp works on 32 neighbouring classes of ONE dimension and
+// sample number -- same base, same digit count, no divergence but the permutation's rejection loop -- and each value is
+// computed once instead of once per pixel that shares the index (39 pixels at 800 x 800).  Filled lazily by the
+// paths themselves, the 39 first users of an entry all ran in the same wavefront iteration and nearly every warp of
+// the sampler stage dragged a few missing lanes through the digit loops (profiles/r02_summary.md).
+__global__ void __launch_bounds__(256) k_memo_fill(const SamplerDim* __restrict__ table, SamplerParams spar, SampleMemo memo, uint32_t cls_w,
+                                                    uint32_t cls_h, uint32_t s_begin, uint32_t s_count) {
+    const uint32_t ncls = cls_w * cls_h;
+    const uint64_t per_dim = (uint64_t)s_count * ncls;
+    const uint64_t total = per_dim * memo.dims;
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t dim = (uint32_t)(t / per_dim);
+        const uint32_t rem = (uint32_t)(t - (uint64_t)dim * per_dim);
+        const uint32_t s = rem / ncls, cls = rem - s * ncls;
+        const Sampler smp = sampler_start(spar, cls % cls_w, cls / cls_w, s_begin + s);
+        float v;
+        if (dim == 0) v = radical_inv(2, smp.index >> spar.exp0);
+        else if (dim == 1) v = radical_inv(3, smp.index / spar.scale1);
+        else v = sample_dimension(table, smp, dim);
+        memo_store(memo_slot(memo, dim, smp.index), v);
+    }
+}
+
 // Ordered accumulation of one pass into the running per-pixel sums; on the last pass divide
 // by the sample count and write the three film planes (render.cpp:264-294).
 __global__ void __launch_bounds__(256) k_film(WfBuffers b, PassParams pp, float* acc /* 9 floats per owned pixel */,

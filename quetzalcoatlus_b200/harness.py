@@ -259,6 +259,16 @@ class Harness:
 
         return scope()
 
+    def build_times(self) -> dict:
+        """Scene-build times (ms) of the last build_scene on this thread: OBJ text parse, the whole Scene::commit()
+        (flatten + upload + BVH build) and the device part of it (product harness only)."""
+        fn = getattr(self.lib, self.prefix + "build_times", None)
+        if fn is None:
+            return {}
+        a, b, c = ctypes.c_double(), ctypes.c_double(), ctypes.c_double()
+        fn(ctypes.byref(a), ctypes.byref(b), ctypes.byref(c))
+        return {"obj_parse_ms": a.value, "commit_ms": b.value, "bvh_build_ms": c.value}
+
     def impl(self) -> str:
         return self._fn("impl")().decode()
 

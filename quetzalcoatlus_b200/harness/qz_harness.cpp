@@ -34,6 +34,7 @@ void* qzh_scene_build(const char* name, int width, int height, const char* obj_p
     if (obj_material && *obj_material) o.obj_material = obj_material;
     if (obj_light && *obj_light) o.obj_light = obj_light;
     try {
+        qzhost::reset_build_times();
         auto b = qzscenes::build(name, o);
         if (b && !b->scene->ready()) return nullptr;  // commit failed (e.g. no CUDA device)
         return b.release();
@@ -68,6 +69,14 @@ int qzh_render(void* h, int spp, int max_bounces, float* color, float* normal, f
     if (normal) std::memcpy(normal, r.normal_buffer.data(), n * sizeof(float));
     if (albedo) std::memcpy(albedo, r.albedo_buffer.data(), n * sizeof(float));
     return 0;
+}
+
+// scene-build times of this thread since the last qzh_scene_build (host/render.hpp: BuildTimes)
+void qzh_build_times(double* obj_parse_ms, double* commit_ms, double* bvh_build_ms) {
+    const qzhost::BuildTimes& t = qzhost::build_times();
+    if (obj_parse_ms) *obj_parse_ms = t.obj_parse_ms;
+    if (commit_ms) *commit_ms = t.commit_ms;
+    if (bvh_build_ms) *bvh_build_ms = t.bvh_build_ms;
 }
 
 // stats of the last qzh_render on this thread (the struct of include/qz_b200.h)

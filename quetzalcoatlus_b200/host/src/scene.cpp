@@ -9,6 +9,7 @@
 //   set_bg_light; :22-25 commit; render.cpp:321-397 render().
 #include "../scene.hpp"
 
+#include <chrono>
 #include <cstdlib>
 #include <cstring>
 
@@ -114,8 +115,16 @@ GeometryData* Scene::add_sphere(const Pt3& center, float radius, const Material*
     return g;
 }
 
+namespace qzhost {
+static thread_local BuildTimes g_build_times{};
+const BuildTimes& build_times() { return g_build_times; }
+void reset_build_times() { g_build_times = BuildTimes(); }
+}  // namespace qzhost
+
 GeometryData* Scene::add_obj(const std::string& filename, const Material* material, const Transform& transform) {
+    const auto parse_t0 = std::chrono::steady_clock::now();
     auto obj_data = obj::load_obj(filename);
+    qzhost::g_build_times.obj_parse_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - parse_t0).count();
     if (!obj_data) {
         std::cerr << "Failed to load " << filename << std::endl;
         return nullptr;
@@ -215,6 +224,7 @@ void Scene::commit() {
         std::cerr << "error: scene has no CUDA device (initialize_device failed)" << std::endl;
         return;
     }
+    const auto commit_t0 = std::chrono::steady_clock::now();
     qzhost::Flattener f;
     std::unordered_map<const Light*, int32_t> light_ids;
     for (const auto& l : m_lights) light_ids[l.get()] = l->flatten(f);
@@ -276,6 +286,9 @@ void Scene::commit() {
         std::cerr << "error: " << qz_last_error() << std::endl;
         return;
     }
+    qzhost::g_build_times.commit_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - commit_t0).count();
+    float bvh_ms = 0.0f;
+    if (qz_scene_build_ms(m_handle, &bvh_ms) == QZ_OK) qzhost::g_build_times.bvh_build_ms = bvh_ms;
     m_ready = true;
 }
 

@@ -201,6 +201,8 @@ int qz_math_probe(int op, uint32_t n, const float* in, float* out) {
     return QZ_OK;
 }
 
+int qz_set_device_count(int) { return 0; }
+int qz_scene_build_ms(qz_scene, float* ms) { if (ms) *ms = 0.0f; return QZ_OK; }
 int qz_film_device(qz_scene, float**, float**, float**, uint32_t*, uint32_t*) { g_error = "host emulation: no device film"; return QZ_ERR_NO_DEVICE; }
 int qz_tone_device(const float*, uint32_t, float, float*, uint8_t*, void*) { g_error = "host emulation: no device"; return QZ_ERR_NO_DEVICE; }
 int qz_tone(const float* rgb, uint32_t n_pixels, float gamma, float* bgr255, uint8_t* bgr8) {

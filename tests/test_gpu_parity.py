@@ -438,6 +438,29 @@ def test_film_stays_on_the_device_for_a_denoiser(qz):
         assert (bgr8.cpu().numpy().reshape(40, 48, 3) == want).all()
 
 
+def test_in_library_multi_gpu_render_is_bit_identical(qz):
+    """Multi-GPU behind render() (qz_set_device_count / QZ_DEVICES): the scene is replicated, every device renders its
+    interleaved strips and writes them into device 0's film over peer memory; the film must equal the one-GPU film bit
+    for bit, for a flat scene and for a BVH scene.  Needs two visible GPUs (gpurun --gpus 2)."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    n = min(torch.cuda.device_count(), 4)
+    for name, w, h in [("cornell_box", 96, 80), ("mandelbrot", 64, 48)]:
+        with qz.build_scene(name, w, h) as sc:
+            want = sc.render(spp=4, max_bounces=8)
+        qz.lib.qz_set_device_count(n)
+        try:
+            with qz.build_scene(name, w, h) as sc:
+                got = sc.render(spp=4, max_bounces=8)
+                stats = sc.last_stats()
+        finally:
+            qz.lib.qz_set_device_count(0)
+        assert stats["paths"] == w * h * 4
+        assert bits_equal(got.color, want.color).all() and bits_equal(got.normal, want.normal).all() and bits_equal(got.albedo, want.albedo).all()
+
+
 def test_error_conventions(qz):
     import ctypes
 
