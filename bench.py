@@ -14,9 +14,17 @@ elsewhere).
 
 `value`  whole-job Mpaths/s, scene and film resident in HBM, device-timed (CUDA events,
          max over ranks).
-`e2e`    the same metric through the reference-facing call render(camera, scene, spp, bounces)
-         with HOST RenderResult buffers: per step the camera/sensor tables go host->device
-         and the three film planes come back device->host inside the timed region.
+`e2e`    the same metric through the reference-facing call: at N = 1 the host library's
+         render(camera, scene, spp, bounces) itself (harness entry qzh_render), which returns
+         a RenderResult of pageable std::vectors -- per step the camera / sensor tables go
+         host->device and the three film planes come back device->host, staged through the
+         library's pinned area (`e2e.pinned_value`: the same through the C ABI with caller-pinned
+         buffers).  At N > 1 each rank renders its strips into its device film, ONE NCCL reduce
+         assembles them on rank 0's device and rank 0 copies the film to pinned host memory.
+`secondary` (N = 1) the two BVH workloads -- obj_viewer on the synthetic 1M-triangle mesh and
+         mandelbrot (2.87M triangles) -- a few steps each, with the traversal stage's roofline
+         (algorithmic GB/s against the HBM peak, measured L2 and DRAM bytes, issue-slot share)
+         and the scene-build times (OBJ parse, commit, GPU BVH build).
 `roofline`     the dominant kernel stage against the measured HBM peak (MEASURED_PEAKS.json).
 `cpu_baseline` the oracle (reference sources over the Embree shim -- NOT real Embree, which is
                absent) timed on this box's host cores on a bounded sample of the same workload.
@@ -112,16 +120,21 @@ def build_scene(harness, workload: str, width: int, height: int, mesh_tris: int)
     return harness.build_scene(scene, width, height)
 
 
+def oracle_library(workload: str) -> Path:
+    """oracle/_ref: the reference's sources over the Embree shim.  The obj_viewer workload uses the variant whose ONLY
+    difference is the OBJ text parser (oracle/Makefile, liboracle_ref_fastobj.so): everything that is timed is the reference's."""
+    name = "liboracle_ref_fastobj.so" if WORKLOADS[workload][0] == "obj_viewer" else "liboracle_ref.so"
+    return ROOT / "oracle" / "_ref" / name
+
+
 def cpu_baseline(workload: str, width: int, height: int, max_bounces: int, mesh_tris: int, budget_s: float = 15.0) -> dict:
     """The oracle on this box's host cores, bounded sample: full resolution, reduced spp."""
     from quetzalcoatlus_b200.harness import Harness
 
-    lib = ROOT / "oracle" / "_ref" / "liboracle_ref.so"
+    lib = oracle_library(workload)
     if not lib.exists():
         return {"value": None, "unit": "Mpaths/s", "cores": 0, "kind": "reference", "sample": "oracle/_ref not built"}
     orc = Harness(lib, "orc_")
-    if WORKLOADS[workload][0] == "obj_viewer":
-        mesh_tris = min(mesh_tris, 20_000)  # the reference's regex OBJ loader needs ~0.8 ms per line
     with build_scene(orc, workload, width, height, mesh_tris) as sc:
         probe = sc.render(1, max_bounces)
         spp = int(max(1, min(WORKLOADS[workload][3], budget_s / max(probe.seconds, 1e-3))))
@@ -131,7 +144,8 @@ def cpu_baseline(workload: str, width: int, height: int, max_bounces: int, mesh_
             "mrays_per_s": r.rays / r.seconds / 1e6,
             "sample": f"{workload} {width}x{height}, {spp} spp of the workload's samples, {max_bounces} bounces, "
                       f"{r.seconds:.2f} s; reference integrator over the oracle's Embree shim (not real Embree)"
-                      + (f"; mesh reduced to {mesh_tris} triangles" if WORKLOADS[workload][0] == "obj_viewer" else "")}
+                      + (f"; the same {mesh_tris}-triangle OBJ text, parsed by the product's loader (oracle/Makefile: the reference's "
+                         "regex loader needs ~25 min for it)" if WORKLOADS[workload][0] == "obj_viewer" else "")}
 
 
 def run_reference(args) -> None:
@@ -143,13 +157,12 @@ def run_reference(args) -> None:
     width, height = args.width or w0, args.height or h0
     from quetzalcoatlus_b200.harness import Harness
 
-    lib = ROOT / "oracle" / "_ref" / "liboracle_ref.so"
+    lib = oracle_library(args.workload)
     if not lib.exists():
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/liboracle_ref.so is not built"}))
+        print(json.dumps({"impl": "reference", "unavailable": f"{lib.relative_to(ROOT)} is not built"}))
         return
     orc = Harness(lib, "orc_")
-    mesh_tris = min(args.mesh_triangles, 20_000)
-    with build_scene(orc, args.workload, width, height, mesh_tris) as sc:
+    with build_scene(orc, args.workload, width, height, args.mesh_triangles) as sc:
         probe = sc.render(1, mb)
         # each step = a bounded sample of the workload: as many of its spp as fit ~8 s
         spp = int(max(1, min(spp0 * args.gpus, 8.0 / max(probe.seconds, 1e-3))))
@@ -176,6 +189,64 @@ def run_reference(args) -> None:
     }))
 
 
+def load_counters() -> dict:
+    """ncu counters per unit of work (profiles/r02_counters.json, written by tools/ncu_counters.py from the committed
+    steady-state captures): DRAM bytes, L2 bytes and executed warp instructions per ray / per shaded bounce, per scene."""
+    p = ROOT / "profiles" / "r02_counters.json"
+    return json.loads(p.read_text()) if p.exists() else {}
+
+
+def stage_report(inst: dict, scene_name: str, flags: int, sm_mhz: float | None) -> tuple[dict, dict]:
+    """Roofline of the dominant stage from one instrumented step pair (traversal counters + per-stage events)."""
+    n_rays = inst["rays_closest"] + inst["rays_shadow"]
+    n_node = inst["node_visits"] / max(n_rays, 1)
+    n_prim = inst["prim_tests"] / max(n_rays, 1)
+    # SURVEY.md 8.d: B_ray = N_node*128 + N_prim*64 + 32 (ray read) + 32 (hit write; 4 for shadow rays)
+    bytes_trav = inst["node_visits"] * 128 + inst["prim_tests"] * 64 + inst["rays_closest"] * 64 + inst["rays_shadow"] * 36
+    # scenes of <= 96 primitives are intersected by the flat kernel (primitive records staged in shared memory
+    # once per CTA, no BVH): per ray only the ray read and the result write are memory traffic
+    n_prims_scene = (inst["bvh_bytes"] - inst["bvh_nodes"] * 128) // 64
+    flat_scene = 0 < n_prims_scene <= 96 and not (flags & 8)
+    if flat_scene:
+        bytes_trav = inst["rays_closest"] * 64 + inst["rays_shadow"] * 36
+    # per shaded bounce: the path record is read and written once (288 B); a bounce's draws are one 32-byte sector of
+    # the path's memo row (late bounces: 32 B written by the sampler stage and read back)
+    bytes_shade = inst["shade_calls"] * (288 + 32) + inst["rays_shadow"] * 48
+    bytes_sample = inst["shade_calls"] * 64
+    stages = {"traversal": (inst["ms_closest"] + inst["ms_shadow"], bytes_trav, n_rays),
+              "shading": (inst["ms_shade"], bytes_shade, inst["shade_calls"]),
+              "sampler": (inst["ms_sample"], bytes_sample, inst["shade_calls"])}
+    dom = max(stages, key=lambda k: stages[k][0])
+    d_ms, d_bytes, d_units = stages[dom]
+    peak, how = measured_peaks()
+    achieved = d_bytes / (d_ms * 1e-3) / 1e9 if d_ms > 0 else 0.0
+    cnt = load_counters().get(scene_name, {}).get(dom)
+    traffic = l2_gbs = issue = None
+    if cnt:
+        traffic = cnt["dram_bytes_per_unit"] * d_units
+        l2_gbs = cnt["l2_bytes_per_unit"] * d_units / (d_ms * 1e-3) / 1e9 if d_ms > 0 else None
+        clock = (sm_mhz or 1965.0) * 1e6
+        issue_peak = 148 * 4 * clock                        # warp instructions per second: 148 SMs x 4 schedulers
+        wips = cnt["warp_inst_per_unit"] * d_units / (d_ms * 1e-3) if d_ms > 0 else 0.0
+        issue = {"warp_inst_per_s": wips, "peak": issue_peak, "frac": wips / issue_peak,
+                 "active_lanes": cnt.get("threads_per_inst"), "source": "profiles/r02_counters.json x this step's counts"}
+    kernel_names = {"traversal": "traversal (k_step_flat)" if flat_scene else "traversal (k_trace_lane<closest> + <any hit>)",
+                    "shading": "shading (k_shade<family> + k_albedo_conductor)", "sampler": "sampler (k_sample)"}
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "algorithmic_bytes": d_bytes, "kernel": kernel_names[dom], "peak_source": how,
+                "l2_gbs": l2_gbs, "dram_over_algorithmic": (traffic / d_bytes) if traffic else None, "issue": issue,
+                "stage_ms": {**{k: v[0] for k, v in stages.items()}, "finish + regenerate + bin": inst["ms_other"], "step": inst["ms_total"]},
+                "note": "algorithmic bytes per step (SURVEY.md 8.d) over the stage's device time in a serial (one-pipeline, "
+                        "event-per-stage) step of this run; traffic / l2 / issue = ncu counters per unit of the committed "
+                        "steady-state capture x this step's counts.  The analytic scenes' stages are bound by instruction "
+                        "issue and latency, not HBM: `issue` is the roof that applies there (DESIGN.md section 6)"}
+    extra = {"flat_intersection": flat_scene, "n_node_per_ray": n_node, "n_prim_per_ray": n_prim,
+             "bounces_per_path": inst["shade_calls"] / max(inst["paths"], 1),
+             "shadow_ray_fraction": inst["rays_shadow"] / max(n_rays, 1), "bvh_nodes": inst["bvh_nodes"],
+             "whole_pipeline_algorithmic_gbs": (bytes_trav + bytes_shade + bytes_sample) / (inst["ms_total"] * 1e-3) / 1e9}
+    return roofline, extra
+
+
 def run_ours(args) -> None:
     import torch
     import torch.distributed as dist
@@ -197,165 +268,164 @@ def run_ours(args) -> None:
 
     qz = load_harness()
     lib = qz.lib
-    _, w0, h0, spp0, mb = WORKLOADS[args.workload]
-    width, height = args.width or w0, args.height or h0
-    spp = (args.spp or spp0) * world
-    sc = build_scene(qz, args.workload, width, height, args.mesh_triangles)
-    handle, cam = ctypes.c_void_p(sc.c_scene_handle()), sc.c_camera()
-    STRIP_ROWS = strip_rows_for(height, world)
-    region = QzRegion(STRIP_ROWS, world, rank)
-    film = torch.zeros((3, height, width, 3), dtype=torch.float32, device="cuda")  # colour, normal, albedo planes
+    lib.qz_last_error.restype = ctypes.c_char_p
     stream = torch.cuda.current_stream()
-
-    def step(flags: int = 0) -> dict:
-        """One render into the device-resident film + (N > 1) the single NCCL reduce."""
-        if world > 1:
-            film.zero_()
-        st = QzStats()
-        opts = QzRenderOptions(flags | args.flags, args.pool, 0, 0)
-        rc = lib.qz_render_device(handle, ctypes.byref(cam), spp, mb, ctypes.byref(region), ctypes.byref(opts),
-                                  ctypes.c_void_p(film[0].data_ptr()), ctypes.c_void_p(film[1].data_ptr()),
-                                  ctypes.c_void_p(film[2].data_ptr()), ctypes.c_void_p(stream.cuda_stream), ctypes.byref(st))
-        if rc != 0:
-            lib.qz_last_error.restype = ctypes.c_char_p
-            raise RuntimeError(f"qz_render_device failed: {lib.qz_last_error().decode()}")
-        if world > 1:
-            dist.reduce(film, dst=0, op=dist.ReduceOp.SUM)
-        return st.as_dict()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step()
-    barrier()
-    clocks = ClockSampler(local_rank)
-    clocks.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    stats = [step() for _ in range(args.steps)]
-    e1.record(stream)
-    barrier()
-    clock_info = clocks.stop()
-    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_total = float(ms.item())
-    launches = sum(s["kernel_launches"] for s in stats)
-    rays = torch.tensor([float(sum(s["rays_closest"] + s["rays_shadow"] for s in stats)),
-                         float(sum(s["shade_calls"] for s in stats)), float(launches)], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(rays, op=dist.ReduceOp.SUM)
-    total_paths = width * height * spp * args.steps
-    value = total_paths / (ms_total * 1e-3) / 1e6
+    def measure(workload: str, spp_per_gpu: int, steps: int, warmup: int, with_e2e: bool) -> dict:
+        """Device-timed steps (+ end-to-end steps) of one workload, and the instrumented step pair for its roofline."""
+        _, w0, h0, spp0, mb = WORKLOADS[workload]
+        width, height = (args.width or w0, args.height or h0) if workload == args.workload else (w0, h0)
+        spp = (spp_per_gpu or spp0) * world
+        sc = build_scene(qz, workload, width, height, args.mesh_triangles)
+        build = qz.build_times()
+        handle, cam = ctypes.c_void_p(sc.c_scene_handle()), sc.c_camera()
+        strip_rows = strip_rows_for(height, world)
+        region = QzRegion(strip_rows, world, rank)
+        film = torch.zeros((3, height, width, 3), dtype=torch.float32, device="cuda")  # colour, normal, albedo planes
 
-    # ---- end to end through render() with HOST buffers (the reference-facing call): per step the camera /
-    # sensor tables go host->device and the three film planes come back device->host into page-locked
-    # RenderResult buffers that the caller keeps across frames
-    host_film = torch.zeros((3, height, width, 3), dtype=torch.float32).pin_memory()
-    host_ptrs = [ctypes.c_void_p(host_film[k].data_ptr()) for k in range(3)]
+        def step(flags: int = 0) -> dict:
+            """One render into the device-resident film + (N > 1) the single NCCL reduce."""
+            if world > 1:
+                film.zero_()
+            st = QzStats()
+            opts = QzRenderOptions(flags | args.flags, args.pool, 0, 0)
+            rc = lib.qz_render_device(handle, ctypes.byref(cam), spp, mb, ctypes.byref(region), ctypes.byref(opts),
+                                      ctypes.c_void_p(film[0].data_ptr()), ctypes.c_void_p(film[1].data_ptr()),
+                                      ctypes.c_void_p(film[2].data_ptr()), ctypes.c_void_p(stream.cuda_stream), ctypes.byref(st))
+            if rc != 0:
+                raise RuntimeError(f"qz_render_device failed: {lib.qz_last_error().decode()}")
+            if world > 1:
+                dist.reduce(film, dst=0, op=dist.ReduceOp.SUM)
+            return st.as_dict()
 
-    def e2e_step():
-        st = QzStats()
-        opts = QzRenderOptions(args.flags, args.pool, 0, 0)
+        for _ in range(warmup):
+            step()
+        barrier()
+        clocks = ClockSampler(local_rank)
+        clocks.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        stats = [step() for _ in range(steps)]
+        e1.record(stream)
+        barrier()
+        clock_info = clocks.stop()
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
         if world > 1:
-            host_film.zero_()
-        rc = lib.qz_render(handle, ctypes.byref(cam), spp, mb, ctypes.byref(region), ctypes.byref(opts),
-                           host_ptrs[0], host_ptrs[1], host_ptrs[2], ctypes.byref(st))
-        assert rc == 0
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        ms_total = float(ms.item())
+        sums = torch.tensor([float(sum(s["rays_closest"] + s["rays_shadow"] for s in stats)),
+                             float(sum(s["kernel_launches"] for s in stats))], device="cuda", dtype=torch.float64)
         if world > 1:
-            t = host_film.cuda(non_blocking=True)
-            dist.reduce(t, dst=0, op=dist.ReduceOp.SUM)
-            host_film.copy_(t)
-        return float(host_film[0, 0, 0, 0])   # the result is read on the host
+            dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+        out = {"workload": workload, "scene": WORKLOADS[workload][0], "width": width, "height": height, "spp": spp, "max_bounces": mb,
+               "strip_rows": strip_rows, "ms_per_step": ms_total / steps, "value": width * height * spp * steps / (ms_total * 1e-3) / 1e6,
+               "mrays_per_s": float(sums[0].item()) / (ms_total * 1e-3) / 1e6, "gpu_launches": int(sums[1].item()),
+               "clocks": clock_info, "build": build}
 
-    for _ in range(2):
-        e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    e2e_steps = max(1, args.steps)
-    for _ in range(e2e_steps):
-        e2e_step()
-    barrier()
-    e2e_s = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_value = width * height * spp * e2e_steps / float(e2e_s.item()) / 1e6
-    film_bytes = 3 * height * width * 3 * 4
-    h2d = 3 * 471 * 4 + height * 4 + (film_bytes if world > 1 else 0)
+        if with_e2e:
+            film_bytes = 3 * height * width * 3 * 4
+            host_film = torch.zeros((3, height, width, 3), dtype=torch.float32).pin_memory()
+            host_ptrs = [ctypes.c_void_p(host_film[k].data_ptr()) for k in range(3)]
 
-    # ---- roofline of the dominant stage: one instrumented step (stage events + traversal counters), rank 0, untimed
-    roofline, extra = None, {}
-    # every rank runs the instrumented steps (they contain the collective); rank 0 reports its own stages
-    inst = step(QZ_FLAG_COUNT_TRAVERSAL)   # traversal counters (BVH kernels)
-    timing = step(QZ_FLAG_STAGE_TIMING)    # per-stage device time of the real kernels
-    if rank == 0:
+            def e2e_render():
+                """N = 1: the host library's render() itself, returning a RenderResult of pageable std::vectors."""
+                return sc.render_only(spp, mb)
+
+            def e2e_pinned():
+                st = QzStats()
+                opts = QzRenderOptions(args.flags, args.pool, 0, 0)
+                rc = lib.qz_render(handle, ctypes.byref(cam), spp, mb, None, ctypes.byref(opts), host_ptrs[0], host_ptrs[1], host_ptrs[2], ctypes.byref(st))
+                assert rc == 0, lib.qz_last_error().decode()
+                return float(host_film[0, 0, 0, 0])
+
+            def e2e_sharded():
+                """N > 1: strips into the device film, one NCCL reduce on the devices, rank 0 reads the film on the host."""
+                step()
+                if rank == 0:
+                    host_film.copy_(film, non_blocking=True)
+                    torch.cuda.synchronize()
+                return float(host_film[0, 0, 0, 0])
+
+            def time_fn(fn, n):
+                for _ in range(2):
+                    fn()
+                barrier()
+                t0 = time.perf_counter()
+                for _ in range(n):
+                    fn()
+                barrier()
+                dt = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+                if world > 1:
+                    dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+                return width * height * spp * n / float(dt.item()) / 1e6
+
+            n_e2e = max(1, steps)
+            if world == 1:
+                # (flags / pool overrides only reach the C-ABI call: render() has no options argument)
+                value_e2e = time_fn(e2e_render, n_e2e)
+                pinned = time_fn(e2e_pinned, n_e2e)
+                out["e2e"] = {"value": value_e2e, "unit": "Mpaths/s", "h2d_bytes_per_step": 3 * 471 * 4 + height * 4,
+                              "d2h_bytes_per_step": film_bytes, "call": "render(camera, scene, spp, bounces) -> RenderResult (pageable std::vector planes)",
+                              "pinned_value": pinned, "pinned_call": "qz_render() with caller-pinned buffers"}
+            else:
+                value_e2e = time_fn(e2e_sharded, n_e2e)
+                out["e2e"] = {"value": value_e2e, "unit": "Mpaths/s", "h2d_bytes_per_step": (3 * 471 * 4 + height * 4) * world,
+                              "d2h_bytes_per_step": film_bytes, "call": "qz_render_device() per rank + one NCCL reduce on the devices + rank 0 device->host"}
+
+        # ---- roofline of the dominant stage: one instrumented step pair (traversal counters, stage events), untimed;
+        # every rank runs them (they contain the collective); rank 0 reports its own stages
+        inst = step(QZ_FLAG_COUNT_TRAVERSAL)
+        timing = step(QZ_FLAG_STAGE_TIMING)
         for k in ("ms_closest", "ms_shadow", "ms_shade", "ms_other", "ms_total", "ms_sample"):
             inst[k] = timing[k]
-        n_rays = inst["rays_closest"] + inst["rays_shadow"]
-        n_node = inst["node_visits"] / max(n_rays, 1)
-        n_prim = inst["prim_tests"] / max(n_rays, 1)
-        # SURVEY.md 8.d: B_ray = N_node*128 + N_prim*64 + 32 (ray read) + 32 (hit write; 4 for shadow rays)
-        bytes_trav = inst["node_visits"] * 128 + inst["prim_tests"] * 64 + inst["rays_closest"] * 64 + inst["rays_shadow"] * 36
-        # scenes of <= 96 primitives are intersected by the flat kernels (primitive records staged in shared memory
-        # once per CTA, no BVH): per ray only the ray read and the result write are memory traffic
-        n_prims_scene = (inst["bvh_bytes"] - inst["bvh_nodes"] * 128) // 64
-        flat_scene = 0 < n_prims_scene <= 96 and not (args.flags & 8)
-        if flat_scene:
-            bytes_trav = inst["rays_closest"] * 64 + inst["rays_shadow"] * 36
-        # per shaded bounce: the path record is read and written once (288 B) and the sampler stage adds 32 B each way
-        bytes_shade = inst["shade_calls"] * 288 + inst["rays_shadow"] * 48
-        bytes_sample = inst["shade_calls"] * 64
-        stages = {"traversal (k_closest_* + k_shadow_*)": (inst["ms_closest"] + inst["ms_shadow"], bytes_trav),
-                  "shading (k_shade<family, first>)": (inst["ms_shade"], bytes_shade),
-                  "sampler (k_sample)": (inst["ms_sample"], bytes_sample)}
-        dom = max(stages, key=lambda k: stages[k][0])
-        d_ms, d_bytes = stages[dom]
-        peak, how = measured_peaks()
-        achieved = d_bytes / (d_ms * 1e-3) / 1e9 if d_ms > 0 else 0.0
-        # DRAM bytes the stage really moved, per step: ncu dram__bytes_read+write per ray / per shaded bounce of a whole
-        # (smaller) render of the same scene (profiles/r01_traffic.json, tools/profile_step.py) x this step's counts
-        traffic = None
-        tj = ROOT / "profiles" / "r01_traffic.json"
-        scene_name = WORKLOADS[args.workload][0]
-        if tj.exists() and scene_name in json.loads(tj.read_text()):
-            t = json.loads(tj.read_text())[scene_name]
-            per = {"traversal (k_closest_* + k_shadow_*)": t["traversal"]["dram_bytes_per_ray"] * n_rays,
-                   "shading (k_shade<family, first>)": t["shading"]["dram_bytes_per_shade_call"] * inst["shade_calls"],
-                   "sampler (k_sample)": t["sampler"]["dram_bytes_per_shade_call"] * inst["shade_calls"]}
-            traffic = per[dom]
-        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                    "algorithmic_bytes": d_bytes, "kernel": dom, "peak_source": how,
-                    "stage_ms": {**{k: v[0] for k, v in stages.items()}, "finish + regenerate + bin": inst["ms_other"], "step": inst["ms_total"]},
-                    "note": "algorithmic bytes per step (SURVEY.md 8.d) over the stage's device time in a serial (one-pipeline, "
-                            "event-per-stage) step of this run; traffic = measured DRAM bytes per step of that stage (ncu); the "
-                            "shading and sampler stages are bound by dependent-instruction latency and integer issue, not by HBM "
-                            "(DESIGN.md section 6)"}
-        extra = {"flat_intersection": flat_scene, "n_node_per_ray": n_node, "n_prim_per_ray": n_prim, "bounces_per_path": inst["shade_calls"] / max(inst["paths"], 1),
-                 "shadow_ray_fraction": inst["rays_shadow"] / max(n_rays, 1), "bvh_nodes": inst["bvh_nodes"],
-                 "whole_pipeline_algorithmic_gbs": (bytes_trav + bytes_shade + bytes_sample) / (inst["ms_total"] * 1e-3) / 1e9}
+        roofline, extra = stage_report(inst, WORKLOADS[workload][0], args.flags, clock_info.get("sm_mhz"))
+        out["roofline"], out["extra"] = roofline, extra
+        sc.close()
+        del film
+        torch.cuda.empty_cache()
+        return out
+
+    head = measure(args.workload, args.spp, args.steps, args.warmup, with_e2e=True)
+
+    secondary = None
+    if world == 1 and not args.no_secondary:
+        secondary = {}
+        for wl in ("obj_viewer", "mandelbrot"):
+            if wl == args.workload:
+                continue
+            m = measure(wl, 0, 3, 3, with_e2e=False)
+            secondary[wl] = {"value": m["value"], "unit": "Mpaths/s", "mrays_per_s": m["mrays_per_s"], "ms_per_step": m["ms_per_step"], "steps": 3, "warmup": 3,
+                             "config": {k: m[k] for k in ("scene", "width", "height", "spp", "max_bounces")},
+                             "roofline": m["roofline"], **m["extra"],
+                             "obj_parse_ms": m["build"].get("obj_parse_ms"), "scene_commit_ms": m["build"].get("commit_ms"),
+                             "bvh_build_ms": m["build"].get("bvh_build_ms")}
+            if wl == "obj_viewer":
+                secondary[wl]["config"]["mesh_triangles"] = args.mesh_triangles
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_baseline(args.workload, width, height, mb, args.mesh_triangles)
+        cpu = cpu_baseline(args.workload, head["width"], head["height"], head["max_bounces"], args.mesh_triangles)
 
     if rank == 0:
         print(json.dumps({
-            "metric": "Mpaths/s", "value": value, "unit": "Mpaths/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "metric": "Mpaths/s", "value": head["value"], "unit": "Mpaths/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "scene": WORKLOADS[args.workload][0], "width": width, "height": height,
-                       "spp": spp, "spp_per_gpu": spp // world, "max_bounces": mb,
-                       "parallelism": f"interleaved {STRIP_ROWS}-row strips over {world} GPU(s), one NCCL sum-reduce of the film",
-                       "l2": "per-step working set (path pool + result cells, > 3 GB) exceeds L2"},
-            "mrays_per_s": float(rays[0].item()) / (ms_total * 1e-3) / 1e6,
-            "gpu_launches": int(rays[2].item()),
-            "e2e": {"value": e2e_value, "unit": "Mpaths/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": film_bytes},
-            "roofline": roofline, "cpu_baseline": cpu, "clocks": clock_info, **extra,
+            "config": {"workload": args.workload, "scene": head["scene"], "width": head["width"], "height": head["height"],
+                       "spp": head["spp"], "spp_per_gpu": head["spp"] // world, "max_bounces": head["max_bounces"],
+                       "parallelism": f"interleaved {head['strip_rows']}-row strips over {world} GPU(s), one NCCL sum-reduce of the film",
+                       "l2": "per-step working set (path pool + result cells + sample memo, > 4 GB) exceeds L2"},
+            "mrays_per_s": head["mrays_per_s"],
+            "gpu_launches": head["gpu_launches"],
+            "e2e": head["e2e"], "roofline": head["roofline"], "cpu_baseline": cpu, "clocks": head["clocks"],
+            "bvh_build_ms": head["build"].get("bvh_build_ms"), "obj_parse_ms": head["build"].get("obj_parse_ms"),
+            "secondary": secondary, **head["extra"],
         }))
-    sc.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -374,6 +444,7 @@ def main() -> None:
     ap.add_argument("--flags", type=int, default=0, help="extra QZ_FLAG_* bits for the timed steps (1 unsorted shading, 8 force BVH)")
     ap.add_argument("--mesh-triangles", type=int, default=1_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the obj_viewer / mandelbrot lines under `secondary`")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -17,6 +17,10 @@ void generate(const Stage& s, uint32_t first_id, uint32_t n) {
     QZL_UNPACK
     k_generate<<<s.lean_blocks, 256, 0, s.stream>>>(sc, *static_cast<const DCamera*>(s.cam), b, *static_cast<const PassParams*>(s.pass), first_id, n);
 }
+void memo_spectra(const Stage& s, const void* sampler_params, uint32_t cls_w, uint32_t cls_h, uint32_t s_begin, uint32_t s_count) {
+    QZL_UNPACK
+    k_memo_spectra<<<s.lean_blocks, 256, 0, s.stream>>>(sc, *static_cast<const SamplerParams*>(sampler_params), cls_w, cls_h, s_begin, s_count);
+}
 void albedo(const Stage& s) {
     QZL_UNPACK
     k_albedo_conductor<<<s.lean_blocks * 2, 256, 0, s.stream>>>(sc, b, s.max_bounces);

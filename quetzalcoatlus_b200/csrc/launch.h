@@ -35,6 +35,7 @@ void tone(const float* rgb, uint32_t n_pixels, float gamma, float* bgr255, uint8
 // one set per arithmetic mode
 #define QZL_MODE_API                                                                                          \
     void generate(const Stage& s, uint32_t first_id, uint32_t n);                                           \
+    void memo_spectra(const Stage& s, const void* sampler_params, uint32_t cls_w, uint32_t cls_h, uint32_t s_begin, uint32_t s_count); \
     void albedo(const Stage& s);                                                                            \
     void shade(const Stage& s, int family /* 0 misc, 1 diffuse, 2 conductor, 3 dielectric */);              \
     void finish(const Stage& s);                                                                            \

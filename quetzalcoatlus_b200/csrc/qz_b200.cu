@@ -450,7 +450,7 @@ static int render_impl(qz_scene s, const qz_camera* camera, uint32_t n_samples, 
                        cudaStream_t stream, qz_stats* stats_out) {
     // the kernels receive a per-call copy of the scene view: it carries the pass's sample memo (sampler.cuh)
     DScene sc = s->store.view;
-    sc.memo = SampleMemo{nullptr, 0, 0, 0};
+    sc.memo = SampleMemo{};
     const uint32_t W = camera->image_width, H = camera->image_height;
     if (!W || !H || !n_samples) return fail(QZ_ERR_INVALID, "empty image or zero samples");
     if (max_bounces > 65535) return fail(QZ_ERR_INVALID, "max_bounces > 65535 is not supported (the path depth is a 16-bit field)");
@@ -530,17 +530,20 @@ static int render_impl(qz_scene s, const qz_camera* camera, uint32_t n_samples, 
     // several times more pixels than there are (x mod 128, y mod 128) classes.  Rows: the jitter, the wavelength draw
     // and eight bounces' worth of dimensions (later bounces evaluate directly), within a 2 GB budget.
     static const int env_memo = [] { const char* e = std::getenv("QZ_MEMO"); return e ? std::atoi(e) : 1; }();
-    uint32_t memo_dims = 0;
+    uint32_t memo_dims = 0, memo_stride = 0, memo_dim_off = 0;
     const uint64_t memo_n = (uint64_t)s_pass * spar.stride;
     {
         const uint64_t classes = (uint64_t)std::min<uint32_t>(W, QZ_MAX_HALTON_RESOLUTION) * std::min<uint32_t>(H, QZ_MAX_HALTON_RESOLUTION);
         if (env_memo && n_pix64 >= 4 * classes && memo_n < (1ull << 31)) {
-            const uint64_t fit = (2ull << 30) / (memo_n * 4);
-            memo_dims = (uint32_t)std::min<uint64_t>(3 + 8 * 8, fit);
+            memo_dim_off = ((4u * QZ_MEMO_MAX_HOT + 7u) & ~7u) + 5u;          // hot spectra block, then dimension 3 on a sector boundary
+            const uint64_t fit = (3ull << 30) / (memo_n * 4);               // words per row within the budget
+            memo_dims = 3 + 8 * 8;
+            while (memo_dims >= 3 + 8 && ((memo_dim_off + memo_dims + 7u) & ~7u) > fit) memo_dims -= 8;
             if (memo_dims < 3 + 8) memo_dims = 0;
+            memo_stride = (memo_dim_off + memo_dims + 7u) & ~7u;
         }
     }
-    if (memo_dims) QZ_CUDA(wm.memo.reserve((size_t)memo_dims * memo_n * 4));
+    if (memo_dims) QZ_CUDA(wm.memo.reserve((size_t)memo_stride * memo_n * 4));
     const bool multi_pass = s_pass < n_samples;
     if (multi_pass) QZ_CUDA(acc.reserve((size_t)n_pix * 9 * 4));
     QZ_CUDA(cudaMemcpyAsync(rowsb.p, rows.data(), rows.size() * 4, cudaMemcpyHostToDevice, stream));
@@ -707,10 +710,26 @@ static int render_impl(qz_scene s, const qz_camera* camera, uint32_t n_samples, 
             sc.memo.dims = memo_dims;
             sc.memo.n = pp.s_count * spar.stride;
             sc.memo.index0 = s_begin * spar.stride;
-            QZ_RENDER_CUDA(cudaMemsetAsync(sc.memo.tab, 0xff, (size_t)memo_dims * sc.memo.n * 4, stream));
+            sc.memo.stride = memo_stride;
+            sc.memo.dim_off = memo_dim_off;
+            sc.memo.n_hot = 0;   // (set after the fill: k_memo_spectra itself must evaluate, not look up)
+            QZ_RENDER_CUDA(cudaMemsetAsync(sc.memo.tab, 0xff, (size_t)memo_stride * sc.memo.n * 4, stream));
             qzl::memo_fill(sc.sampler_table, &spar, &sc.memo, std::min<uint32_t>(W, QZ_MAX_HALTON_RESOLUTION), std::min<uint32_t>(H, QZ_MAX_HALTON_RESOLUTION),
                            s_begin, pp.s_count, n_sm * 8, stream);
             st.kernel_launches++;
+            const uint32_t n_hot = (uint32_t)s->store.hot_spectra.size();
+            if (n_hot) {
+                for (uint32_t k = 0; k < n_hot; k++) sc.memo.hot_id[k] = s->store.hot_spectra[k];
+                DScene sc_fill = sc;
+                sc_fill.memo.n_hot = n_hot;   // the kernel reads the list; from_spectrum() never consults the memo
+                qzl::Stage fs = stg[0];
+                fs.scene = &sc_fill;
+                fs.stream = stream;
+                const uint32_t cw = std::min<uint32_t>(W, QZ_MAX_HALTON_RESOLUTION), ch = std::min<uint32_t>(H, QZ_MAX_HALTON_RESOLUTION);
+                exact ? qzl::exact::memo_spectra(fs, &spar, cw, ch, s_begin, pp.s_count) : qzl::fast::memo_spectra(fs, &spar, cw, ch, s_begin, pp.s_count);
+                st.kernel_launches++;
+                sc.memo.n_hot = n_hot;
+            }
             QZ_RENDER_CUDA(cudaGetLastError());
         }
 

@@ -199,28 +199,44 @@ QZ_HD float sample_dimension(const SamplerDim* __restrict__ table, const Sampler
 
 // SAMPLE MEMO.  The value of a dimension depends on nothing but (dimension, Halton index), and the index depends on
 // the pixel only through (x mod 128, y mod 128) (sampler_start): in an 800 x 800 image 39 pixels share every index of
-// a sample number, in a 4K image 506.  The wavefront therefore keeps, per render pass, a table value[dim][index -
-// index0] over the pass's index range (32-bit float patterns, all-ones = not yet computed; a valid value is < 1):
-// the first path that needs an entry runs the digit loops and stores the result, every later one loads it.  Entries
-// only ever change from "empty" to the one value the reference's arithmetic gives, so races are harmless and the
-// samples are the reference's bit for bit.  Rows 0 and 1 hold the two pixel-jitter radical inverses.  tab == nullptr
+// a sample number, in a 4K image 506.  The wavefront therefore keeps, per render pass, one ROW per Halton index of the
+// pass -- filled ahead of the wavefront by k_memo_fill, one evaluation per (index, dimension) instead of one per pixel
+// and bounce -- and the shading kernels read a bounce's draws straight from the path's row:
+//   words [0, 4 * n_hot)      "hot" spectra (the lights' emission, the conductors' eta and k) at the four wavelengths
+//                             of the index -- they too depend on nothing but the index (the wavelengths come from
+//                             dimension 2) -- 16 bytes per spectrum (wf_shade.cuh: k_memo_spectra);
+//   word  dim_off + d         the value of dimension d as a float pattern, d < dims (d = 0, 1: the pixel jitter's two
+//                             radical inverses).  dim_off = 5 mod 8, so that dimension 3 -- where the first bounce's
+//                             eight draws start -- begins a 32-byte sector: a bounce's draws are one sector.
+// All-ones = not computed (a valid value is < 1): kept as a lazy fallback; entries only ever change from "empty" to the
+// one value the reference's arithmetic gives, so the samples are the reference's bit for bit.  tab == nullptr
 // (per-path replay, host emulation, small images without reuse) evaluates directly.
 #define QZ_MEMO_EMPTY 0xffffffffu
+#define QZ_MEMO_MAX_HOT 8
 struct SampleMemo {
     uint32_t* tab;
-    uint32_t dims;     // rows
-    uint32_t n;        // entries per row
-    uint32_t index0;   // first Halton index of the pass
+    uint32_t dims;      // dimensions per row
+    uint32_t n;         // rows (Halton indices of the pass)
+    uint32_t index0;    // first Halton index of the pass
+    uint32_t stride;    // words per row (multiple of 8)
+    uint32_t dim_off;   // word of dimension 0
+    uint32_t n_hot;     // hot spectra per row
+    int32_t hot_id[QZ_MEMO_MAX_HOT];   // their spectrum ids
 };
-QZ_HD uint32_t* memo_slot(const SampleMemo& m, uint32_t dim, uint32_t index) {
-    if (!m.tab || dim >= m.dims) return nullptr;
+QZ_HD uint32_t* memo_row(const SampleMemo& m, uint32_t index) {
+    if (!m.tab) return nullptr;
     const uint32_t i = index - m.index0;
     if (i >= m.n) return nullptr;
-    return m.tab + (size_t)dim * m.n + i;
+    return m.tab + (size_t)i * m.stride;
+}
+QZ_HD uint32_t* memo_slot(const SampleMemo& m, uint32_t dim, uint32_t index) {
+    uint32_t* row = memo_row(m, index);
+    if (!row || dim >= m.dims) return nullptr;
+    return row + m.dim_off + dim;
 }
 QZ_HD uint32_t memo_load(const uint32_t* p) {
 #if defined(__CUDA_ARCH__)
-    return p ? __ldcg(p) : QZ_MEMO_EMPTY;   // L2: the table is shared by all SMs and written while it is read
+    return p ? __ldcg(p) : QZ_MEMO_EMPTY;   // L2: the table is shared by all SMs
 #else
     return p ? *p : QZ_MEMO_EMPTY;
 #endif
@@ -231,6 +247,13 @@ QZ_HD void memo_store(uint32_t* p, float v) {
 #else
     if (p) *p = float_as_u32(v);
 #endif
+}
+// slot of a spectrum in the rows' hot block, or -1
+QZ_HD int memo_hot_slot(const SampleMemo& m, int32_t spectrum_id) {
+    int slot = -1;
+    for (int k = 0; k < QZ_MEMO_MAX_HOT; k++)
+        if (k < (int)m.n_hot && m.hot_id[k] == spectrum_id) slot = k;
+    return slot;
 }
 QZ_HD float sample_dimension_memo(const SamplerDim* __restrict__ table, const SampleMemo& m, uint32_t index, uint32_t dim) {
     uint32_t* p = memo_slot(m, dim, index);

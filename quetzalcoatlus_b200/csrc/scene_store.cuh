@@ -18,6 +18,7 @@ struct SceneStore {
     BvhBuildResult bvh{};
     bool committed = false;
     std::vector<void*> owned;
+    std::vector<int32_t> hot_spectra;   // spectra the shading code evaluates per bounce at the path's wavelengths (sampler.cuh, SAMPLE MEMO)
 
     template <class T>
     const T* put(Exec& ex, const T* src, size_t n) {
@@ -141,6 +142,16 @@ struct SceneStore {
             sp.aux = (int32_t)accel.size();
             accel.insert(accel.end(), table, table + QZ_PW_BUCKETS);
         }
+        // lights' emission first, then the conductors' eta and k
+        hot_spectra.clear();
+        auto add_hot = [&](int32_t id) {
+            if (id < 0 || hot_spectra.size() >= QZ_MEMO_MAX_HOT) return;
+            for (int32_t h : hot_spectra) if (h == id) return;
+            hot_spectra.push_back(id);
+        };
+        for (uint32_t i = 0; i < t.n_lights; i++) add_hot(t.lights[i].spectrum);
+        for (uint32_t i = 0; i < t.n_materials; i++)
+            if (t.materials[i].kind == QZ_MAT_CONDUCTOR) { add_hot(t.materials[i].a); add_hot(t.materials[i].b); }
         view.spectra = put(ex, spectra.data(), spectra.size());
         view.pw_accel = put(ex, accel.data(), accel.size());
         view.textures = put(ex, t.textures, t.n_textures);

@@ -57,6 +57,23 @@ QZ_HD V2 sphere_uv(V3 n) {
     return v2(u, v);
 }
 
+// from_spectrum at the PATH's wavelengths for a spectrum that may be "hot" (sampler.cuh, SAMPLE MEMO: the lights'
+// emission, the conductors' eta and k): the four values depend on the Halton index only and sit in the path's memo
+// row, computed once per index by k_memo_spectra with this very function -- the same bits as evaluating here.
+QZ_HD Spec4 from_spectrum_path(const DScene& sc, uint32_t index, int32_t id, const Spec4& lambda) {
+#if defined(__CUDA_ARCH__)
+    if (sc.memo.n_hot) {
+        const int slot = memo_hot_slot(sc.memo, id);
+        const uint32_t* row = memo_row(sc.memo, index);
+        if (slot >= 0 && row) {
+            const float4 v = __ldcg(reinterpret_cast<const float4*>(row) + slot);
+            return spec4(v.x, v.y, v.z, v.w);
+        }
+    }
+#endif
+    return from_spectrum(sc, id, lambda);
+}
+
 // Texture::value (texture.cpp)
 QZ_HD Spec4 texture_value(const DScene& sc, int32_t tex_id, V2 uv, const Spec4& lambda) {
     const qz_texture t = sc.textures[tex_id];
@@ -126,7 +143,7 @@ QZ_HD SurfacePoint make_surface_point(const DScene& sc, const Ray& ray, const Hi
 
 // Material::bsdf for a resolved (non-mixed) material; may terminate secondary wavelengths
 template <int KH>
-QZ_HD Bsdf make_bsdf(const DScene& sc, int32_t mat, SurfacePoint& sp, const Spec4& lambda, Spec4& pdf) {
+QZ_HD Bsdf make_bsdf(const DScene& sc, int32_t mat, SurfacePoint& sp, const Spec4& lambda, Spec4& pdf, uint32_t index) {
     const qz_material m = sc.materials[mat];
     Bsdf f;
     f.a = spec4(0.0f); f.b = spec4(0.0f); f.rough.ax = 0.0f; f.rough.ay = 0.0f; f.ior = 1.0f;
@@ -139,8 +156,8 @@ QZ_HD Bsdf make_bsdf(const DScene& sc, int32_t mat, SurfacePoint& sp, const Spec
         f.a = texture_value(sc, m.a, sp.uv, lambda);
     } else if (KH == KH_CONDUCTOR || (KH == KH_ANY && m.kind == QZ_MAT_CONDUCTOR)) {
         f.kind = BX_CONDUCTOR;
-        f.a = from_spectrum(sc, m.a, lambda);
-        f.b = from_spectrum(sc, m.b, lambda);
+        f.a = from_spectrum_path(sc, index, m.a, lambda);
+        f.b = from_spectrum_path(sc, index, m.b, lambda);
         f.rough.ax = m.alpha_x; f.rough.ay = m.alpha_y;
     } else {
         f.kind = m.kind == QZ_MAT_DIELECTRIC ? BX_DIELECTRIC : BX_THIN;
@@ -151,9 +168,9 @@ QZ_HD Bsdf make_bsdf(const DScene& sc, int32_t mat, SurfacePoint& sp, const Spec
 }
 
 // Light emission towards w from a point with normal n (light.cpp:48-53)
-QZ_HD Spec4 light_emission(const DScene& sc, const qz_light& l, V3 n, V3 w, const Spec4& lambda) {
+QZ_HD Spec4 light_emission(const DScene& sc, const qz_light& l, V3 n, V3 w, const Spec4& lambda, uint32_t index) {
     if (!l.two_sided && dot(n, w) < 0.0f) return spec4(0.0f);
-    return from_spectrum(sc, l.spectrum, lambda) * l.scale;
+    return from_spectrum_path(sc, index, l.spectrum, lambda) * l.scale;
 }
 
 // ------------------------------------------------------------------ where a bounce's samples come from
@@ -183,6 +200,13 @@ struct SamplesPrecomputed {
     QZ_HD float one(int role, uint32_t) const { return v[role]; }
     QZ_HD V2 two(int role, uint32_t) const { return v2(v[role], v[role + 1]); }
 };
+
+// A bounce that starts at dimension d0 draws at most nine dimensions (bounce_dims below: nine in a scene without
+// lights).  When all of them lie in the path's memo row (sampler.cuh) the shading kernel reads them there and the
+// sampler stage skips the bounce; later bounces go through k_sample and the record as before.
+QZ_HD bool bounce_in_memo(const SampleMemo& m, uint32_t index, uint32_t d0) {
+    return m.tab && d0 + 9u <= m.dims && index - m.index0 < m.n;
+}
 
 // dimensions of every role of a bounce that starts at dimension d0 (same skip calls as shade_bounce)
 QZ_HD void bounce_dims(uint32_t d0, bool nee, bool has_lights, uint32_t dims[R_COUNT]) {
@@ -234,7 +258,7 @@ QZ_HD void sample_lights(const DScene& sc, const SurfacePoint& sp, const Bsdf& f
     if (l.kind == QZ_LIGHT_POINT) {
         V3 dv = lp - sp.point;
         wi = r_normalized(dv);
-        spec = from_spectrum(sc, l.spectrum, lambda) * r_div(l.scale, norm_squared(dv));
+        spec = from_spectrum_path(sc, smp.index, l.spectrum, lambda) * r_div(l.scale, norm_squared(dv));
         pdf = 1.0f;
         p_light = lp;
     } else {
@@ -250,7 +274,7 @@ QZ_HD void sample_lights(const DScene& sc, const SurfacePoint& sp, const Bsdf& f
         V3 dv = p_light - sp.point;
         if (pdf == 0.0f || norm_squared(dv) == 0.0f) return;
         wi = r_normalized(dv);
-        spec = light_emission(sc, l, n, -wi, lambda);
+        spec = light_emission(sc, l, n, -wi, lambda, smp.index);
         if (is_zero(spec)) return;
     }
     if (is_zero(spec) || pdf == 0.0f) return;
@@ -292,7 +316,7 @@ QZ_HD bool shade_bounce(const DScene& sc, PathState& ps, PathAov& aov, const Hit
 
     if (sp.light >= 0) {
         const qz_light l = sc.lights[sp.light];
-        Spec4 emitted = light_emission(sc, l, sp.normal, -ps.ray.d, ps.lambda);
+        Spec4 emitted = light_emission(sc, l, sp.normal, -ps.ray.d, ps.lambda, ps.smp.index);
         if (!is_zero(emitted)) {
             has_gain = true;
             if (first || (ps.flags & QZ_FLAG_SPECULAR_BOUNCE)) {
@@ -318,7 +342,7 @@ QZ_HD bool shade_bounce(const DScene& sc, PathState& ps, PathAov& aov, const Hit
     float mat_sample = 0.0f;
     if (KH == KH_ANY && sc.materials[sp.material].kind == QZ_MAT_MIXED) mat_sample = src.one(R_MAT, mat_dim);
     const int32_t mat = KH == KH_ANY ? resolve_material(sc, sp.material, mat_sample) : sp.material;
-    Bsdf f = make_bsdf<KH>(sc, mat, sp, ps.lambda, ps.pdf);
+    Bsdf f = make_bsdf<KH>(sc, mat, sp, ps.lambda, ps.pdf, ps.smp.index);
 
     // the wavefront's conductor kernel leaves the estimate to k_albedo_conductor (wf_shade.cuh)
     if (first && !(KH == KH_CONDUCTOR && ALBEDO_STAGE)) aov.albedo = bsdf_rho_hd<KH>(sc, f, sp.wo);

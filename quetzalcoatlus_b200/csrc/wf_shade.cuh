@@ -92,7 +92,13 @@ __global__ void __launch_bounds__(256) k_albedo_conductor(DScene sc, WfBuffers b
             mat = sc.materials[sp.material];
             const int j = i & 7;
             const float lam = j & 2 ? (j & 1 ? lambda.v[3] : lambda.v[2]) : (j & 1 ? lambda.v[1] : lambda.v[0]);
-            coeff = eval_spectrum_rec<true>(sc, load_spectrum(sc, j < 4 ? mat.a : mat.b), lam);
+            {
+                const int32_t sid = j < 4 ? mat.a : mat.b;
+                const int hot = sc.memo.n_hot ? memo_hot_slot(sc.memo, sid) : -1;
+                const uint32_t* row = hot >= 0 ? memo_row(sc.memo, b.misc.get(slot).y) : nullptr;
+                if (row) coeff = __uint_as_float(__ldcg(row + 4 * hot + (j & 3)));
+                else coeff = eval_spectrum_rec<true>(sc, load_spectrum(sc, sid), lam);
+            }
         }
         Bsdf f;
         f.kind = BX_CONDUCTOR; f.ior = 1.0f;
@@ -120,6 +126,27 @@ __global__ void __launch_bounds__(256) k_albedo_conductor(DScene sc, WfBuffers b
             if (ok) acc = acc + v;
         }
         if (live && i == 0) b.aov_a.set(slot, f4(acc / 16.0f));
+    }
+}
+
+// Fills the hot-spectra block of the memo rows (sampler.cuh): one thread per (sample number, pixel class) derives the
+// row's wavelengths from its dimension-2 value (already filled by k_memo_fill) exactly as start_path does and evaluates
+// every hot spectrum with from_spectrum -- the function the shading code would otherwise call per bounce.
+__global__ void __launch_bounds__(256) k_memo_spectra(DScene sc, SamplerParams spar, uint32_t cls_w, uint32_t cls_h, uint32_t s_begin, uint32_t s_count) {
+    const uint32_t ncls = cls_w * cls_h;
+    const uint64_t total = (uint64_t)s_count * ncls;
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t s = (uint32_t)(t / ncls), cls = (uint32_t)(t - (uint64_t)s * ncls);
+        const Sampler smp = sampler_start(spar, cls % cls_w, cls / cls_w, s_begin + s);
+        uint32_t* row = memo_row(sc.memo, smp.index);
+        if (!row) continue;
+        const float ul = __uint_as_float(__ldcg(row + sc.memo.dim_off + 2));
+        Spec4 lambda, pdf;
+        sample_wavelengths(ul, lambda, pdf);
+        for (uint32_t k = 0; k < sc.memo.n_hot; k++) {
+            const Spec4 v = from_spectrum(sc, sc.memo.hot_id[k], lambda);
+            __stcg(reinterpret_cast<float4*>(row) + k, f4(v));
+        }
     }
 }
 
@@ -191,11 +218,36 @@ k_shade(DScene sc, WfBuffers b, uint32_t max_bounces) {
             src.tab = sc.sampler_table; src.index = ps.smp.index; src.memo = sc.memo;
             alive = shade_bounce<KH, -1, true>(sc, ps, aov, hit, max_bounces, sh, src, gain, has_gain);
         } else {
-            const float4* sv = b.samples.at(slot);
-            const float4 s0 = __ldcg(sv), s1 = __ldcg(sv + 1);
             SamplesPrecomputed src;
-            src.v[0] = s0.x; src.v[1] = s0.y; src.v[2] = s0.z; src.v[3] = s0.w;
-            src.v[4] = s1.x; src.v[5] = s1.y; src.v[6] = s1.z; src.v[7] = s1.w;
+            const uint32_t d0 = m.z & 0xffffu;
+            if (bounce_in_memo(sc.memo, m.y, d0)) {
+                // this bounce's draws sit in the path's memo row (sampler.cuh), one 32-byte sector: no sampler stage
+                bool nee = KH == KH_DIFFUSE;
+                if (KH == KH_CONDUCTOR) {
+                    const qz_material mat = sc.materials[sc.geoms[hit.geom_id].material];
+                    nee = !(mat.alpha_x < 1e-3f && mat.alpha_y < 1e-3f);
+                }
+                uint32_t dims[R_COUNT];
+                bounce_dims(d0, nee, sc.n_lights != 0, dims);
+                const uint32_t* row = memo_row(sc.memo, m.y) + sc.memo.dim_off;
+#pragma unroll
+                for (int k = 0; k < R_COUNT; k++) src.v[k] = 0.0f;
+                if (KH == KH_DIELECTRIC) {
+                    src.v[R_U1] = __uint_as_float(__ldcg(row + dims[R_U1]));
+                } else {
+                    if (sc.n_lights > 1) src.v[R_PICK] = __uint_as_float(__ldcg(row + dims[R_PICK]));
+                    src.v[R_LIGHT] = __uint_as_float(__ldcg(row + dims[R_LIGHT]));
+                    src.v[R_LIGHT + 1] = __uint_as_float(__ldcg(row + dims[R_LIGHT + 1]));
+                    src.v[R_BSDF] = __uint_as_float(__ldcg(row + dims[R_BSDF]));
+                    src.v[R_BSDF + 1] = __uint_as_float(__ldcg(row + dims[R_BSDF + 1]));
+                }
+                src.v[R_RR] = __uint_as_float(__ldcg(row + dims[R_RR]));
+            } else {
+                const float4* sv = b.samples.at(slot);
+                const float4 s0 = __ldcg(sv), s1 = __ldcg(sv + 1);
+                src.v[0] = s0.x; src.v[1] = s0.y; src.v[2] = s0.z; src.v[3] = s0.w;
+                src.v[4] = s1.x; src.v[5] = s1.y; src.v[6] = s1.z; src.v[7] = s1.w;
+            }
             alive = shade_bounce<KH, -1, true>(sc, ps, aov, hit, max_bounces, sh, src, gain, has_gain);
         }
         if (has_gain) b.radiance.set(slot, f4(s4(b.radiance.get(slot)) + gain));
@@ -386,11 +438,25 @@ __global__ void __launch_bounds__(128, 4) k_step_flat(DScene sc, DCamera cam, Wf
         }
         __syncthreads();
         // ---- phase 3: closest hit of every slot of the tile that carries a ray
+        // (the next entry's tag and ray are loaded before this entry's primitive loop: the loop hides their latency)
+        uint32_t slot_n = 0;
+        uint8_t st_n = ST_EMPTY;
+        float4 ro_n = f4(0.0f, 0.0f, 0.0f, 0.0f), rd_n = ro_n;
+        if (threadIdx.x < tile_n) {
+            slot_n = s_slot[threadIdx.x];
+            st_n = b.stage[slot_n];
+            ro_n = b.ray_o.get(slot_n); rd_n = b.ray_d.get(slot_n);
+        }
         for (uint32_t k = threadIdx.x; k < tile_n; k += blockDim.x) {
-            const uint32_t slot = s_slot[k];
-            const uint8_t st = b.stage[slot];
+            const uint32_t slot = slot_n;
+            const uint8_t st = st_n;
+            const float4 ro = ro_n, rd = rd_n;
+            if (k + blockDim.x < tile_n) {
+                slot_n = s_slot[k + blockDim.x];
+                st_n = b.stage[slot_n];
+                ro_n = b.ray_o.get(slot_n); rd_n = b.ray_d.get(slot_n);
+            }
             if (st == ST_EMPTY) { b.fam[slot] = QZ_FAM_NONE; continue; }
-            const float4 ro = b.ray_o.get(slot), rd = b.ray_d.get(slot);
             n_closest++;
             const V3 O = v3(ro.x, ro.y, ro.z), D = v3(rd.x, rd.y, rd.z);
             const float rd2 = 1.0f / dot(D, D);

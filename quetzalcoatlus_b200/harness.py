@@ -143,6 +143,14 @@ class Scene:
             raise RuntimeError(f"{self._h.prefix}render failed with code {rc}")
         return RenderOutput(color, normal, albedo, sec.value, rays.value, nthr.value)
 
+    def render_only(self, spp: int, max_bounces: int) -> float:
+        """render() with the RenderResult kept on the C++ side (product harness): returns one value of the colour plane."""
+        sec, v = ctypes.c_double(), ctypes.c_float()
+        rc = self._h._fn("render_only")(self._handle, spp, max_bounces, ctypes.byref(sec), ctypes.byref(v))
+        if rc != 0:
+            raise RuntimeError(f"{self._h.prefix}render_only failed with code {rc}")
+        return v.value
+
     def trace_paths(self, xys, spp: int | None = None, max_bounces: int | None = None) -> np.ndarray:
         """Replay pixel-samples (x, y, s) -- y is the sampler/camera y (= H-1-row) -- and return
         one 32-float record per path (layout in include/qz_b200.h: qz_trace_paths)."""

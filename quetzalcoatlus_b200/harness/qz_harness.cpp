@@ -71,6 +71,19 @@ int qzh_render(void* h, int spp, int max_bounces, float* color, float* normal, f
     return 0;
 }
 
+// render() exactly as an application of the reference's API calls it: the RenderResult stays on the C++ side (one value
+// of it is read back), so the time is render()'s own -- table uploads, kernels, the three planes device->host into the
+// RenderResult's pageable vectors -- without this harness's copy into caller buffers (bench.py: e2e)
+int qzh_render_only(void* h, int spp, int max_bounces, double* seconds, float* first_value) {
+    auto* b = static_cast<qzscenes::Bundle*>(h);
+    auto t0 = std::chrono::steady_clock::now();
+    RenderResult r = render(*b->camera, *b->scene, size_t(spp), size_t(max_bounces));
+    auto t1 = std::chrono::steady_clock::now();
+    if (seconds) *seconds = std::chrono::duration<double>(t1 - t0).count();
+    if (first_value) *first_value = r.color_buffer.empty() ? 0.0f : r.color_buffer[0];
+    return r.color_buffer.empty() ? 1 : 0;
+}
+
 // scene-build times of this thread since the last qzh_scene_build (host/render.hpp: BuildTimes)
 void qzh_build_times(double* obj_parse_ms, double* commit_ms, double* bvh_build_ms) {
     const qzhost::BuildTimes& t = qzhost::build_times();
