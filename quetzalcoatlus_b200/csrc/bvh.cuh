@@ -27,7 +27,7 @@
 //   super-root, so they cannot bloat every ancestor box on their path.
 //
 // TRAVERSAL: one ray per thread, near-to-far with a per-thread stack; the kernels in
-// wavefront.cu wrap it in a persistent, warp-scheduled loop with warp-vote refill.  The
+// csrc/wf_trace.cuh wrap it in a persistent, warp-scheduled loop with warp-vote refill.  The
 // answer equals brute force over all primitives under the (t, key) order: boxes are
 // conservative, entry distances equal to the current best are still visited.
 #pragma once

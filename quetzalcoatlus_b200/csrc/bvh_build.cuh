@@ -88,6 +88,7 @@ bool build_wide_bvh(Exec& ex, const F4* d_src_prims, uint32_t n, BvhBuildResult&
         return true;
     }
 
+    ex.mark("(start)");
     // ---- 1: boxes, scene bounds
     Aabb* d_box = ex.template alloc<Aabb>(n);
     int* d_bounds = ex.template alloc<int>(12);  // [0..5] all-primitive bounds, [6..11] small-centroid bounds
@@ -126,6 +127,7 @@ bool build_wide_bvh(Exec& ex, const F4* d_src_prims, uint32_t n, BvhBuildResult&
         });
     }
 
+    ex.mark("1 boxes + bounds");
     // ---- hoisting of huge primitives
     uint32_t* d_large = ex.template alloc<uint32_t>(64);
     uint32_t* d_counters = ex.template alloc<uint32_t>(8);  // 0 large, 1 small, 2 node, 3 prim, 4 queue
@@ -169,6 +171,7 @@ bool build_wide_bvh(Exec& ex, const F4* d_src_prims, uint32_t n, BvhBuildResult&
         ex.free(d_is_large);
     }
 
+    ex.mark("hoist huge primitives");
     uint32_t* d_final_src = ex.template alloc<uint32_t>(n);
     const uint32_t small_root = n_large ? 1u : 0u;
     BvhNode* d_nodes = ex.template alloc<BvhNode>((size_t)n_small + 2);
@@ -208,7 +211,9 @@ bool build_wide_bvh(Exec& ex, const F4* d_src_prims, uint32_t n, BvhBuildResult&
             const uint32_t p = d_small[k];
             d_keys[k] = morton_key(d_box[p], cb, p);
         });
+        ex.mark("2 morton keys");
         ex.sort_u64(d_keys, n_small);
+        ex.mark("2 radix sort");
 
         // ---- 3, 4: topology and boxes
         Lbvh t;
@@ -226,6 +231,7 @@ bool build_wide_bvh(Exec& ex, const F4* d_src_prims, uint32_t n, BvhBuildResult&
         ex.parallel_for(n_small, QZ_LAMBDA(uint32_t i) { t.box[(t.n - 1) + i] = d_box[(uint32_t)t.keys[i]]; });
         ex.parallel_for(n_small, QZ_LAMBDA(uint32_t i) { lbvh_fit_body(t, i); });
         ex.download(&small_union, t.box, 1);
+        ex.mark("3-4 topology + fit");
 
         // ---- 5: collapse, one launch per tree level
         CollapseItem* d_q[2] = {ex.template alloc<CollapseItem>(n_small), ex.template alloc<CollapseItem>(n_small)};
@@ -255,6 +261,7 @@ bool build_wide_bvh(Exec& ex, const F4* d_src_prims, uint32_t n, BvhBuildResult&
             cur ^= 1;
             out.depth++;
         }
+        ex.mark("5 collapse");
         n_nodes = h_counters[2];
         // collapse wrote sorted positions: turn them into host-order primitive indices
         ex.parallel_for(n_small, QZ_LAMBDA(uint32_t s) { d_final_src[s] = (uint32_t)t.keys[d_final_src[s]]; });
@@ -276,6 +283,7 @@ bool build_wide_bvh(Exec& ex, const F4* d_src_prims, uint32_t n, BvhBuildResult&
     // ---- 6: gather the records into leaf order
     F4* d_prims = ex.template alloc<F4>((size_t)n * 4);
     ex.parallel_for(n, QZ_LAMBDA(uint32_t s) { gather_prim_body(d_src_prims, d_prims, s, d_final_src[s]); });
+    ex.mark("6 gather");
 
     ex.free(d_box); ex.free(d_bounds); ex.free(d_large); ex.free(d_counters); ex.free(d_small); ex.free(d_final_src);
     out.nodes = d_nodes;

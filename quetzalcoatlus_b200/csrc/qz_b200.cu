@@ -65,6 +65,16 @@ struct CudaExec {
     template <class T> void upload(T* dst, const T* src, size_t n) { if (n) note(cudaMemcpy(dst, src, n * sizeof(T), cudaMemcpyHostToDevice)); }
     template <class T> void download(T* dst, const T* src, size_t n) { if (n) note(cudaMemcpy(dst, src, n * sizeof(T), cudaMemcpyDeviceToHost)); }
     void zero(void* p, size_t bytes) { if (bytes) note(cudaMemset(p, 0, bytes)); }
+    // QZ_BUILD_TRACE=1: device-synchronised wall time of every build step on stderr
+    std::chrono::steady_clock::time_point t_mark = std::chrono::steady_clock::now();
+    void mark(const char* what) {
+        static const bool on = [] { const char* e = std::getenv("QZ_BUILD_TRACE"); return e && std::atoi(e) != 0; }();
+        if (!on) return;
+        cudaDeviceSynchronize();
+        const auto now = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[qz build] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_mark).count());
+        t_mark = now;
+    }
     template <class F> void parallel_for(uint32_t n, F f) {
         if (!n || err != cudaSuccess) return;
         uint32_t blocks = std::min<uint32_t>((n + 255u) / 256u, 148u * 16u);
@@ -259,14 +269,15 @@ struct DevBuf {
 #define QZ_MAX_PIPELINES 4
 
 struct WorkMem {
-    DevBuf rec_hot, rec_side, qbufs[8], tags[3], counters, statsb, res_a, res_b, res_c, rowsb, sensor, acc, memo;
+    DevBuf rec_hot, rec_side, qbufs[8], q_late, tags[3], counters, statsb, res_a, res_b, res_c, rowsb, sensor, acc, memo;
     uint32_t pool = 0;
     uint64_t cells = 0, acc_pix = 0, rows = 0;
     uint32_t* h_counters = nullptr;  // pinned
     DevBuf film[3];                  // device film planes of the host-buffer entry (qz_render)
     bool film_valid[3] = {false, false, false};
     uint32_t film_w = 0, film_h = 0;
-    float* h_film = nullptr;         // pinned staging for pageable caller buffers
+    float* h_film = nullptr;         // pinned staging for pageable caller buffers (three planes)
+    cudaEvent_t copy_done[3] = {};
     size_t h_film_bytes = 0;
     std::vector<cudaEvent_t> stage_events;
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_a = nullptr, ev_b = nullptr;
@@ -280,6 +291,7 @@ struct WorkMem {
         for (cudaEvent_t e : stage_events) cudaEventDestroy(e);
         for (cudaStream_t q : pipe_stream) if (q) cudaStreamDestroy(q);
         for (cudaEvent_t e : pipe_done) if (e) cudaEventDestroy(e);
+        for (cudaEvent_t e : copy_done) if (e) cudaEventDestroy(e);
         if (fork) cudaEventDestroy(fork);
     }
 };
@@ -518,6 +530,7 @@ static int render_impl(qz_scene s, const qz_camera* camera, uint32_t n_samples, 
     QZ_CUDA(wm.rec_hot.reserve((size_t)sub_pool * P * QZ_REC_BYTES));
     QZ_CUDA(wm.rec_side.reserve((size_t)sub_pool * P * QZ_REC_BYTES));
     for (auto& buf : qbufs) QZ_CUDA(buf.reserve((size_t)q_stride * P * 4));
+    QZ_CUDA(wm.q_late.reserve((size_t)q_stride * P * 4));
     for (auto& buf : wm.tags) QZ_CUDA(buf.reserve((size_t)tag_stride * P));
     QZ_CUDA(counters.reserve((size_t)C_WORDS * 4 * QZ_MAX_PIPELINES));
     QZ_CUDA(statsb.reserve(S_WORDS * 8));
@@ -565,6 +578,7 @@ static int render_impl(qz_scene s, const qz_camera* camera, uint32_t n_samples, 
         b.fam = wm.tags[1].as<uint8_t>() + (size_t)p * tag_stride;
         b.post = wm.tags[2].as<uint8_t>() + (size_t)p * tag_stride;
         for (int k = 0; k < SQ_COUNT; k++) b.q_shade[k] = qbufs[k].as<uint32_t>() + (size_t)p * q_stride;
+        b.q_late = wm.q_late.as<uint32_t>() + (size_t)p * q_stride;
         b.counters = counters.as<uint32_t>() + (size_t)p * C_WORDS;
         b.next_path = counters.as<uint32_t>() + C_NEXT_PATH;   // pipeline 0's block holds the shared cursor
         b.stats = statsb.as<unsigned long long>();
@@ -865,11 +879,16 @@ int qz_render(qz_scene s, const qz_camera* camera, uint32_t n_samples, uint32_t 
         if (cudaPointerGetAttributes(&attr, host[k]) == cudaSuccess && attr.type == cudaMemoryTypeHost) pinned[k] = true;
         else { cudaGetLastError(); need_staging = true; }
     }
-    if (need_staging && wm.h_film_bytes < n * 4) {
+    // (staging holds all three planes: the device->host copies are queued back to back and each plane is copied out to
+    // the caller's pageable buffer, by a few host threads, while the next one is still arriving)
+    if (need_staging && wm.h_film_bytes < 3 * n * 4) {
         if (wm.h_film) cudaFreeHost(wm.h_film);
         wm.h_film = nullptr; wm.h_film_bytes = 0;
-        QZ_CUDA(cudaMallocHost(&wm.h_film, n * 4));
-        wm.h_film_bytes = n * 4;
+        QZ_CUDA(cudaMallocHost(&wm.h_film, 3 * n * 4));
+        wm.h_film_bytes = 3 * n * 4;
+    }
+    if (need_staging && !wm.copy_done[0]) {
+        for (int k = 0; k < 3; k++) QZ_CUDA(cudaEventCreateWithFlags(&wm.copy_done[k], cudaEventDisableTiming));
     }
     const bool sharded = region && region->strip_rows && region->n_shards > 1;
     if (sharded) {
@@ -931,10 +950,24 @@ int qz_render(qz_scene s, const qz_camera* camera, uint32_t n_samples, uint32_t 
         if (pinned[k]) {
             QZ_CUDA(cudaMemcpyAsync(host[k], dev[k]->p, n * 4, cudaMemcpyDeviceToHost, nullptr));
         } else {
-            QZ_CUDA(cudaMemcpyAsync(wm.h_film, dev[k]->p, n * 4, cudaMemcpyDeviceToHost, nullptr));
-            QZ_CUDA(cudaStreamSynchronize(nullptr));
-            std::memcpy(host[k], wm.h_film, n * 4);
+            QZ_CUDA(cudaMemcpyAsync(wm.h_film + (size_t)k * n, dev[k]->p, n * 4, cudaMemcpyDeviceToHost, nullptr));
+            QZ_CUDA(cudaEventRecord(wm.copy_done[k], nullptr));
         }
+    }
+    for (int k = 0; k < 3; k++) {
+        if (!host[k] || pinned[k]) continue;
+        QZ_CUDA(cudaEventSynchronize(wm.copy_done[k]));
+        const float* src = wm.h_film + (size_t)k * n;
+        float* dst = host[k];
+        const int n_thr = n >= (1u << 20) ? 4 : 1;
+        const size_t chunk = (n + n_thr - 1) / n_thr;
+        std::vector<std::thread> helpers;
+        for (int t = 1; t < n_thr; t++) {
+            const size_t a = (size_t)t * chunk, e = std::min<size_t>(n, a + chunk);
+            if (a < e) helpers.emplace_back([=] { std::memcpy(dst + a, src + a, (e - a) * 4); });
+        }
+        std::memcpy(dst, src, std::min<size_t>(n, chunk) * 4);
+        for (auto& h : helpers) h.join();
     }
     QZ_CUDA(cudaStreamSynchronize(nullptr));
     return QZ_OK;

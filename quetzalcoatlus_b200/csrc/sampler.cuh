@@ -2,7 +2,7 @@
 // (sampler.cpp:161-198 permutation_element / mix_bits, :298-314 radical_inv, :316-324
 // inv_radical_inv, :335-352 owen_scrambled_radical_inv, :383-454 Sampler).  Everything up
 // to the final float multiply is integer arithmetic, so the device values equal the
-// oracle's bit for bit (tests/test_sampler.py checks the known answers of SURVEY.md
+// oracle's bit for bit (tests/test_gpu_parity.py::test_sampler_bit_exact* and tests/test_emu_parity.py check the known answers of SURVEY.md
 // section 4 and random (x, y, s, dim) tuples).
 //
 // B200 shaping: per-dimension constants live in a 16-byte record (one LDG.128): the prime

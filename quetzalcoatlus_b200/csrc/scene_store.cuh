@@ -166,6 +166,7 @@ struct SceneStore {
         view.lut_z = put(ex, t.rgb2spec_z, 32);
         view.lut_coeffs = put(ex, t.rgb2spec_coeffs, (size_t)3 * 32 * 32 * 32 * 3);
         const F4* src = put(ex, reinterpret_cast<const F4*>(t.prims), (size_t)t.n_prims * 4);
+        ex.mark("upload tables");
         if (!build_wide_bvh(ex, src, t.n_prims, bvh)) return false;
         ex.free(const_cast<F4*>(src));
         owned.pop_back();

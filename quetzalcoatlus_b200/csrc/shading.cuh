@@ -180,7 +180,7 @@ QZ_HD Spec4 light_emission(const DScene& sc, const qz_light& l, V3 n, V3 w, cons
 //   SOURCE for the value of a role at a dimension:
 //   * SamplesOnTheFly evaluates the Owen-scrambled dimension right there (per-path replay, the
 //     run-time-dispatch kernels, the host emulation);
-//   * SamplesPrecomputed returns what k_sample (wavefront.cuh) computed for this bounce in a
+//   * SamplesPrecomputed returns what k_sample (wf_stage.cuh) computed for this bounce in a
 //     separate, fully convergent, high-occupancy integer kernel.
 enum SampleRole { R_MAT = 0, R_PICK = 1, R_LIGHT = 2 /* and 3 */, R_BSDF = 4 /* and 5 */, R_U1 = 6, R_RR = 7, R_COUNT = 8 };
 
@@ -207,6 +207,9 @@ struct SamplesPrecomputed {
 QZ_HD bool bounce_in_memo(const SampleMemo& m, uint32_t index, uint32_t d0) {
     return m.tab && d0 + 9u <= m.dims && index - m.index0 < m.n;
 }
+
+// (a new path's first bounce starts at dimension 3, and every Halton index of the pass has a row)
+QZ_HD bool first_bounce_in_memo(const SampleMemo& m) { return m.tab && 3u + 9u <= m.dims; }
 
 // dimensions of every role of a bounce that starts at dimension d0 (same skip calls as shade_bounce)
 QZ_HD void bounce_dims(uint32_t d0, bool nee, bool has_lights, uint32_t dims[R_COUNT]) {

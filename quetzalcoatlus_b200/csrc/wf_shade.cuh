@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(256) k_generate(DScene sc, DCamera cam, WfBuff
         if (i < n) {
             float4 o, d;
             init_slot(sc, cam, b, pp, i, first_id + i, o, d);
-            b.stage[i] = ST_TRACE_FIRST;
+            b.stage[i] = (uint8_t)(ST_TRACE_FIRST | (first_bounce_in_memo(sc.memo) ? 0 : ST_LATE));
             b.q_shade[0][i] = i;
         } else {
             b.stage[i] = ST_EMPTY;
@@ -180,10 +180,11 @@ k_shade(DScene sc, WfBuffers b, uint32_t max_bounces) {
     for (; i < count; i += stride) {
         const uint32_t slot = slot_cur;
         const uint32_t slot_after = (i + 2u * stride < count && i + 2u * stride >= i) ? entry(i + 2u * stride) : 0u;
-        if (i + stride < count) {
-            prefetch_line(b.ray_o.at(slot_next));
-            if (KH != KH_ANY) prefetch_line(b.samples.at(slot_next));
-        }
+        // (tried: loading the next path's misc word here and prefetching its memo row at the bottom of the trip -- the
+        // extra live registers spilled and the stage got 16 % slower, profiles/r02_summary.md)
+        // (the side line is only written -- shadow request, radiance -- except by the late bounces, which read their draws
+        // there: prefetching it for every path was 750 MB of DRAM reads per 8.4 M slots for nothing)
+        if (i + stride < count) prefetch_line(b.ray_o.at(slot_next));
         slot_cur = slot_next;
         slot_next = slot_after;
         const bool first = i < n_first;
@@ -276,7 +277,10 @@ k_shade(DScene sc, WfBuffers b, uint32_t max_bounces) {
         if (TOUCHES_PDF) b.lpdf.set(slot, f4(ps.pdf));
         b.misc.set(slot, pack_misc(m.x, ps));
         b.post[slot] = (uint8_t)post;
-        b.stage[slot] = alive ? (ps.depth == 0 ? ST_TRACE_FIRST : ST_TRACE) : ST_EMPTY;
+        // (a path at depth 0 after an emitter pass-through is a first hit again; a continued path whose next bounce lies
+        // beyond the memo row goes through the sampler stage)
+        const bool late = !bounce_in_memo(sc.memo, ps.smp.index, ps.smp.dim);
+        b.stage[slot] = alive ? (uint8_t)((ps.depth == 0 ? ST_TRACE_FIRST : ST_TRACE) | (late ? ST_LATE : 0)) : (uint8_t)ST_EMPTY;
     }
 }
 
@@ -302,12 +306,13 @@ __device__ __forceinline__ uint8_t finish_and_regenerate(const DScene& sc, const
     const uint32_t next_id = base + __popc(peers & ((1u << lane) - 1u));
     if (next_id >= pp.total) return ST_EMPTY;
     init_slot(sc, cam, b, pp, slot, next_id, ray_o, ray_d);
-    return ST_TRACE_FIRST;
+    return (uint8_t)(ST_TRACE_FIRST | (first_bounce_in_memo(sc.memo) ? 0 : ST_LATE));
 }
 
 // BVH scenes: the finish stage between the two traversal kernels.  Walks the work list, consumes the post tags.
 __global__ void __launch_bounds__(256) k_finish(DScene sc, DCamera cam, WfBuffers b, PassParams pp) {
     if (blockIdx.x == 0 && threadIdx.x < SQ_COUNT) b.counters[C_SHADE0 + threadIdx.x] = 0;   // consumed by the shading stage; k_bin refills them
+    if (blockIdx.x == 0 && threadIdx.x == SQ_COUNT) b.counters[C_LATE] = 0;
     WorkList wl;
     wl.load(b.counters);
     const uint32_t n_work = wl.total();
@@ -388,6 +393,7 @@ __global__ void __launch_bounds__(128, 4) k_step_flat(DScene sc, DCamera cam, Wf
         s_emit[i] = sc.geoms[float_as_u32(sc.prims[4 * i].w)].light >= 0 ? 1 : 0;
     if (threadIdx.x == 0) wl.load(b.counters);
     if (blockIdx.x == 0 && threadIdx.x < SQ_COUNT) b.counters[C_SHADE0 + threadIdx.x] = 0;   // consumed by the shading stage; k_bin refills them
+    if (blockIdx.x == 0 && threadIdx.x == SQ_COUNT) b.counters[C_LATE] = 0;
     __syncthreads();
     for (uint32_t i = threadIdx.x; i < n_prims; i += blockDim.x) {
         uint32_t before_same = 0, n_emit = 0;
@@ -478,7 +484,7 @@ __global__ void __launch_bounds__(128, 4) k_step_flat(DScene sc, DCamera cam, Wf
                           : ((kind == QZ_MAT_DIELECTRIC || kind == QZ_MAT_THIN_DIELECTRIC) ? SQ_DIELECTRIC : SQ_MISC));
                 }
             }
-            b.fam[slot] = (uint8_t)(fam + (st == ST_TRACE_FIRST && !unsorted ? SQ_FAMILIES : 0));
+            b.fam[slot] = (uint8_t)(fam + ((st & ST_FIRST) && !unsorted ? SQ_FAMILIES : 0) + ((st & ST_LATE) ? QZ_FAM_LATE : 0u));
         }
     }
     stat_add(&b.stats[S_RAYS_CLOSEST], n_closest);

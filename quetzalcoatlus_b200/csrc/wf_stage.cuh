@@ -10,8 +10,10 @@ namespace qz {
 // ascend within every block's share; one atomicAdd per block and queue reserves the share.
 template <int NQ>
 __global__ void __launch_bounds__(256) k_bin(WfBuffers b) {
-    __shared__ uint32_t s_warp[8][NQ];
-    __shared__ uint32_t s_base[NQ];
+    // queue NQ is the late queue (tag bit QZ_FAM_LATE): a slot can be in its family queue and in the late queue
+    constexpr int NQL = NQ + 1;
+    __shared__ uint32_t s_warp[8][NQL];
+    __shared__ uint32_t s_base[NQL];
     const uint8_t* __restrict__ tags = b.fam;
     const uint32_t n_slots = b.pool;
     uint32_t* counters = b.counters + C_SHADE0;
@@ -28,19 +30,22 @@ __global__ void __launch_bounds__(256) k_bin(WfBuffers b) {
             for (uint32_t k = 0; k < 8; k++) tg[k] = first_slot + k < n_slots ? tags[first_slot + k] : QZ_FAM_NONE;
         }
         // membership masks (bit k = this thread's k-th slot) and per-thread counts
-        uint32_t member[NQ], cnt[NQ];
+        uint32_t member[NQL], cnt[NQL];
 #pragma unroll
-        for (int q = 0; q < NQ; q++) {
+        for (int q = 0; q < NQL; q++) {
             uint32_t m = 0;
 #pragma unroll
-            for (uint32_t k = 0; k < 8; k++) m |= (tg[k] == (uint32_t)q ? 1u : 0u) << k;
+            for (uint32_t k = 0; k < 8; k++) {
+                const bool in = tg[k] != QZ_FAM_NONE && (q < NQ ? (tg[k] & 0x0fu) == (uint32_t)q : (tg[k] & QZ_FAM_LATE) != 0u);
+                m |= (in ? 1u : 0u) << k;
+            }
             member[q] = m;
             cnt[q] = __popc(m);
         }
         // exclusive scan of the counts over the block, per queue
-        uint32_t excl[NQ];
+        uint32_t excl[NQL];
 #pragma unroll
-        for (int q = 0; q < NQ; q++) {
+        for (int q = 0; q < NQL; q++) {
             uint32_t x = cnt[q];
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
@@ -51,15 +56,16 @@ __global__ void __launch_bounds__(256) k_bin(WfBuffers b) {
             if (lane == 31) s_warp[warp][q] = x;
         }
         __syncthreads();
-        if (threadIdx.x < NQ) {
+        if (threadIdx.x < NQL) {
             uint32_t total = 0;
             for (int w = 0; w < 8; w++) { const uint32_t c = s_warp[w][threadIdx.x]; s_warp[w][threadIdx.x] = total; total += c; }
-            s_base[threadIdx.x] = total ? atomicAdd(&counters[threadIdx.x], total) : 0u;
+            uint32_t* counter = threadIdx.x < NQ ? &counters[threadIdx.x] : &b.counters[C_LATE];
+            s_base[threadIdx.x] = total ? atomicAdd(counter, total) : 0u;
         }
         __syncthreads();
 #pragma unroll
-        for (int q = 0; q < NQ; q++) {
-            uint32_t* queue = b.q_shade[q];
+        for (int q = 0; q < NQL; q++) {
+            uint32_t* queue = q < NQ ? b.q_shade[q] : b.q_late;
             uint32_t pos = s_base[q] + s_warp[warp][q] + excl[q];
             uint32_t m = member[q];
             while (m) {
@@ -99,10 +105,6 @@ __device__ __forceinline__ uint32_t queue_roles(int queue_id, uint32_t n_lights)
 // Thread 0 of the stage also does the pipeline's per-iteration bookkeeping (queue lengths -> statistics and the
 // termination count, traversal cursors back to zero): no traversal kernel runs concurrently on this stream.
 __global__ void __launch_bounds__(256) k_sample(DScene sc, WfBuffers b) {
-    uint32_t start[SQ_COUNT + 1];
-    start[0] = 0;
-#pragma unroll
-    for (int q = 0; q < SQ_COUNT; q++) start[q + 1] = start[q] + (queue_roles(q, sc.n_lights) ? b.counters[C_SHADE0 + q] : 0u);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         uint32_t shade = 0;
         for (int q = 0; q < SQ_COUNT; q++) shade += b.counters[C_SHADE0 + q];
@@ -113,15 +115,15 @@ __global__ void __launch_bounds__(256) k_sample(DScene sc, WfBuffers b) {
         b.counters[C_CURSOR_TRACE] = 0;
         b.counters[C_CURSOR_SHADOW] = 0;
     }
-    const uint32_t total = start[SQ_COUNT];
+    // only the bounces beyond the memo row (the late queue, built by k_bin) get their draws here; all others read them
+    // from the row in k_shade
+    const uint32_t total = b.counters[C_LATE];
     const bool has_lights = sc.n_lights != 0;
     for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
-        int q = 0;
-#pragma unroll
-        for (int k = 1; k < SQ_COUNT; k++) q += (t >= start[k]) ? 1 : 0;
-        const uint32_t slot = b.q_shade[q][t - start[q]];
+        const uint32_t slot = b.q_late[t];
+        const int q = (int)(b.fam[slot] & 0x0fu);
+        if (!queue_roles(q, sc.n_lights)) continue;   // run-time dispatch: evaluated on the fly inside k_shade<KH_ANY>
         const uint4 misc = b.misc.get(slot);
-        if (bounce_in_memo(sc.memo, misc.y, misc.z & 0xffffu)) continue;   // k_shade reads the row itself
         const int fam = q % SQ_FAMILIES;
         bool nee = fam == SQ_DIFFUSE;
         if (fam == SQ_CONDUCTOR) {

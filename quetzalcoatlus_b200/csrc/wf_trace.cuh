@@ -57,15 +57,18 @@ __device__ __forceinline__ int classify_hit(const DScene& sc, uint32_t geom_id, 
 }
 
 // closest-hit epilogue: write the hit record and the tag of the shade queue the path belongs to
-__device__ __forceinline__ void finish_closest(const DScene& sc, const WfBuffers& b, uint32_t slot, bool first, const Hit& h, uint32_t flags) {
+__device__ __forceinline__ void finish_closest(const DScene& sc, const WfBuffers& b, uint32_t slot, bool first, bool late, const Hit& h, uint32_t flags) {
     b.hit_a.set(slot, f4(h.t, h.u, h.v, __uint_as_float(h.prim_id)));
     b.hit_b.set(slot, f4(h.ng.x, h.ng.y, h.ng.z, __uint_as_float(h.geom_id)));
     const bool unsorted = (flags & QZ_FLAG_UNSORTED_SHADING) != 0;
     const int fam = classify_hit(sc, h.geom_id, unsorted);
-    b.fam[slot] = (uint8_t)(fam + (first && !unsorted ? SQ_FAMILIES : 0));
+    b.fam[slot] = (uint8_t)(fam + (first && !unsorted ? SQ_FAMILIES : 0) + (late ? QZ_FAM_LATE : 0u));
 }
 
-enum LaneState { LS_IDLE = 0, LS_NODE = 1, LS_PRIM = 2, LS_DONE = 3 };
+// LS_POP: the lane finished its leaf primitives and takes its next node from the stack at the head of the next node
+// stream, together with the other lanes in that state (popping right where the primitive stream ends ran the stack
+// loop for the three or four lanes that had just finished: 6 % of the kernel's instructions at 4 of 32 lanes)
+enum LaneState { LS_IDLE = 0, LS_NODE = 1, LS_PRIM = 2, LS_DONE = 3, LS_POP = 4 };
 
 #define QZ_CSWAP_DESC(a, b) { const uint32_t hi_ = a > b ? a : b, lo_ = a > b ? b : a; a = hi_; b = lo_; }
 
@@ -82,7 +85,7 @@ __global__ void __launch_bounds__(128, QZ_TRACE_MIN_BLOCKS) k_trace_lane(DScene 
     int state = LS_IDLE;
     bool exhausted = false;  // warp-uniform
     uint32_t slot = 0, cur = 0, leafbits = 0, leaf_base = 0;
-    bool first = false, occl = false;
+    bool first = false, late = false, occl = false;
     V3 O = v3(0.0f, 0.0f, 0.0f), D = v3(0.0f, 0.0f, 0.0f);
     float inv[3] = {0.0f, 0.0f, 0.0f};
     float limit = 0.0f;   // closest hit: best t so far; any hit: the end of the segment
@@ -114,7 +117,7 @@ __global__ void __launch_bounds__(128, QZ_TRACE_MIN_BLOCKS) k_trace_lane(DScene 
     };
 
     for (;;) {
-        const unsigned m_node = __ballot_sync(full, state == LS_NODE);
+        const unsigned m_node = __ballot_sync(full, state == LS_NODE || state == LS_POP);
         const unsigned m_prim = __ballot_sync(full, state == LS_PRIM);
         const unsigned m_done = __ballot_sync(full, state == LS_DONE);
         const unsigned m_idle = ~(m_node | m_prim | m_done);
@@ -130,7 +133,7 @@ __global__ void __launch_bounds__(128, QZ_TRACE_MIN_BLOCKS) k_trace_lane(DScene 
                         b.radiance.set(slot, f4(L.x + c.x, L.y + c.y, L.z + c.z, L.w + c.w));
                     }
                 } else {
-                    finish_closest(sc, b, slot, first, best, flags);
+                    finish_closest(sc, b, slot, first, late, best, flags);
                 }
                 state = LS_IDLE;
             }
@@ -157,7 +160,8 @@ __global__ void __launch_bounds__(128, QZ_TRACE_MIN_BLOCKS) k_trace_lane(DScene 
                             live = st != ST_EMPTY;
                             if (live) {
                                 slot = idx;
-                                first = st == ST_TRACE_FIRST;
+                                first = (st & ST_FIRST) != 0;
+                                late = (st & ST_LATE) != 0;
                                 ro = b.ray_o.get(slot); rd = b.ray_d.get(slot);
                                 limit = INFINITY;
                             } else {
@@ -198,7 +202,7 @@ __global__ void __launch_bounds__(128, QZ_TRACE_MIN_BLOCKS) k_trace_lane(DScene 
                     limit = best.t;
                 }
                 if (state == LS_PRIM) {
-                    if (leafbits == 0u) pop_next();
+                    if (leafbits == 0u) state = LS_POP;
                     else prefetch_line_l1(sc.prims + (size_t)(leaf_base + (uint32_t)(__ffs(leafbits) - 1)) * 4);
                 }
             }
@@ -206,6 +210,7 @@ __global__ void __launch_bounds__(128, QZ_TRACE_MIN_BLOCKS) k_trace_lane(DScene 
         }
 
         // ---- node stream: open one node per lane
+        if (state == LS_POP) pop_next();
         if (state == LS_NODE) {
             const uint4* np = reinterpret_cast<const uint4*>(sc.nodes + cur);
             uint4 w[8];
@@ -220,8 +225,20 @@ __global__ void __launch_bounds__(128, QZ_TRACE_MIN_BLOCKS) k_trace_lane(DScene 
             // quantised planes: words 2..4 = qlo[x,y,z][8], words 5..7 = qhi[x,y,z][8] (u16 each).  Per axis
             // the ray's direction sign says which of the two is the entry plane -- chosen once per
             // node on the packed words, not per child on the decoded distances.
+            //
+            // SLAB DISTANCES.  The distance to plane q of an axis is ((org + q * 2^e) - O) * inv = q * A + B with
+            // A = 2^e * inv (exact: a power of two) and B = (org - O) * inv -- ONE multiply-add per plane, and no
+            // integer-to-float conversion either: 0x4B000000 | q is the float 2^23 + q, so the distance is
+            // fma(2^23 + q, A, B - 2^23 * A).  This is not the build's decode expression rounded the build's way;
+            // it is within  |A| (the two roundings at magnitude 2^23 |A|: one quantisation step, 1/65535 of the node)
+            // + 2^-24 (3 |B| + pmax |inv| + 4 |t|)  of it (B: two roundings; the decoded plane's own rounding, pmax = the
+            // node's largest coordinate; the final rounding), so each axis interval is widened by
+            // slack = 1.6 |A| + 1e-6 |B| + 4e-7 pmax |inv| (which also covers the few ulps box_hit adds): conservative, and the
+            // closest hit does not depend on which boxes are opened beyond those that contain it.  (The first version
+            // decoded every plane as the build does -- convert, multiply-add, subtract, multiply: 64 instructions per
+            // child, over half of the kernel: profiles/r02_summary.md.)
             uint32_t qn[3][4], qf[3][4];
-            float bias[3];
+            float A[3], Bn[3], Bf[3];
 #pragma unroll
             for (int a = 0; a < 3; a++) {
                 const bool fwd = inv[a] >= 0.0f;
@@ -229,7 +246,15 @@ __global__ void __launch_bounds__(128, QZ_TRACE_MIN_BLOCKS) k_trace_lane(DScene 
                 const uint32_t* hi4 = reinterpret_cast<const uint32_t*>(&w[5 + a]);
 #pragma unroll
                 for (int j = 0; j < 4; j++) { qn[a][j] = fwd ? lo4[j] : hi4[j]; qf[a][j] = fwd ? hi4[j] : lo4[j]; }
-                bias[a] = a == 0 ? O.x : (a == 1 ? O.y : O.z);
+                const float Oa = a == 0 ? O.x : (a == 1 ? O.y : O.z);
+                A[a] = scl[a] * inv[a];
+                const float B = (org[a] - Oa) * inv[a];
+                const float Bp = __fmaf_rn(-8388608.0f, A[a], B);
+                const float pmax = fmaxf(fabsf(org[a]), fabsf(__fmaf_rn(65535.0f, scl[a], org[a])));
+                // (+ the few ulps of the distance itself, |t| <= |B| + 65535 |A|, that box_hit applies multiplicatively)
+                const float slack = __fmaf_rn(4e-7f, pmax * fabsf(inv[a]), __fmaf_rn(1e-6f, fabsf(B), 1.6f * fabsf(A[a])));
+                Bn[a] = Bp - slack;
+                Bf[a] = Bp + slack;
             }
             uint32_t key[8];
             uint32_t lb = 0;
@@ -239,23 +264,16 @@ __global__ void __launch_bounds__(128, QZ_TRACE_MIN_BLOCKS) k_trace_lane(DScene 
                 float t0 = QZ_TNEAR, t1 = limit;
 #pragma unroll
                 for (int a = 0; a < 3; a++) {
-                    const uint32_t q0 = (qn[a][k >> 1] >> (16 * (k & 1))) & 0xffffu;
-                    const uint32_t q1 = (qf[a][k >> 1] >> (16 * (k & 1))) & 0xffffu;
-                    // plane = org + q * 2^e: the product is exact, so the fused form rounds once, to the same value
-                    const float pn = __fmaf_rn((float)q0, scl[a], org[a]);
-                    const float pf = __fmaf_rn((float)q1, scl[a], org[a]);
-                    t0 = fmaxf(t0, (pn - bias[a]) * inv[a]);   // fmaxf / fminf drop NaN (0 * inf)
-                    t1 = fminf(t1, (pf - bias[a]) * inv[a]);
+                    // bytes of the u16 under 0x4B00: the float 2^23 + q
+                    const float xn = __uint_as_float(__byte_perm(qn[a][k >> 1], 0x4B000000u, (k & 1) ? 0x7632u : 0x7610u));
+                    const float xf = __uint_as_float(__byte_perm(qf[a][k >> 1], 0x4B000000u, (k & 1) ? 0x7632u : 0x7610u));
+                    t0 = fmaxf(t0, __fmaf_rn(xn, A[a], Bn[a]));   // fmaxf / fminf drop NaN (0 * inf, inf - inf)
+                    t1 = fminf(t1, __fmaf_rn(xf, A[a], Bf[a]));
                 }
-                // box_hit's conservative widening (bvh.cuh) is a monotone map of each slab distance, so it
-                // is applied once, to the max / min of them; QZ_TNEAR and the limit stay as they are
-                float e0 = t0 * (t0 >= 0.0f ? 0.9999995f : 1.0000005f);
-                float e1 = t1 * (t1 >= 0.0f ? 1.0000005f : 0.9999995f);
-                e0 = fmaxf(e0, QZ_TNEAR);
-                e1 = fminf(e1, limit);
-                const bool hit = m != 0u && e0 <= e1;
+                // (t0 >= QZ_TNEAR > 0 and t1 <= limit by their initial values; the conservative widening is in the slack)
+                const bool hit = m != 0u && t0 <= t1;
                 const bool internal = (m & 0x80u) != 0u;
-                key[k] = (hit && internal) ? ((__float_as_uint(e0) & ~7u) | (m & 7u)) : 0u;
+                key[k] = (hit && internal) ? ((__float_as_uint(t0) & ~7u) | (m & 7u)) : 0u;
                 if (hit && !internal) lb |= ((1u << (m >> 5)) - 1u) << (m & 31u);
             }
             // sort the (distance | child slot) keys descending: Batcher's 19-comparator network.  Shadow rays stop at

@@ -37,7 +37,12 @@ namespace qz {
 enum ShadeQueue { SQ_MISC = 0, SQ_DIFFUSE = 1, SQ_CONDUCTOR = 2, SQ_DIELECTRIC = 3, SQ_FAMILIES = 4, SQ_COUNT = 8 };
 
 // per-slot stage tag (what the next closest-hit stage does with the slot)
-enum StageTag : uint8_t { ST_EMPTY = 0, ST_TRACE = 1, ST_TRACE_FIRST = 2 };
+// Bits: live | first hit (depth 0) | LATE = the next bounce's draws are not in the path's memo row (sampler.cuh: it
+// starts beyond the row's dimensions, or the render has no memo), so they come from the sampler stage.  The trace stage
+// passes that on as QZ_FAM_LATE in the family tag and k_bin lists such slots in the late queue as well, so k_sample
+// visits only them.
+enum StageTag : uint8_t { ST_EMPTY = 0, ST_TRACE = 1, ST_FIRST = 2, ST_TRACE_FIRST = 3, ST_LATE = 4 };
+#define QZ_FAM_LATE 0x10u    /* family tag bit: the bounce needs the sampler stage */
 #define QZ_FAM_NONE 0xffu   /* family tag of a slot that was not traced this iteration */
 // post-shade tag bits: consumed (and cleared) by the shadow / finish stage of the next iteration
 #define QZ_POST_SHADOW 1u
@@ -48,6 +53,7 @@ enum StageTag : uint8_t { ST_EMPTY = 0, ST_TRACE = 1, ST_TRACE_FIRST = 2 };
 enum Counter {
     C_ACTIVE = 0,                         // paths shaded in the last completed iteration (termination test)
     C_SHADE0 = 2,                         // .. C_SHADE0 + SQ_COUNT - 1: queue lengths of this iteration
+    C_LATE = 10,                          // length of the late queue (bounces that need the sampler stage)
     C_CURSOR_TRACE = 12, C_CURSOR_SHADOW = 13,   // work cursors of the persistent traversal kernels
     C_NEXT_PATH = 14,                     // (pipeline 0's block only) next path id of the pass to hand out
     C_WORK0 = 16,                         // .. C_WORK0 + SQ_COUNT - 1: queue lengths of the PREVIOUS iteration = this iteration's work list
@@ -86,6 +92,7 @@ struct WfBuffers {
     RecField<float4> samples;           // R_COUNT floats per slot (two elements): this bounce's draws, written by k_sample
     uint8_t *stage, *fam, *post;  // per-slot tags (StageTag, family queue id or QZ_FAM_NONE, QZ_POST_* bits)
     uint32_t* q_shade[SQ_COUNT];
+    uint32_t* q_late;           // slots of this iteration whose bounce needs k_sample (QZ_FAM_LATE)
     uint32_t* counters;         // this pipeline's counter block
     uint32_t* next_path;        // next path id of the pass to hand out (shared by all pipelines)
     unsigned long long* stats;  // shared by all pipelines (atomics)

@@ -2,7 +2,7 @@
 // frame is computed on the host exactly as the reference does (tanf of half the field of
 // view, right = look_at x up, unnormalised ray directions) and handed to the GPU as a
 // qz_camera.  cast_ray() is kept for API parity; the render path generates rays on the
-// device (csrc/wavefront.cu: k_raygen).
+// device (csrc/shading.cuh: start_path, called by k_generate and the finish stages of csrc/wf_shade.cuh).
 #pragma once
 
 #include <cmath>

@@ -1,6 +1,6 @@
 // The reference's interaction.hpp (SurfaceInteraction: hit point, wo, normal, uv, material,
 // light) is integrator-internal state; on the B200 it is the hit record of the wavefront
-// pipeline (csrc/path_state.cuh).  This header exists so that code including it still compiles.
+// pipeline (csrc/wf_types.cuh: WfBuffers).  This header exists so that code including it still compiles.
 #pragma once
 
 #include "light.hpp"

@@ -7,7 +7,7 @@
 // intersection, the LBVH build and traversal, the path loop -- against the oracle, bit for
 // bit except for nothing: in this build the transcendental functions are the host libm's.
 // What it cannot cover is the wavefront scheduling, queues and film kernels of
-// wavefront.cu; those are covered by the -m gpu tests.
+// csrc/wf_*.cuh; those are covered by the -m gpu tests.
 //
 // The product never routes through this file: bench.py, __graft_entry__.smoke() and the
 // quetzalcoatlus_b200 package load libqz_b200.so only, which fails loudly without a GPU.
@@ -31,6 +31,7 @@ struct SeqExec {
     void zero(void* p, size_t bytes) { std::memset(p, 0, bytes); }
     template <class F> void parallel_for(uint32_t n, F f) { for (uint32_t i = 0; i < n; i++) f(i); }
     void sort_u64(uint64_t* keys, uint32_t n) { std::sort(keys, keys + n); }
+    void mark(const char*) {}
 };
 
 thread_local std::string g_error;
