@@ -550,7 +550,8 @@ static int render_impl(qz_scene s, const qz_camera* camera, uint32_t n_samples, 
         if (env_memo && n_pix64 >= 4 * classes && memo_n < (1ull << 31)) {
             memo_dim_off = ((4u * QZ_MEMO_MAX_HOT + 7u) & ~7u) + 5u;          // hot spectra block, then dimension 3 on a sector boundary
             const uint64_t fit = (3ull << 30) / (memo_n * 4);               // words per row within the budget
-            memo_dims = 3 + 8 * 8;
+            static const int env_memo_bounces = [] { const char* e = std::getenv("QZ_MEMO_BOUNCES"); int v = e ? std::atoi(e) : 0; return v; }();
+            memo_dims = 3 + 8 * (uint32_t)(env_memo_bounces > 0 ? std::min(env_memo_bounces, 32) : 8);
             while (memo_dims >= 3 + 8 && ((memo_dim_off + memo_dims + 7u) & ~7u) > fit) memo_dims -= 8;
             if (memo_dims < 3 + 8) memo_dims = 0;
             memo_stride = (memo_dim_off + memo_dims + 7u) & ~7u;

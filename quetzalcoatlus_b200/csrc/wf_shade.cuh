@@ -150,6 +150,7 @@ __global__ void __launch_bounds__(256) k_memo_spectra(DScene sc, SamplerParams s
     }
 }
 
+#define QZ_REC_GET get_l1   /* k_shade reads the hot line it prefetched into L1 */
 #ifndef QZ_SHADE_MIN_BLOCKS_LIGHT
 #define QZ_SHADE_MIN_BLOCKS_LIGHT 4   /* diffuse / dielectric shade kernels: 128 registers (5 blocks = 96 registers spills: -12 % on the stage) */
 #endif
@@ -182,26 +183,31 @@ k_shade(DScene sc, WfBuffers b, uint32_t max_bounces) {
         const uint32_t slot_after = (i + 2u * stride < count && i + 2u * stride >= i) ? entry(i + 2u * stride) : 0u;
         // (tried: loading the next path's misc word here and prefetching its memo row at the bottom of the trip -- the
         // extra live registers spilled and the stage got 16 % slower, profiles/r02_summary.md)
-        // (the side line is only written -- shadow request, radiance -- except by the late bounces, which read their draws
-        // there: prefetching it for every path was 750 MB of DRAM reads per 8.4 M slots for nothing)
-        if (i + stride < count) prefetch_line(b.ray_o.at(slot_next));
+        // (the side line is mostly written -- shadow request, radiance -- yet fetching it ahead pays: without it the
+        // partial-line stores wait for their fill, step 93.2 -> 95.3 ms)
+        // The hot line goes to L1 and is then read through L1 (RecField::get_l1): a slot is read by one thread per
+        // kernel and L1 starts every kernel empty, so the line cannot be stale (+2 % on the step over an L2 prefetch).
+        if (i + stride < count) {
+            prefetch_line_l1(b.ray_o.at(slot_next));
+            if (KH != KH_ANY) prefetch_line(b.samples.at(slot_next));
+        }
         slot_cur = slot_next;
         slot_next = slot_after;
         const bool first = i < n_first;
         PathState ps;
-        const float4 o = b.ray_o.get(slot), d = b.ray_d.get(slot);
+        const float4 o = b.ray_o.QZ_REC_GET(slot), d = b.ray_d.QZ_REC_GET(slot);
         ps.ray.o = v3(o.x, o.y, o.z); ps.ior_scale = o.w;
         ps.ray.d = v3(d.x, d.y, d.z); ps.p_b = d.w;
-        ps.weight = s4(b.weight.get(slot));
-        ps.lambda = s4(b.lambda.get(slot));
+        ps.weight = s4(b.weight.QZ_REC_GET(slot));
+        ps.lambda = s4(b.lambda.QZ_REC_GET(slot));
         // only a dispersive dielectric changes the wavelength pdf (terminate_secondary): the other families neither load nor store it
         constexpr bool TOUCHES_PDF = KH == KH_DIELECTRIC || KH == KH_ANY;
-        ps.pdf = TOUCHES_PDF ? s4(b.lpdf.get(slot)) : spec4(0.0f);
+        ps.pdf = TOUCHES_PDF ? s4(b.lpdf.QZ_REC_GET(slot)) : spec4(0.0f);
         ps.L = spec4(0.0f);
-        const uint4 m = b.misc.get(slot);
+        const uint4 m = b.misc.QZ_REC_GET(slot);
         unpack_misc(m, ps);
         ps.n_rays += 1;  // + the closest-hit query that produced this hit
-        const float4 ha = b.hit_a.get(slot), hb = b.hit_b.get(slot);
+        const float4 ha = b.hit_a.QZ_REC_GET(slot), hb = b.hit_b.QZ_REC_GET(slot);
         Hit hit;
         hit.t = ha.x; hit.u = ha.y; hit.v = ha.z; hit.prim_id = __float_as_uint(ha.w);
         hit.ng = v3(hb.x, hb.y, hb.z);
@@ -230,6 +236,7 @@ k_shade(DScene sc, WfBuffers b, uint32_t max_bounces) {
                 }
                 uint32_t dims[R_COUNT];
                 bounce_dims(d0, nee, sc.n_lights != 0, dims);
+                // (tried: prefetching the row's hot-spectra line into L1 here -- no change)
                 const uint32_t* row = memo_row(sc.memo, m.y) + sc.memo.dim_off;
 #pragma unroll
                 for (int k = 0; k < R_COUNT; k++) src.v[k] = 0.0f;
@@ -414,6 +421,8 @@ __global__ void __launch_bounds__(128, 4) k_step_flat(DScene sc, DCamera cam, Wf
         if (tile >= n_work) break;
         const uint32_t tile_n = min((uint32_t)QZ_FLAT_TILE, n_work - tile);
         // ---- phase 1: shadow tests, collect the finished paths
+        // (tried: the tags of all of a thread's entries loaded up front and the next shadow request loaded before the
+        // current primitive loop, as in phase 3 -- 105 registers, one CTA per SM fewer, step 93.2 -> 97.7 ms)
         for (uint32_t k = threadIdx.x; k < tile_n; k += blockDim.x) {
             const uint32_t slot = wl.slot(b.q_shade, tile + k);
             s_slot[k] = slot;

@@ -71,6 +71,9 @@ struct RecField {
     char* base;
     __device__ __forceinline__ T* at(uint32_t slot) const { return reinterpret_cast<T*>(base + (size_t)slot * QZ_REC_BYTES); }
     __device__ __forceinline__ T get(uint32_t slot) const { return __ldcg(at(slot)); }
+    // through L1: for a line the same thread prefetched into L1 a trip earlier (k_shade); a slot is read by one thread
+    // per kernel and L1 starts every kernel empty, so the line cannot be stale
+    __device__ __forceinline__ T get_l1(uint32_t slot) const { return __ldca(at(slot)); }
     __device__ __forceinline__ void set(uint32_t slot, const T& v) const { __stcg(at(slot), v); }
 };
 
