@@ -185,6 +185,11 @@ typedef struct qz_region {
  * this flag every float operation is performed as the reference's x86-64 build performs it: paths are
  * bit-identical to the reference's, at about twice the shading time.                                             */
 #define QZ_FLAG_EXACT_ARITHMETIC 64u
+/* The per-pass sample memo (csrc/sampler.cuh: sampler values and hot spectra tabulated per Halton index) is used when the
+ * call owns at least four times more pixels than (x mod 128, y mod 128) classes; these two flags force it on or off
+ * (parity tests: the film is bit-identical either way).                                                            */
+#define QZ_FLAG_FORCE_MEMO 128u
+#define QZ_FLAG_NO_MEMO 256u
 
 typedef struct qz_render_options {
     uint32_t flags;

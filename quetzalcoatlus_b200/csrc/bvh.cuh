@@ -47,7 +47,7 @@ struct alignas(16) BvhNode {
 };
 static_assert(sizeof(BvhNode) == 128, "a wide node is exactly one 128-byte line");
 
-#define QZ_LEAF_MAX 3 /* primitives per leaf child */
+#define QZ_LEAF_MAX 3 /* primitives per leaf child: the count shares the meta byte with the internal flag (bit 7), so 3 is the maximum */
 
 struct Aabb {
     float lo[3], hi[3];

@@ -17,9 +17,9 @@ void generate(const Stage& s, uint32_t first_id, uint32_t n) {
     QZL_UNPACK
     k_generate<<<s.lean_blocks, 256, 0, s.stream>>>(sc, *static_cast<const DCamera*>(s.cam), b, *static_cast<const PassParams*>(s.pass), first_id, n);
 }
-void memo_spectra(const Stage& s, const void* sampler_params, uint32_t cls_w, uint32_t cls_h, uint32_t s_begin, uint32_t s_count) {
+void memo_spectra(const Stage& s) {
     QZL_UNPACK
-    k_memo_spectra<<<s.lean_blocks, 256, 0, s.stream>>>(sc, *static_cast<const SamplerParams*>(sampler_params), cls_w, cls_h, s_begin, s_count);
+    k_memo_spectra<<<s.lean_blocks, 256, 0, s.stream>>>(sc);
 }
 void albedo(const Stage& s) {
     QZL_UNPACK

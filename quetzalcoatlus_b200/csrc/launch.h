@@ -29,13 +29,13 @@ void sample(const Stage& s);
 void film(const Stage& s, float* acc, bool first_pass, bool last_pass, uint32_t n_samples_total, float* color, float* normal, float* albedo, int blocks);
 
 void memo_fill(const void* sampler_table /* qz::SamplerDim */, const void* sampler_params /* qz::SamplerParams */, const void* memo /* qz::SampleMemo */,
-               uint32_t cls_w, uint32_t cls_h, uint32_t s_begin, uint32_t s_count, int blocks, cudaStream_t stream);
+               int blocks, cudaStream_t stream);
 void tone(const float* rgb, uint32_t n_pixels, float gamma, float* bgr255, uint8_t* bgr8, int blocks, cudaStream_t stream);
 
 // one set per arithmetic mode
 #define QZL_MODE_API                                                                                          \
     void generate(const Stage& s, uint32_t first_id, uint32_t n);                                           \
-    void memo_spectra(const Stage& s, const void* sampler_params, uint32_t cls_w, uint32_t cls_h, uint32_t s_begin, uint32_t s_count); \
+    void memo_spectra(const Stage& s);                                                                      \
     void albedo(const Stage& s);                                                                            \
     void shade(const Stage& s, int family /* 0 misc, 1 diffuse, 2 conductor, 3 dielectric */);              \
     void finish(const Stage& s);                                                                            \

@@ -269,7 +269,7 @@ struct DevBuf {
 #define QZ_MAX_PIPELINES 4
 
 struct WorkMem {
-    DevBuf rec_hot, rec_side, qbufs[8], q_late, tags[3], counters, statsb, res_a, res_b, res_c, rowsb, sensor, acc, memo;
+    DevBuf rec_hot, rec_side, qbufs[8], q_late, tags[3], counters, statsb, res_a, res_b, res_c, rowsb, sensor, acc, memo, memo_rank, memo_idx;
     uint32_t pool = 0;
     uint64_t cells = 0, acc_pix = 0, rows = 0;
     uint32_t* h_counters = nullptr;  // pinned
@@ -496,11 +496,43 @@ static int render_impl(qz_scene s, const qz_camera* camera, uint32_t n_samples, 
     }
     s_pass = std::min(s_pass, n_samples);
     while ((uint64_t)s_pass * n_pix >= (1ull << 31)) s_pass = std::max(1u, s_pass / 2);
+    // SAMPLE MEMO (sampler.cuh): worth its fill when several pixels share a Halton index, i.e. when the call owns several
+    // times more pixels than (x mod 128, y mod 128) classes.  Rows: hot spectra, the jitter, the wavelength draw and eight
+    // bounces' worth of dimensions (later bounces go through the sampler stage).
+    static const int env_memo = [] { const char* e = std::getenv("QZ_MEMO"); return e ? std::atoi(e) : 1; }();
+    uint32_t memo_dims = 0, memo_stride = 0, memo_dim_off = 0;
+    std::vector<uint32_t> cls_rank, cls_idx;   // (x mod 128, y mod 128) classes the call owns (sampler.cuh, SampleMemo)
+    if ((env_memo || (flags & QZ_FLAG_FORCE_MEMO)) && !(flags & QZ_FLAG_NO_MEMO)) {
+        bool own_py[QZ_MAX_HALTON_RESOLUTION] = {};
+        for (uint32_t r : rows) own_py[(H - 1u - r) & (QZ_MAX_HALTON_RESOLUTION - 1)] = true;
+        cls_rank.assign(spar.stride, 0xffffffffu);
+        const uint32_t cw = std::min<uint32_t>(W, QZ_MAX_HALTON_RESOLUTION);
+        for (uint32_t py = 0; py < QZ_MAX_HALTON_RESOLUTION; py++) {
+            if (!own_py[py]) continue;
+            for (uint32_t px = 0; px < cw; px++) {
+                const uint32_t idx = sampler_start(spar, px, py, 0).index;
+                if (cls_rank[idx] == 0xffffffffu) { cls_rank[idx] = (uint32_t)cls_idx.size(); cls_idx.push_back(idx); }
+            }
+        }
+        const uint64_t n_cls = cls_idx.size();
+        if ((flags & QZ_FLAG_FORCE_MEMO) || (n_pix64 >= 4 * n_cls && n_pix64 >= 65536)) {
+            memo_dim_off = ((4u * QZ_MEMO_MAX_HOT + 7u) & ~7u) + 5u;          // hot spectra block, then dimension 3 on a sector boundary
+            static const int env_memo_bounces = [] { const char* e = std::getenv("QZ_MEMO_BOUNCES"); int v = e ? std::atoi(e) : 0; return v; }();
+            memo_dims = 3 + 8 * (uint32_t)(env_memo_bounces > 0 ? std::min(env_memo_bounces, 32) : 8);
+            memo_stride = (memo_dim_off + memo_dims + 7u) & ~7u;
+            // a pass must also fit its rows into the memo's budget (3 GB)
+            const uint64_t rows_fit = (3ull << 30) / ((uint64_t)memo_stride * 4 * n_cls);
+            if (rows_fit == 0) memo_dims = 0;
+            else s_pass = (uint32_t)std::min<uint64_t>(s_pass, rows_fit);
+        }
+    }
     const uint64_t cells = (uint64_t)s_pass * n_pix;
-    uint32_t pool = options && options->pool_paths ? options->pool_paths : (1u << 23);
+    // paths in flight: 2^23 for the flat scenes, 2^24 where the BVH is traversed (fewer, fuller iterations: obj_viewer +4 %;
+    // cornell_box -1 %)
+    const bool flat_scene = sc.n_prims <= QZ_FLAT_MAX_PRIMS && sc.n_prims > 0 && !(flags & (QZ_FLAG_COUNT_TRAVERSAL | QZ_FLAG_FORCE_BVH));
+    uint32_t pool = options && options->pool_paths ? options->pool_paths : (flat_scene ? (1u << 23) : (1u << 24));
     pool = (uint32_t)std::min<uint64_t>(pool, cells);
     pool = std::max(pool, 1u);
-
     const bool count_trav = (flags & QZ_FLAG_COUNT_TRAVERSAL) != 0;
     const bool stage_timing = (flags & QZ_FLAG_STAGE_TIMING) != 0;
     // ARITHMETIC MODE (common.cuh): radiometric values fused / approximate by default; QZ_FLAG_EXACT_ARITHMETIC (or
@@ -542,22 +574,13 @@ static int render_impl(qz_scene s, const qz_camera* camera, uint32_t n_samples, 
     // SAMPLE MEMO (sampler.cuh): worth its memset when several pixels share a Halton index, i.e. when the call owns
     // several times more pixels than there are (x mod 128, y mod 128) classes.  Rows: the jitter, the wavelength draw
     // and eight bounces' worth of dimensions (later bounces evaluate directly), within a 2 GB budget.
-    static const int env_memo = [] { const char* e = std::getenv("QZ_MEMO"); return e ? std::atoi(e) : 1; }();
-    uint32_t memo_dims = 0, memo_stride = 0, memo_dim_off = 0;
-    const uint64_t memo_n = (uint64_t)s_pass * spar.stride;
-    {
-        const uint64_t classes = (uint64_t)std::min<uint32_t>(W, QZ_MAX_HALTON_RESOLUTION) * std::min<uint32_t>(H, QZ_MAX_HALTON_RESOLUTION);
-        if (env_memo && n_pix64 >= 4 * classes && memo_n < (1ull << 31)) {
-            memo_dim_off = ((4u * QZ_MEMO_MAX_HOT + 7u) & ~7u) + 5u;          // hot spectra block, then dimension 3 on a sector boundary
-            const uint64_t fit = (3ull << 30) / (memo_n * 4);               // words per row within the budget
-            static const int env_memo_bounces = [] { const char* e = std::getenv("QZ_MEMO_BOUNCES"); int v = e ? std::atoi(e) : 0; return v; }();
-            memo_dims = 3 + 8 * (uint32_t)(env_memo_bounces > 0 ? std::min(env_memo_bounces, 32) : 8);
-            while (memo_dims >= 3 + 8 && ((memo_dim_off + memo_dims + 7u) & ~7u) > fit) memo_dims -= 8;
-            if (memo_dims < 3 + 8) memo_dims = 0;
-            memo_stride = (memo_dim_off + memo_dims + 7u) & ~7u;
-        }
+    if (memo_dims) {
+        QZ_CUDA(wm.memo.reserve((size_t)memo_stride * 4 * s_pass * cls_idx.size()));
+        QZ_CUDA(wm.memo_rank.reserve(cls_rank.size() * 4));
+        QZ_CUDA(wm.memo_idx.reserve(cls_idx.size() * 4));
+        QZ_CUDA(cudaMemcpyAsync(wm.memo_rank.p, cls_rank.data(), cls_rank.size() * 4, cudaMemcpyHostToDevice, stream));
+        QZ_CUDA(cudaMemcpyAsync(wm.memo_idx.p, cls_idx.data(), cls_idx.size() * 4, cudaMemcpyHostToDevice, stream));
     }
-    if (memo_dims) QZ_CUDA(wm.memo.reserve((size_t)memo_stride * memo_n * 4));
     const bool multi_pass = s_pass < n_samples;
     if (multi_pass) QZ_CUDA(acc.reserve((size_t)n_pix * 9 * 4));
     QZ_CUDA(cudaMemcpyAsync(rowsb.p, rows.data(), rows.size() * 4, cudaMemcpyHostToDevice, stream));
@@ -723,14 +746,18 @@ static int render_impl(qz_scene s, const qz_camera* camera, uint32_t n_samples, 
         if (memo_dims) {
             sc.memo.tab = wm.memo.as<uint32_t>();
             sc.memo.dims = memo_dims;
-            sc.memo.n = pp.s_count * spar.stride;
-            sc.memo.index0 = s_begin * spar.stride;
+            sc.memo.n_cls = (uint32_t)cls_idx.size();
+            sc.memo.s_begin = s_begin;
+            sc.memo.s_count = pp.s_count;
             sc.memo.stride = memo_stride;
             sc.memo.dim_off = memo_dim_off;
+            sc.memo.idx_stride = spar.stride;
+            sc.memo.idx_magic = (uint32_t)((1ull << 32) / spar.stride);
+            sc.memo.cls_rank = wm.memo_rank.as<uint32_t>();
+            sc.memo.cls_idx = wm.memo_idx.as<uint32_t>();
             sc.memo.n_hot = 0;   // (set after the fill: k_memo_spectra itself must evaluate, not look up)
-            QZ_RENDER_CUDA(cudaMemsetAsync(sc.memo.tab, 0xff, (size_t)memo_stride * sc.memo.n * 4, stream));
-            qzl::memo_fill(sc.sampler_table, &spar, &sc.memo, std::min<uint32_t>(W, QZ_MAX_HALTON_RESOLUTION), std::min<uint32_t>(H, QZ_MAX_HALTON_RESOLUTION),
-                           s_begin, pp.s_count, n_sm * 8, stream);
+            QZ_RENDER_CUDA(cudaMemsetAsync(sc.memo.tab, 0xff, (size_t)memo_stride * 4 * pp.s_count * cls_idx.size(), stream));
+            qzl::memo_fill(sc.sampler_table, &spar, &sc.memo, n_sm * 8, stream);
             st.kernel_launches++;
             const uint32_t n_hot = (uint32_t)s->store.hot_spectra.size();
             if (n_hot) {
@@ -740,8 +767,7 @@ static int render_impl(qz_scene s, const qz_camera* camera, uint32_t n_samples, 
                 qzl::Stage fs = stg[0];
                 fs.scene = &sc_fill;
                 fs.stream = stream;
-                const uint32_t cw = std::min<uint32_t>(W, QZ_MAX_HALTON_RESOLUTION), ch = std::min<uint32_t>(H, QZ_MAX_HALTON_RESOLUTION);
-                exact ? qzl::exact::memo_spectra(fs, &spar, cw, ch, s_begin, pp.s_count) : qzl::fast::memo_spectra(fs, &spar, cw, ch, s_begin, pp.s_count);
+                exact ? qzl::exact::memo_spectra(fs) : qzl::fast::memo_spectra(fs);
                 st.kernel_launches++;
                 sc.memo.n_hot = n_hot;
             }

@@ -213,21 +213,35 @@ QZ_HD float sample_dimension(const SamplerDim* __restrict__ table, const Sampler
 // (per-path replay, host emulation, small images without reuse) evaluates directly.
 #define QZ_MEMO_EMPTY 0xffffffffu
 #define QZ_MEMO_MAX_HOT 8
+// ROWS.  A Halton index is idx_pix + s * 31104 with idx_pix one of 31104 residues, of which an image uses at most
+// 128 x 128 -- and a multi-GPU shard, which owns every n-th strip of rows, only its share of the y classes.  The rows of
+// a pass are therefore laid out as (sample number, class rank): `cls_rank` maps idx_pix to the rank of the (x mod 128,
+// y mod 128) class among those the call owns (0xffffffff: not owned), `cls_idx` is the inverse list.
 struct SampleMemo {
     uint32_t* tab;
     uint32_t dims;      // dimensions per row
-    uint32_t n;         // rows (Halton indices of the pass)
-    uint32_t index0;    // first Halton index of the pass
+    uint32_t n_cls;     // owned pixel classes
+    uint32_t s_begin, s_count;   // sample numbers of the pass
     uint32_t stride;    // words per row (multiple of 8)
     uint32_t dim_off;   // word of dimension 0
     uint32_t n_hot;     // hot spectra per row
-    int32_t hot_id[QZ_MEMO_MAX_HOT];   // their spectrum ids
+    uint32_t idx_stride, idx_magic;      // the sampler's index stride (31104) and floor(2^32 / stride)
+    const uint32_t* cls_rank;            // [idx_stride]
+    const uint32_t* cls_idx;             // [n_cls]: idx_pix of each owned class
+    int32_t hot_id[QZ_MEMO_MAX_HOT];     // spectrum ids of the hot spectra
 };
 QZ_HD uint32_t* memo_row(const SampleMemo& m, uint32_t index) {
     if (!m.tab) return nullptr;
-    const uint32_t i = index - m.index0;
-    if (i >= m.n) return nullptr;
-    return m.tab + (size_t)i * m.stride;
+    uint32_t idx_pix;
+    const uint32_t s = div_magic(index, m.idx_stride, m.idx_magic, idx_pix) - m.s_begin;
+    if (s >= m.s_count) return nullptr;
+#if defined(__CUDA_ARCH__)
+    const uint32_t r = __ldg(m.cls_rank + idx_pix);
+#else
+    const uint32_t r = m.cls_rank[idx_pix];
+#endif
+    if (r >= m.n_cls) return nullptr;
+    return m.tab + ((size_t)s * m.n_cls + r) * m.stride;
 }
 QZ_HD uint32_t* memo_slot(const SampleMemo& m, uint32_t dim, uint32_t index) {
     uint32_t* row = memo_row(m, index);

@@ -205,7 +205,8 @@ struct SamplesPrecomputed {
 // lights).  When all of them lie in the path's memo row (sampler.cuh) the shading kernel reads them there and the
 // sampler stage skips the bounce; later bounces go through k_sample and the record as before.
 QZ_HD bool bounce_in_memo(const SampleMemo& m, uint32_t index, uint32_t d0) {
-    return m.tab && d0 + 9u <= m.dims && index - m.index0 < m.n;
+    (void)index;   // every path of the pass has a row: its sample number and pixel class are the pass's and the call's
+    return m.tab && d0 + 9u <= m.dims;
 }
 
 // (a new path's first bounce starts at dimension 3, and every Halton index of the pass has a row)

@@ -132,19 +132,16 @@ __global__ void __launch_bounds__(256) k_albedo_conductor(DScene sc, WfBuffers b
 // Fills the hot-spectra block of the memo rows (sampler.cuh): one thread per (sample number, pixel class) derives the
 // row's wavelengths from its dimension-2 value (already filled by k_memo_fill) exactly as start_path does and evaluates
 // every hot spectrum with from_spectrum -- the function the shading code would otherwise call per bounce.
-__global__ void __launch_bounds__(256) k_memo_spectra(DScene sc, SamplerParams spar, uint32_t cls_w, uint32_t cls_h, uint32_t s_begin, uint32_t s_count) {
-    const uint32_t ncls = cls_w * cls_h;
-    const uint64_t total = (uint64_t)s_count * ncls;
+__global__ void __launch_bounds__(256) k_memo_spectra(DScene sc) {
+    const SampleMemo& memo = sc.memo;
+    const uint64_t total = (uint64_t)memo.s_count * memo.n_cls;
     for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t s = (uint32_t)(t / ncls), cls = (uint32_t)(t - (uint64_t)s * ncls);
-        const Sampler smp = sampler_start(spar, cls % cls_w, cls / cls_w, s_begin + s);
-        uint32_t* row = memo_row(sc.memo, smp.index);
-        if (!row) continue;
-        const float ul = __uint_as_float(__ldcg(row + sc.memo.dim_off + 2));
+        uint32_t* row = memo.tab + (size_t)t * memo.stride;
+        const float ul = __uint_as_float(__ldcg(row + memo.dim_off + 2));
         Spec4 lambda, pdf;
         sample_wavelengths(ul, lambda, pdf);
-        for (uint32_t k = 0; k < sc.memo.n_hot; k++) {
-            const Spec4 v = from_spectrum(sc, sc.memo.hot_id[k], lambda);
+        for (uint32_t k = 0; k < memo.n_hot; k++) {
+            const Spec4 v = from_spectrum(sc, memo.hot_id[k], lambda);
             __stcg(reinterpret_cast<float4*>(row) + k, f4(v));
         }
     }

@@ -168,52 +168,47 @@ __global__ void __launch_bounds__(256) k_sample(DScene sc, WfBuffers b) {
 }
 
 // Fills the dimension words of the pass's sample memo (sampler.cuh) ahead of the wavefront: every sample number of the
-// pass, every (x mod 128, y mod 128) class of the image, every dimension.  A CTA of eight warps takes 32 neighbouring
+// pass, every (x mod 128, y mod 128) class the call owns, every dimension.  A CTA of eight warps takes 32 neighbouring
 // classes of one sample number and eight consecutive words of their rows: warp w evaluates ONE dimension for the 32
 // classes -- same base, same digit count, no divergence but the permutation's rejection loop -- and the CTA then writes
 // each row's eight words as one 32-byte sector.  Each value is computed once instead of once per pixel that shares
 // the index (39 pixels at 800 x 800) and bounce.  (Filled lazily by the paths themselves, the 39 first users of an
 // entry all ran in the same wavefront iteration and nearly every warp of the sampler stage dragged a few missing
 // lanes through the digit loops: profiles/r02_summary.md.)
-__global__ void __launch_bounds__(256) k_memo_fill(const SamplerDim* __restrict__ table, SamplerParams spar, SampleMemo memo, uint32_t cls_w,
-                                                    uint32_t cls_h, uint32_t s_begin, uint32_t s_count) {
+__global__ void __launch_bounds__(256) k_memo_fill(const SamplerDim* __restrict__ table, SamplerParams spar, SampleMemo memo) {
     __shared__ uint32_t s_val[32][9];
-    __shared__ uint32_t s_index[32];
-    const uint32_t ncls = cls_w * cls_h;
+    const uint32_t ncls = memo.n_cls;
     const uint32_t cls_groups = (ncls + 31u) / 32u;
     const uint32_t word0 = memo.dim_off - 5u;                       // first word of the dimension region, 32-byte aligned
     const uint32_t n_chunks = (memo.dims + 5u + 7u) / 8u;
-    const uint64_t total = (uint64_t)s_count * cls_groups * n_chunks;
+    const uint64_t total = (uint64_t)memo.s_count * cls_groups * n_chunks;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     for (uint64_t item = blockIdx.x; item < total; item += gridDim.x) {
         // chunk-major: consecutive CTAs work on the same dimensions
-        const uint32_t chunk = (uint32_t)(item / ((uint64_t)s_count * cls_groups));
-        const uint32_t rem = (uint32_t)(item - (uint64_t)chunk * s_count * cls_groups);
-        const uint32_t s = rem / cls_groups, cls = (rem - s * cls_groups) * 32u + lane;
+        const uint32_t chunk = (uint32_t)(item / ((uint64_t)memo.s_count * cls_groups));
+        const uint32_t rem = (uint32_t)(item - (uint64_t)chunk * memo.s_count * cls_groups);
+        const uint32_t s = rem / cls_groups, cls0 = (rem - s * cls_groups) * 32u, cls = cls0 + lane;
         const int dim = (int)(chunk * 8u + warp) - 5;
         uint32_t bits = QZ_MEMO_EMPTY;
-        if (cls < ncls) {
-            const Sampler smp = sampler_start(spar, cls % cls_w, cls / cls_w, s_begin + s);
-            if (warp == 0) s_index[lane] = smp.index;
-            if (dim >= 0 && dim < (int)memo.dims) {
-                float v;
-                if (dim == 0) v = radical_inv(2, smp.index >> spar.exp0);
-                else if (dim == 1) v = radical_inv(3, smp.index / spar.scale1);
-                else v = sample_dimension(table, smp, (uint32_t)dim);
-                bits = __float_as_uint(v);
-            }
-        } else if (warp == 0) {
-            s_index[lane] = 0xffffffffu;
+        if (cls < ncls && dim >= 0 && dim < (int)memo.dims) {
+            Sampler smp;
+            smp.index = memo.cls_idx[cls] + (memo.s_begin + s) * memo.idx_stride;
+            smp.dim = 0;
+            float v;
+            if (dim == 0) v = radical_inv(2, smp.index >> spar.exp0);
+            else if (dim == 1) v = radical_inv(3, smp.index / spar.scale1);
+            else v = sample_dimension(table, smp, (uint32_t)dim);
+            bits = __float_as_uint(v);
         }
         s_val[lane][warp] = bits;
         __syncthreads();
         if (threadIdx.x < 64u) {
             const uint32_t r = threadIdx.x >> 1, half = threadIdx.x & 1u;
-            const uint32_t index = s_index[r];
-            uint32_t* row = index != 0xffffffffu ? memo_row(memo, index) : nullptr;
             const uint32_t w = word0 + chunk * 8u + half * 4u;
-            if (row && w + 4u <= memo.stride)
+            if (cls0 + r < ncls && w + 4u <= memo.stride) {
+                uint32_t* row = memo.tab + ((size_t)s * ncls + cls0 + r) * memo.stride;
                 __stcg(reinterpret_cast<uint4*>(row + w), make_uint4(s_val[r][half * 4u], s_val[r][half * 4u + 1u], s_val[r][half * 4u + 2u], s_val[r][half * 4u + 3u]));
+            }
         }
         __syncthreads();
     }

@@ -286,6 +286,7 @@ __global__ void __launch_bounds__(128, QZ_TRACE_MIN_BLOCKS) k_trace_lane(DScene 
                 QZ_CSWAP_DESC(key[2], key[4]); QZ_CSWAP_DESC(key[3], key[5]);
                 QZ_CSWAP_DESC(key[1], key[2]); QZ_CSWAP_DESC(key[3], key[4]); QZ_CSWAP_DESC(key[5], key[6]);
             }
+            // (tried: a fast path without per-entry range checks when all eight would fit the shared-memory part -- no change)
 #pragma unroll
             for (int k = 0; k < 8; k++) {
                 if (key[k]) push(make_uint2(key[k], child_base + (key[k] & 7u)));

@@ -88,6 +88,8 @@ QZ_FLAG_FORCE_BVH = 8
 QZ_FLAG_LANE_TRAVERSAL = 16   # round-1 evidence arms: rejected with QZ_ERR_INVALID
 QZ_FLAG_OCTET_TRAVERSAL = 32
 QZ_FLAG_EXACT_ARITHMETIC = 64
+QZ_FLAG_FORCE_MEMO = 128
+QZ_FLAG_NO_MEMO = 256
 
 
 @dataclass

@@ -438,6 +438,23 @@ def test_film_stays_on_the_device_for_a_denoiser(qz):
         assert (bgr8.cpu().numpy().reshape(40, 48, 3) == want).all()
 
 
+@pytest.mark.parametrize("name,w,h,spp,bounces,spp_pass", [("cornell_box", 200, 136, 6, 12, 0), ("cornell_box", 96, 80, 7, 40, 3),
+                                                            ("textures", 72, 64, 4, 8, 0), ("opposing_planes", 96, 54, 4, 24, 0),
+                                                            ("mandelbrot", 64, 48, 4, 8, 2)])
+def test_sample_memo_does_not_change_the_film(qz, mode, name, w, h, spp, bounces, spp_pass):
+    """The per-pass sample memo (csrc/sampler.cuh: sampler values and hot spectra tabulated per Halton index, read by the
+    shading kernels instead of running the digit loops / spectrum lookups per bounce) is a pure memoisation: forced on
+    (QZ_FLAG_FORCE_MEMO; real renders enable it from 65536 pixels) and forced off, the film must be the same bit for bit --
+    single and multiple passes, bounces within and beyond the memo's eight, flat and BVH scenes."""
+    from quetzalcoatlus_b200.harness import QZ_FLAG_FORCE_MEMO, QZ_FLAG_NO_MEMO
+
+    with qz.build_scene(name, w, h) as sc:
+        on, st_on = sc.render_flags(spp, bounces, flags=QZ_FLAG_FORCE_MEMO, samples_per_pass=spp_pass)
+        off, st_off = sc.render_flags(spp, bounces, flags=QZ_FLAG_NO_MEMO, samples_per_pass=spp_pass)
+    assert bits_equal(on.color, off.color).all() and bits_equal(on.normal, off.normal).all() and bits_equal(on.albedo, off.albedo).all()
+    assert (st_on["rays_closest"], st_on["rays_shadow"], st_on["shade_calls"]) == (st_off["rays_closest"], st_off["rays_shadow"], st_off["shade_calls"])
+
+
 def test_in_library_multi_gpu_render_is_bit_identical(qz):
     """Multi-GPU behind render() (qz_set_device_count / QZ_DEVICES): the scene is replicated, every device renders its
     interleaved strips and writes them into device 0's film over peer memory; the film must equal the one-GPU film bit
@@ -450,15 +467,18 @@ def test_in_library_multi_gpu_render_is_bit_identical(qz):
     for name, w, h in [("cornell_box", 96, 80), ("mandelbrot", 64, 48)]:
         with qz.build_scene(name, w, h) as sc:
             want = sc.render(spp=4, max_bounces=8)
-        qz.lib.qz_set_device_count(n)
-        try:
-            with qz.build_scene(name, w, h) as sc:
-                got = sc.render(spp=4, max_bounces=8)
-                stats = sc.last_stats()
-        finally:
-            qz.lib.qz_set_device_count(0)
-        assert stats["paths"] == w * h * 4
-        assert bits_equal(got.color, want.color).all() and bits_equal(got.normal, want.normal).all() and bits_equal(got.albedo, want.albedo).all()
+        for flags in (0, 128):   # 128 = QZ_FLAG_FORCE_MEMO: every device tabulates the pixel classes of its own strips
+            qz.lib.qz_set_device_count(n)
+            old = qz.set_default_flags(flags)
+            try:
+                with qz.build_scene(name, w, h) as sc:
+                    got = sc.render(spp=4, max_bounces=8)
+                    stats = sc.last_stats()
+            finally:
+                qz.lib.qz_set_device_count(0)
+                qz.set_default_flags(old)
+            assert stats["paths"] == w * h * 4
+            assert bits_equal(got.color, want.color).all() and bits_equal(got.normal, want.normal).all() and bits_equal(got.albedo, want.albedo).all()
 
 
 def test_error_conventions(qz):
