@@ -59,9 +59,11 @@ WORKLOADS = {
 
 
 def strip_rows_for(height: int, world: int) -> int:
-    """Rows per interleaved strip: the largest height <= 8 that gives every rank the same number of rows (round 1's fixed
-    8-row strips gave 13 vs 12 strips per rank at 800 rows over 8 GPUs: 96 % efficiency from the imbalance alone)."""
-    for rows in range(8, 0, -1):
+    """Rows per interleaved strip: a height <= 8 that gives every rank the same number of rows (round 1's fixed 8-row
+    strips gave 13 vs 12 strips per rank at 800 rows over 8 GPUs: 96 % efficiency from the imbalance alone), powers of
+    two first: with strip * world dividing 128 a rank owns 1/world of the (y mod 128) pixel classes and its sample memo
+    tabulates only those (csrc/sampler.cuh); 5-row strips over 8 ranks touch all 128 and the fill costs 8 x as much."""
+    for rows in (8, 4, 2, 1, 7, 6, 5, 3):
         if height % rows == 0 and (height // rows) % world == 0:
             return rows
     return 1

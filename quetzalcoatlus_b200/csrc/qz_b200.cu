@@ -272,6 +272,9 @@ struct WorkMem {
     DevBuf rec_hot, rec_side, qbufs[8], q_late, tags[3], counters, statsb, res_a, res_b, res_c, rowsb, sensor, acc, memo, memo_rank, memo_idx;
     uint32_t pool = 0;
     uint64_t cells = 0, acc_pix = 0, rows = 0;
+    std::vector<uint32_t> cls_rank, cls_idx;   // pixel classes of the last render's image size and region (sample memo)
+    uint64_t cls_key[5] = {};
+    bool cls_uploaded = false;
     uint32_t* h_counters = nullptr;  // pinned
     DevBuf film[3];                  // device film planes of the host-buffer entry (qz_render)
     bool film_valid[3] = {false, false, false};
@@ -326,9 +329,11 @@ void destroy_replicas(qz_scene_t* s) {
     s->replicas.clear();
     cudaSetDevice(s->device);
 }
-// rows per interleaved strip: the largest height <= 8 that gives every device the same number of rows
+// rows per interleaved strip: a height <= 8 that gives every device the same number of rows, powers of two first (with
+// strip * n dividing 128 a device owns 1/n of the (y mod 128) pixel classes: its sample memo tabulates only those)
 uint32_t balanced_strip_rows(uint32_t height, uint32_t n) {
-    for (uint32_t rows = 8; rows >= 1; rows--)
+    const uint32_t order[8] = {8, 4, 2, 1, 7, 6, 5, 3};
+    for (uint32_t rows : order)
         if (height % rows == 0 && (height / rows) % n == 0) return rows;
     return 1;
 }
@@ -501,18 +506,29 @@ static int render_impl(qz_scene s, const qz_camera* camera, uint32_t n_samples, 
     // bounces' worth of dimensions (later bounces go through the sampler stage).
     static const int env_memo = [] { const char* e = std::getenv("QZ_MEMO"); return e ? std::atoi(e) : 1; }();
     uint32_t memo_dims = 0, memo_stride = 0, memo_dim_off = 0;
-    std::vector<uint32_t> cls_rank, cls_idx;   // (x mod 128, y mod 128) classes the call owns (sampler.cuh, SampleMemo)
+    // (x mod 128, y mod 128) classes the call owns (sampler.cuh, SampleMemo): a function of the image size and the region
+    // only, kept with the handle between calls (host: 16 k sampler_start evaluations, ~1.5 ms -- 10 % of a textures frame)
+    std::vector<uint32_t>& cls_rank = s->work.cls_rank;
+    std::vector<uint32_t>& cls_idx = s->work.cls_idx;
+    bool cls_fresh = false;
     if ((env_memo || (flags & QZ_FLAG_FORCE_MEMO)) && !(flags & QZ_FLAG_NO_MEMO)) {
-        bool own_py[QZ_MAX_HALTON_RESOLUTION] = {};
-        for (uint32_t r : rows) own_py[(H - 1u - r) & (QZ_MAX_HALTON_RESOLUTION - 1)] = true;
-        cls_rank.assign(spar.stride, 0xffffffffu);
-        const uint32_t cw = std::min<uint32_t>(W, QZ_MAX_HALTON_RESOLUTION);
-        for (uint32_t py = 0; py < QZ_MAX_HALTON_RESOLUTION; py++) {
-            if (!own_py[py]) continue;
-            for (uint32_t px = 0; px < cw; px++) {
-                const uint32_t idx = sampler_start(spar, px, py, 0).index;
-                if (cls_rank[idx] == 0xffffffffu) { cls_rank[idx] = (uint32_t)cls_idx.size(); cls_idx.push_back(idx); }
+        const uint64_t key[5] = {((uint64_t)W << 32) | H, region ? region->strip_rows : 0u, region ? region->n_shards : 0u, region ? region->shard : 0u, spar.stride};
+        if (cls_rank.empty() || std::memcmp(key, s->work.cls_key, sizeof(key)) != 0) {
+            bool own_py[QZ_MAX_HALTON_RESOLUTION] = {};
+            for (uint32_t r : rows) own_py[(H - 1u - r) & (QZ_MAX_HALTON_RESOLUTION - 1)] = true;
+            cls_rank.assign(spar.stride, 0xffffffffu);
+            cls_idx.clear();
+            const uint32_t cw = std::min<uint32_t>(W, QZ_MAX_HALTON_RESOLUTION);
+            for (uint32_t py = 0; py < QZ_MAX_HALTON_RESOLUTION; py++) {
+                if (!own_py[py]) continue;
+                for (uint32_t px = 0; px < cw; px++) {
+                    const uint32_t idx = sampler_start(spar, px, py, 0).index;
+                    if (cls_rank[idx] == 0xffffffffu) { cls_rank[idx] = (uint32_t)cls_idx.size(); cls_idx.push_back(idx); }
+                }
             }
+            std::memcpy(s->work.cls_key, key, sizeof(key));
+            cls_fresh = true;
+            s->work.cls_uploaded = false;   // (the device copies belong to the previous key until this one is uploaded)
         }
         const uint64_t n_cls = cls_idx.size();
         if ((flags & QZ_FLAG_FORCE_MEMO) || (n_pix64 >= 4 * n_cls && n_pix64 >= 65536)) {
@@ -576,10 +592,14 @@ static int render_impl(qz_scene s, const qz_camera* camera, uint32_t n_samples, 
     // and eight bounces' worth of dimensions (later bounces evaluate directly), within a 2 GB budget.
     if (memo_dims) {
         QZ_CUDA(wm.memo.reserve((size_t)memo_stride * 4 * s_pass * cls_idx.size()));
+        const bool realloc = wm.memo_rank.bytes < cls_rank.size() * 4 || wm.memo_idx.bytes < cls_idx.size() * 4 || !wm.memo_rank.p || !wm.memo_idx.p;
         QZ_CUDA(wm.memo_rank.reserve(cls_rank.size() * 4));
         QZ_CUDA(wm.memo_idx.reserve(cls_idx.size() * 4));
-        QZ_CUDA(cudaMemcpyAsync(wm.memo_rank.p, cls_rank.data(), cls_rank.size() * 4, cudaMemcpyHostToDevice, stream));
-        QZ_CUDA(cudaMemcpyAsync(wm.memo_idx.p, cls_idx.data(), cls_idx.size() * 4, cudaMemcpyHostToDevice, stream));
+        if (cls_fresh || realloc || !wm.cls_uploaded) {
+            QZ_CUDA(cudaMemcpyAsync(wm.memo_rank.p, cls_rank.data(), cls_rank.size() * 4, cudaMemcpyHostToDevice, stream));
+            QZ_CUDA(cudaMemcpyAsync(wm.memo_idx.p, cls_idx.data(), cls_idx.size() * 4, cudaMemcpyHostToDevice, stream));
+            wm.cls_uploaded = true;
+        }
     }
     const bool multi_pass = s_pass < n_samples;
     if (multi_pass) QZ_CUDA(acc.reserve((size_t)n_pix * 9 * 4));
