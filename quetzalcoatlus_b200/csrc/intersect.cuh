@@ -213,6 +213,96 @@ QZ_HD void flat_prim_test(const DScene& sc, const FlatPrim& f, uint32_t slot, V3
     }
 }
 
+// LAZY variant for the flat kernel's closest-hit loop.  A hit costs three IEEE divisions (t, u, v) and a normal, but a ray
+// keeps only its closest hit: per candidate only t is computed (the order needs it, rounded exactly as the reference's
+// quotient), the barycentric numerators stay as they are, and u, v, Ng, the ids are produced ONCE per ray by
+// flat_best_finish() with the very expressions of tri_test_pre / sphere_test_rd2 / flat_prim_test -- same bits.  In the
+// lock-step loop the three divisions ran for the few lanes that had just hit something: a tenth of the kernel's
+// instructions at 4-8 of 32 lanes (profiles/r02_source_k_step_flat.txt).
+struct FlatBest {
+    float t, U, V, absDen;
+    uint32_t info;   // staged primitive index | 0x100 second triangle of the quad | 0x200 sphere; 0xffffffff = miss
+    uint32_t key;
+};
+#define QZ_FB_FLIP 0x100u
+#define QZ_FB_SPHERE 0x200u
+
+// tri_test_pre up to the distance: true = valid hit, t = T / absDen
+QZ_HD bool tri_test_lazy(V3 O, V3 D, float tnear, float tfar, V3 v0, V3 e1, V3 e2, V3 ng, float& t, float& Uo, float& Vo, float& absDen_o) {
+    V3 C = v0 - O;
+    V3 R = cross(C, D);
+    float den = dot(ng, D);
+    float absDen = fabsf(den);
+    uint32_t s = float_as_u32(den) & 0x80000000u;
+    float U = xor_sign(dot(R, e2), s);
+    float V = xor_sign(dot(R, e1), s);
+    if (!(den != 0.0f) || !(U >= 0.0f) || !(V >= 0.0f) || !(U + V <= absDen)) return false;
+    float T = xor_sign(dot(ng, C), s);
+    if (!(absDen * tnear < T) || !(T <= absDen * tfar)) return false;
+    t = T / absDen;
+    Uo = U; Vo = V; absDen_o = absDen;
+    return true;
+}
+
+QZ_HD void flat_prim_test_lazy(const FlatPrim& f, uint32_t slot, V3 O, V3 D, float rd2, float tnear, float tfar, FlatBest& best) {
+    const uint32_t w2 = float_as_u32(f.e1a.w);
+    const uint32_t kind = prim_kind(w2);
+    float t = 0.0f, U = 0.0f, V = 0.0f, absDen = 0.0f;
+    uint32_t info = slot;
+    bool found = false;
+    if (kind == QZ_PRIM_SPHERE) {
+        PrimHit h;
+        found = sphere_test_rd2(O, D, rd2, tnear, tfar, xyz(f.a), f.b.x, h);
+        t = h.t;
+        info |= QZ_FB_SPHERE;
+    } else {
+        float ta, Ua, Va, da, tb, Ub, Vb, db;
+        const bool fa = tri_test_lazy(O, D, tnear, tfar, xyz(f.a), xyz(f.e1a), xyz(f.e2a), xyz(f.nga), ta, Ua, Va, da);
+        const bool fb = kind != QZ_PRIM_TRIANGLE && f.c.w != 0.0f &&
+                        tri_test_lazy(O, D, tnear, tfar, xyz(f.c), xyz(f.e1b), xyz(f.e2b), v3(f.nga.w, f.e1b.w, f.e2b.w), tb, Ub, Vb, db);
+        if (fa && (!fb || ta <= tb)) { t = ta; U = Ua; V = Va; absDen = da; found = true; }
+        else if (fb) { t = tb; U = Ub; V = Vb; absDen = db; info |= QZ_FB_FLIP; found = true; }
+    }
+    if (!found) return;
+    const uint32_t key = prim_key(w2);
+    if (t < best.t || (t == best.t && key < best.key)) {
+        best.t = t; best.U = U; best.V = V; best.absDen = absDen; best.info = info; best.key = key;
+    }
+}
+
+// the full hit record of the winner (prims = the staged FlatPrim list the loop ran over)
+QZ_HD void flat_best_finish(const DScene& sc, const FlatPrim* prims, const FlatBest& fb, V3 O, V3 D, float rd2, float tnear, float tfar, Hit& out) {
+    out.t = INFINITY; out.u = 0.0f; out.v = 0.0f; out.prim = QZ_NO_HIT; out.key = 0xffffffffu;
+    out.ng = v3(0.0f, 0.0f, 0.0f); out.geom_id = QZ_NO_HIT; out.prim_id = 0;
+    if (fb.info == 0xffffffffu) return;
+    const uint32_t p = fb.info & 0xffu;
+    const FlatPrim& f = prims[p];
+    out.t = fb.t; out.prim = p; out.key = fb.key;
+    out.geom_id = float_as_u32(f.a.w); out.prim_id = float_as_u32(f.b.w);
+    if (fb.info & QZ_FB_SPHERE) {
+        PrimHit h;
+        sphere_test_rd2(O, D, rd2, tnear, tfar, xyz(f.a), f.b.x, h);   // the same call that found it: same t, and its normal
+        out.ng = h.ng;
+        return;
+    }
+    const bool flip = (fb.info & QZ_FB_FLIP) != 0u;
+    if (flip) {
+        out.u = (fb.absDen - fb.U) / fb.absDen;
+        out.v = (fb.absDen - fb.V) / fb.absDen;
+        out.ng = v3(f.nga.w, f.e1b.w, f.e2b.w);
+    } else {
+        out.u = fb.U / fb.absDen;
+        out.v = fb.V / fb.absDen;
+        out.ng = xyz(f.nga);
+    }
+    if (prim_kind(float_as_u32(f.e1a.w)) == QZ_PRIM_GRIDCELL) {
+        const uint32_t cell = float_as_u32(f.e2a.w);
+        const uint32_t dims = sc.grid_dims[float_as_u32(f.a.w)];
+        out.u = ((float)(cell & 0xffffu) + out.u) / (float)(dims & 0xffffu);
+        out.v = ((float)(cell >> 16) + out.v) / (float)(dims >> 16);
+    }
+}
+
 QZ_HD void prim_test(const DScene& sc, uint32_t slot, V3 O, V3 D, float tnear, float tfar, Hit& best) {
     const F4* rec = sc.prims + (size_t)slot * 4;
     const F4 a = load_f4(rec), b = load_f4(rec + 1), c = load_f4(rec + 2), d = load_f4(rec + 3);

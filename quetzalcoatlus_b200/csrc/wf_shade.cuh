@@ -162,6 +162,9 @@ __global__ void __launch_bounds__(256) k_memo_spectra(DScene sc) {
 template <int KH>
 __global__ void __launch_bounds__(128, (KH == KH_DIFFUSE || KH == KH_DIELECTRIC) ? QZ_SHADE_MIN_BLOCKS_LIGHT : QZ_SHADE_MIN_BLOCKS_HEAVY)
 k_shade(DScene sc, WfBuffers b, uint32_t max_bounces) {
+    // (tried: a second, lean kernel over the run-time-dispatch queue for the hits without a material -- misses, emitter
+    // geometry -- next to the MixedMaterial one: 80 registers instead of 128, but one more launch and two walks over the
+    // queue; shading stage 45.1 -> 47.0 ms on cornell_box, 13.1 -> 16.6 on mandelbrot: dropped)
     constexpr int FAM = KH == KH_DIFFUSE ? SQ_DIFFUSE : (KH == KH_CONDUCTOR ? SQ_CONDUCTOR : (KH == KH_DIELECTRIC ? SQ_DIELECTRIC : SQ_MISC));
     const uint32_t n_first = b.counters[C_SHADE0 + SQ_FAMILIES + FAM];
     const uint32_t count = n_first + b.counters[C_SHADE0 + FAM];
@@ -472,12 +475,14 @@ __global__ void __launch_bounds__(128, 4) k_step_flat(DScene sc, DCamera cam, Wf
             n_closest++;
             const V3 O = v3(ro.x, ro.y, ro.z), D = v3(rd.x, rd.y, rd.z);
             const float rd2 = 1.0f / dot(D, D);
-            Hit best;
-            best.t = INFINITY; best.u = 0.0f; best.v = 0.0f; best.prim = QZ_NO_HIT; best.key = 0xffffffffu;
-            best.ng = v3(0.0f, 0.0f, 0.0f); best.geom_id = QZ_NO_HIT; best.prim_id = 0;
+            // (per candidate only the distance; u, v, Ng of the winner once per ray: intersect.cuh, FlatBest)
+            FlatBest fbest;
+            fbest.t = INFINITY; fbest.U = 0.0f; fbest.V = 0.0f; fbest.absDen = 0.0f; fbest.info = 0xffffffffu; fbest.key = 0xffffffffu;
 #pragma unroll 1
             for (uint32_t p = 0; p < n_prims; p++)
-                flat_prim_test(sc, s_prims[p], p, O, D, rd2, QZ_TNEAR, INFINITY, best);
+                flat_prim_test_lazy(s_prims[p], p, O, D, rd2, QZ_TNEAR, INFINITY, fbest);
+            Hit best;
+            flat_best_finish(sc, s_prims, fbest, O, D, rd2, QZ_TNEAR, INFINITY, best);
             b.hit_a.set(slot, f4(best.t, best.u, best.v, __uint_as_float(best.prim_id)));
             b.hit_b.set(slot, f4(best.ng.x, best.ng.y, best.ng.z, __uint_as_float(best.geom_id)));
             const bool unsorted = (flags & QZ_FLAG_UNSORTED_SHADING) != 0;

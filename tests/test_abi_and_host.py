@@ -137,3 +137,43 @@ def test_obj_loader_semantics(emu, oracle, tmp_path):
         with emu.build_scene("obj_viewer", 32, 24, **kw) as se, oracle.build_scene("obj_viewer", 32, 24, **kw) as so:
             xys = pixel_samples(so, 600, seed=2)
             assert bits_equal(se.trace_paths(xys), so.trace_paths(xys)).all(), path.name
+
+
+def test_strip_rows_are_balanced_and_keep_a_shard_on_its_own_pixel_classes():
+    """bench.py / qz_render's multi-GPU strips: every rank owns the same number of rows, and where a power-of-two height
+    does that, strip * ranks divides 128 -- a rank then owns 1/ranks of the (y mod 128) pixel classes, which is what its
+    sample memo tabulates (csrc/sampler.cuh).  5-row strips over 8 ranks were balanced too, but touched all 128."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("bench", ROOT / "bench.py")
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    for height in (800, 600, 1080, 2160, 96, 54):
+        for world in (1, 2, 4, 8):
+            rows = bench.strip_rows_for(height, world)
+            owned = [sum(1 for r in range(height) if (r // rows) % world == k) for k in range(world)]
+            if height % world == 0:
+                assert max(owned) == min(owned), (height, world, rows, owned)
+            if height % (world * rows) == 0 and rows in (1, 2, 4, 8):
+                classes = {(height - 1 - r) % 128 for r in range(height) if (r // rows) % world == 0}
+                assert len(classes) <= 128 // world, (height, world, rows, len(classes))
+    assert bench.strip_rows_for(800, 8) == 4 and bench.strip_rows_for(2160, 8) == 2 and bench.strip_rows_for(800, 4) == 8
+
+
+def test_reference_arm_of_the_bench_runs_on_the_cpu(tmp_path):
+    """`bench.py --impl reference` (the reference integrator over the oracle, host cores only) prints ONE JSON line with the
+    keys the driver reads, on a box without a GPU."""
+    import json
+    import sys
+
+    lib = ROOT / "oracle" / "_ref" / "liboracle_ref.so"
+    if not lib.exists():
+        pytest.skip("oracle/_ref not built")
+    out = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--width", "48",
+                          "--height", "40"], capture_output=True, text=True, timeout=300, cwd=tmp_path)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, out.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "Mpaths/s" and d["value"] > 0 and d["cpu_baseline"]["kind"] == "reference"
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
