@@ -200,6 +200,7 @@ __global__ void __launch_bounds__(256) k_memo_fill(const SamplerDim* __restrict_
             else v = sample_dimension(table, smp, (uint32_t)dim);
             bits = __float_as_uint(v);
         }
+        // (tried: every lane storing its own word, no transpose and no barrier, leaving the merge to L2 -- step 91.5 -> 92.3 ms)
         s_val[lane][warp] = bits;
         __syncthreads();
         if (threadIdx.x < 64u) {
