@@ -353,14 +353,16 @@ def run_ours(args) -> None:
         for _ in range(warmup):
             step()
         barrier()
-        clocks = ClockSampler(local_rank)
-        clocks.start()
+        # (rank 0 samples its own GPU: NVML queries take a driver lock that every rank's launches go through)
+        clocks = ClockSampler(local_rank) if rank == 0 else None
+        if clocks:
+            clocks.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         stats = [step() for _ in range(steps)]
         e1.record(stream)
         barrier()
-        clock_info = clocks.stop()
+        clock_info = clocks.stop() if clocks else {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": "rank 0 only"}
         ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
