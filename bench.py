@@ -238,6 +238,18 @@ def run_reference(args) -> None:
     }))
 
 
+def mesh_first_hit_fraction(sc, width: int, height: int) -> float:
+    """obj_viewer: the share of camera rays (pixel centres, every 4th pixel of every 4th row) whose closest hit is the mesh
+    (geomID 0: the OBJ is the scene's first geometry) -- through the closest-hit probe of the C ABI (qz_intersect)."""
+    cf = sc.camera_fields()
+    pos, bl, du, dv = cf[0], cf[4], cf[5], cf[6]
+    xs, ys = np.meshgrid(np.arange(0, width, 4, dtype=np.float32) + 0.5, np.arange(0, height, 4, dtype=np.float32) + 0.5)
+    d = bl[None, :] + du[None, :] * xs.reshape(-1, 1) + dv[None, :] * ys.reshape(-1, 1) - pos[None, :]
+    rays = np.concatenate([np.broadcast_to(pos, d.shape), d], 1).astype(np.float32)
+    hit = sc.intersect(rays)
+    return float(((hit[:, 0] >= 0) & (hit[:, 6] == 0)).mean())
+
+
 def load_counters() -> dict:
     """ncu counters per unit of work (profiles/r02_counters.json, written by tools/ncu_counters.py from the committed
     steady-state captures): DRAM bytes, L2 bytes and executed warp instructions per ray / per shaded bounce, per scene."""
@@ -371,7 +383,9 @@ def run_ours(args) -> None:
                              float(sum(s["kernel_launches"] for s in stats))], device="cuda", dtype=torch.float64)
         if world > 1:
             dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+        mesh_frac = mesh_first_hit_fraction(sc, width, height) if WORKLOADS[workload][0] == "obj_viewer" and rank == 0 else None
         out = {"workload": workload, "scene": WORKLOADS[workload][0], "width": width, "height": height, "spp": spp, "max_bounces": mb,
+               "mesh_first_hit_fraction": mesh_frac,
                "strip_rows": strip_rows, "ms_per_step": ms_total / steps, "value": width * height * spp * steps / (ms_total * 1e-3) / 1e6,
                "mrays_per_s": float(sums[0].item()) / (ms_total * 1e-3) / 1e6, "gpu_launches": int(sums[1].item()),
                "clocks": clock_info, "build": build}
@@ -466,6 +480,7 @@ def run_ours(args) -> None:
                              "bvh_build_ms": m["build"].get("bvh_build_ms")}
             if wl == "obj_viewer":
                 secondary[wl]["config"]["mesh_triangles"] = args.mesh_triangles
+                secondary[wl]["mesh_first_hit_fraction"] = m["mesh_first_hit_fraction"]
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -484,7 +499,8 @@ def run_ours(args) -> None:
             "gpu_launches": head["gpu_launches"],
             "e2e": head["e2e"], "roofline": head["roofline"], "cpu_baseline": cpu, "clocks": head["clocks"],
             "bvh_build_ms": head["build"].get("bvh_build_ms"), "obj_parse_ms": head["build"].get("obj_parse_ms"),
-            "secondary": secondary, **head["extra"],
+            "secondary": secondary, **({"mesh_first_hit_fraction": head["mesh_first_hit_fraction"]} if head["mesh_first_hit_fraction"] is not None else {}),
+            **head["extra"],
         }))
     if world > 1:
         dist.destroy_process_group()
