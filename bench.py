@@ -126,7 +126,7 @@ class ClockSampler(threading.Thread):
                         self.samples.append([f.strip() for f in out.split(",")])
             except Exception:
                 pass
-            self._stop_evt.wait(0.5)
+            self._stop_evt.wait(0.15 if self._nvml is not None else 0.5)
 
     def stop(self) -> dict:
         self._stop_evt.set()
