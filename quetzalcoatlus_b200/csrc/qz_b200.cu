@@ -664,7 +664,8 @@ static int render_impl(qz_scene s, const qz_camera* camera, uint32_t n_samples, 
         qzl::Stage& g = stg[p];
         g.scene = &sc; g.cam = &cam; g.bufs = &bufs[p]; g.pass = &pp_cur;
         g.flags = flags; g.max_bounces = max_bounces;
-        g.lean_blocks = n_sm * (env_lean > 0 ? env_lean : per_sm);
+        // (the lean stages with fewer CTAs than the others when three pipelines share the SMs: +1 % on cornell_box)
+        g.lean_blocks = n_sm * (env_lean > 0 ? env_lean : (P == 3 ? 2 : per_sm));
         g.shade_blocks = n_sm * per_sm;   // persistent CTAs of 4 warps
         g.trav_blocks = n_sm * per_sm;
         g.bin_blocks = (int)std::min<uint32_t>((sub_pool + 2047u) / 2048u, (uint32_t)n_sm * 8u);
