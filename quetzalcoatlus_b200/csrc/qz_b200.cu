@@ -21,6 +21,7 @@
 #include <vector>
 
 #include "launch.h"
+#include "memo_plan.h"
 #include "scene_store.cuh"
 #include "wf_types.cuh"
 
@@ -514,28 +515,16 @@ static int render_impl(qz_scene s, const qz_camera* camera, uint32_t n_samples, 
     if ((env_memo || (flags & QZ_FLAG_FORCE_MEMO)) && !(flags & QZ_FLAG_NO_MEMO)) {
         const uint64_t key[5] = {((uint64_t)W << 32) | H, region ? region->strip_rows : 0u, region ? region->n_shards : 0u, region ? region->shard : 0u, spar.stride};
         if (cls_rank.empty() || std::memcmp(key, s->work.cls_key, sizeof(key)) != 0) {
-            bool own_py[QZ_MAX_HALTON_RESOLUTION] = {};
-            for (uint32_t r : rows) own_py[(H - 1u - r) & (QZ_MAX_HALTON_RESOLUTION - 1)] = true;
-            cls_rank.assign(spar.stride, 0xffffffffu);
-            cls_idx.clear();
-            const uint32_t cw = std::min<uint32_t>(W, QZ_MAX_HALTON_RESOLUTION);
-            for (uint32_t py = 0; py < QZ_MAX_HALTON_RESOLUTION; py++) {
-                if (!own_py[py]) continue;
-                for (uint32_t px = 0; px < cw; px++) {
-                    const uint32_t idx = sampler_start(spar, px, py, 0).index;
-                    if (cls_rank[idx] == 0xffffffffu) { cls_rank[idx] = (uint32_t)cls_idx.size(); cls_idx.push_back(idx); }
-                }
-            }
+            memo_owned_classes(spar, W, H, rows, cls_rank, cls_idx);
             std::memcpy(s->work.cls_key, key, sizeof(key));
             cls_fresh = true;
             s->work.cls_uploaded = false;   // (the device copies belong to the previous key until this one is uploaded)
         }
         const uint64_t n_cls = cls_idx.size();
         if ((flags & QZ_FLAG_FORCE_MEMO) || (n_pix64 >= 4 * n_cls && n_pix64 >= 65536)) {
-            memo_dim_off = ((4u * QZ_MEMO_MAX_HOT + 7u) & ~7u) + 5u;          // hot spectra block, then dimension 3 on a sector boundary
             static const int env_memo_bounces = [] { const char* e = std::getenv("QZ_MEMO_BOUNCES"); int v = e ? std::atoi(e) : 0; return v; }();
-            memo_dims = 3 + 8 * (uint32_t)(env_memo_bounces > 0 ? std::min(env_memo_bounces, 32) : 8);
-            memo_stride = (memo_dim_off + memo_dims + 7u) & ~7u;
+            const MemoLayout lay = memo_layout((uint32_t)(env_memo_bounces > 0 ? std::min(env_memo_bounces, 32) : 8));
+            memo_dim_off = lay.dim_off, memo_dims = lay.dims, memo_stride = lay.stride;
             // a pass must also fit its rows into the memo's budget (3 GB)
             const uint64_t rows_fit = (3ull << 30) / ((uint64_t)memo_stride * 4 * n_cls);
             if (rows_fit == 0) memo_dims = 0;
@@ -587,10 +576,7 @@ static int render_impl(qz_scene s, const qz_camera* camera, uint32_t n_samples, 
     QZ_CUDA(res_c.reserve(cells * 4));
     QZ_CUDA(rowsb.reserve(rows.size() * 4));
     QZ_CUDA(sensor.reserve(3 * 471 * 4));
-    // SAMPLE MEMO (sampler.cuh): worth its memset when several pixels share a Halton index, i.e. when the call owns
-    // several times more pixels than there are (x mod 128, y mod 128) classes.  Rows: the jitter, the wavelength draw
-    // and eight bounces' worth of dimensions (later bounces evaluate directly), within a 2 GB budget.
-    if (memo_dims) {
+    if (memo_dims) {   // the pass's memo rows and the class tables the kernels address them through
         QZ_CUDA(wm.memo.reserve((size_t)memo_stride * 4 * s_pass * cls_idx.size()));
         const bool realloc = wm.memo_rank.bytes < cls_rank.size() * 4 || wm.memo_idx.bytes < cls_idx.size() * 4 || !wm.memo_rank.p || !wm.memo_idx.p;
         QZ_CUDA(wm.memo_rank.reserve(cls_rank.size() * 4));
@@ -765,18 +751,9 @@ static int render_impl(qz_scene s, const qz_camera* camera, uint32_t n_samples, 
         pp.spar = spar;
         pp_cur = pp;
         if (memo_dims) {
-            sc.memo.tab = wm.memo.as<uint32_t>();
-            sc.memo.dims = memo_dims;
-            sc.memo.n_cls = (uint32_t)cls_idx.size();
-            sc.memo.s_begin = s_begin;
-            sc.memo.s_count = pp.s_count;
-            sc.memo.stride = memo_stride;
-            sc.memo.dim_off = memo_dim_off;
-            sc.memo.idx_stride = spar.stride;
-            sc.memo.idx_magic = (uint32_t)((1ull << 32) / spar.stride);
-            sc.memo.cls_rank = wm.memo_rank.as<uint32_t>();
-            sc.memo.cls_idx = wm.memo_idx.as<uint32_t>();
-            sc.memo.n_hot = 0;   // (set after the fill: k_memo_spectra itself must evaluate, not look up)
+            // (n_hot is set after the fill: k_memo_spectra itself must evaluate, not look up)
+            sc.memo = memo_describe(MemoLayout{memo_dim_off, memo_dims, memo_stride}, spar, wm.memo.as<uint32_t>(), wm.memo_rank.as<uint32_t>(),
+                                    wm.memo_idx.as<uint32_t>(), (uint32_t)cls_idx.size(), s_begin, pp.s_count);
             QZ_RENDER_CUDA(cudaMemsetAsync(sc.memo.tab, 0xff, (size_t)memo_stride * 4 * pp.s_count * cls_idx.size(), stream));
             qzl::memo_fill(sc.sampler_table, &spar, &sc.memo, n_sm * 8, stream);
             st.kernel_launches++;

@@ -290,6 +290,20 @@ QZ_HD V2 sampler_pixel_jitter_memo(const SamplerParams& sp, const SampleMemo& m,
     return j;
 }
 
+// what the eager fill (wf_stage.cuh: k_memo_fill) stores for dimension `dim` of the row (sample number s_begin + s, class
+// `cls`): the two radical inverses of the pixel jitter for dimensions 0 and 1, the Owen-scrambled value otherwise
+QZ_HD uint32_t memo_entry_bits(const SamplerDim* __restrict__ table, const SamplerParams& spar, const SampleMemo& m, uint32_t s, uint32_t cls,
+                               uint32_t dim) {
+    Sampler smp;
+    smp.index = m.cls_idx[cls] + (m.s_begin + s) * m.idx_stride;
+    smp.dim = 0;
+    float v;
+    if (dim == 0) v = radical_inv(2, smp.index >> spar.exp0);
+    else if (dim == 1) v = radical_inv(3, smp.index / spar.scale1);
+    else v = sample_dimension(table, smp, dim);
+    return float_as_u32(v);
+}
+
 // two independent dimensions evaluated in one loop: the digit chains of the two dimensions do
 // not depend on each other, so interleaving them doubles the instruction-level parallelism of
 // what is otherwise one long dependent integer chain per digit

@@ -61,17 +61,37 @@ QZ_HD V2 sphere_uv(V3 n) {
 // emission, the conductors' eta and k): the four values depend on the Halton index only and sit in the path's memo
 // row, computed once per index by k_memo_spectra with this very function -- the same bits as evaluating here.
 QZ_HD Spec4 from_spectrum_path(const DScene& sc, uint32_t index, int32_t id, const Spec4& lambda) {
-#if defined(__CUDA_ARCH__)
     if (sc.memo.n_hot) {
         const int slot = memo_hot_slot(sc.memo, id);
         const uint32_t* row = memo_row(sc.memo, index);
         if (slot >= 0 && row) {
+#if defined(__CUDA_ARCH__)
             const float4 v = __ldcg(reinterpret_cast<const float4*>(row) + slot);
             return spec4(v.x, v.y, v.z, v.w);
+#else
+            const uint32_t* w = row + 4 * slot;   // (host emulation, tests/emu)
+            return spec4(u32_as_float(w[0]), u32_as_float(w[1]), u32_as_float(w[2]), u32_as_float(w[3]));
+#endif
         }
     }
-#endif
     return from_spectrum(sc, id, lambda);
+}
+
+// The hot-spectra block of one memo row (wf_shade.cuh: k_memo_spectra): the row's wavelengths come from its dimension-2
+// value exactly as in start_path; every hot spectrum is evaluated by from_spectrum, which never consults the memo.
+QZ_HD void memo_fill_hot(const DScene& sc, uint32_t* row) {
+    const SampleMemo& memo = sc.memo;
+    const float ul = u32_as_float(memo_load(row + memo.dim_off + 2));
+    Spec4 lambda, pdf;
+    sample_wavelengths(ul, lambda, pdf);
+    for (uint32_t k = 0; k < memo.n_hot; k++) {
+        const Spec4 v = from_spectrum(sc, memo.hot_id[k], lambda);
+#if defined(__CUDA_ARCH__)
+        __stcg(reinterpret_cast<float4*>(row) + k, make_float4(v.v[0], v.v[1], v.v[2], v.v[3]));
+#else
+        for (int c = 0; c < 4; c++) row[4 * k + c] = float_as_u32(v.v[c]);
+#endif
+    }
 }
 
 // Texture::value (texture.cpp)

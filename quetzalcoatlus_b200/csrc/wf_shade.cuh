@@ -136,14 +136,7 @@ __global__ void __launch_bounds__(256) k_memo_spectra(DScene sc) {
     const SampleMemo& memo = sc.memo;
     const uint64_t total = (uint64_t)memo.s_count * memo.n_cls;
     for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (uint64_t)gridDim.x * blockDim.x) {
-        uint32_t* row = memo.tab + (size_t)t * memo.stride;
-        const float ul = __uint_as_float(__ldcg(row + memo.dim_off + 2));
-        Spec4 lambda, pdf;
-        sample_wavelengths(ul, lambda, pdf);
-        for (uint32_t k = 0; k < memo.n_hot; k++) {
-            const Spec4 v = from_spectrum(sc, memo.hot_id[k], lambda);
-            __stcg(reinterpret_cast<float4*>(row) + k, f4(v));
-        }
+        memo_fill_hot(sc, memo.tab + (size_t)t * memo.stride);
     }
 }
 

@@ -190,16 +190,7 @@ __global__ void __launch_bounds__(256) k_memo_fill(const SamplerDim* __restrict_
         const uint32_t s = rem / cls_groups, cls0 = (rem - s * cls_groups) * 32u, cls = cls0 + lane;
         const int dim = (int)(chunk * 8u + warp) - 5;
         uint32_t bits = QZ_MEMO_EMPTY;
-        if (cls < ncls && dim >= 0 && dim < (int)memo.dims) {
-            Sampler smp;
-            smp.index = memo.cls_idx[cls] + (memo.s_begin + s) * memo.idx_stride;
-            smp.dim = 0;
-            float v;
-            if (dim == 0) v = radical_inv(2, smp.index >> spar.exp0);
-            else if (dim == 1) v = radical_inv(3, smp.index / spar.scale1);
-            else v = sample_dimension(table, smp, (uint32_t)dim);
-            bits = __float_as_uint(v);
-        }
+        if (cls < ncls && dim >= 0 && dim < (int)memo.dims) bits = memo_entry_bits(table, spar, memo, s, cls, (uint32_t)dim);
         // (tried: every lane storing its own word, no transpose and no barrier, leaving the merge to L2 -- step 91.5 -> 92.3 ms)
         s_val[lane][warp] = bits;
         __syncthreads();

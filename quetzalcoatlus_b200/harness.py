@@ -199,15 +199,18 @@ class Scene:
         self._h._fn("camera")(self._handle, ctypes.byref(cam))
         return cam
 
-    def render_flags(self, spp: int, max_bounces: int | None = None, flags: int = 0, pool: int = 0, samples_per_pass: int = 0):
-        """qz_render through the raw C ABI with explicit render options; returns (RenderOutput, stats)."""
+    def render_flags(self, spp: int, max_bounces: int | None = None, flags: int = 0, pool: int = 0, samples_per_pass: int = 0,
+                     region: tuple[int, int, int] | None = None, reserved: int = 0):
+        """qz_render through the raw C ABI with explicit render options; returns (RenderOutput, stats).
+        region = (strip_rows, n_shards, shard): rows of other shards keep their zeros."""
         max_bounces = self.default_max_bounces if max_bounces is None else max_bounces
         shape = (self.height, self.width, 3)
         color, normal, albedo = (np.zeros(shape, np.float32) for _ in range(3))
-        cam, st, opts = self.c_camera(), QzStats(), QzRenderOptions(flags, pool, samples_per_pass, 0)
+        cam, st, opts = self.c_camera(), QzStats(), QzRenderOptions(flags, pool, samples_per_pass, reserved)
+        reg = ctypes.byref(QzRegion(*region)) if region else None
         lib = self._h.lib
         lib.qz_render.restype = ctypes.c_int
-        rc = lib.qz_render(ctypes.c_void_p(self.c_scene_handle()), ctypes.byref(cam), spp, max_bounces, None, ctypes.byref(opts),
+        rc = lib.qz_render(ctypes.c_void_p(self.c_scene_handle()), ctypes.byref(cam), spp, max_bounces, reg, ctypes.byref(opts),
                            color.ctypes.data_as(ctypes.c_void_p), normal.ctypes.data_as(ctypes.c_void_p),
                            albedo.ctypes.data_as(ctypes.c_void_p), ctypes.byref(st))
         if rc != 0:

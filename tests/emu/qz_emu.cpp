@@ -17,6 +17,7 @@
 #include <string>
 #include <vector>
 
+#include "memo_plan.h"
 #include "scene_store.cuh"
 
 using namespace qz;
@@ -111,13 +112,69 @@ int qz_trace_paths(qz_scene s, const qz_camera* camera, uint32_t n_samples, uint
     return QZ_OK;
 }
 
-// per-pixel loop in the reference's order (render.cpp:260-294); no wavefront here
+// The SAMPLE MEMO of a render (csrc/sampler.cuh) built on the host from the product's own pieces: the class tables and
+// the row layout of csrc/memo_plan.h, every entry by memo_entry_bits (what k_memo_fill stores), the hot-spectra block by
+// memo_fill_hot (what k_memo_spectra runs).  One pass over all sample numbers [s_begin, s_begin + s_count).
+struct HostMemo {
+    std::vector<uint32_t> rank, idx, tab;
+    SampleMemo m{};
+    uint64_t filled = 0;
+    void build(const qz_scene_t& s, const SamplerParams& spar, uint32_t W, uint32_t H, const std::vector<uint32_t>& rows, uint32_t bounces,
+               uint32_t s_begin, uint32_t s_count) {
+        memo_owned_classes(spar, W, H, rows, rank, idx);
+        const MemoLayout lay = memo_layout(bounces);
+        tab.assign((size_t)lay.stride * s_count * idx.size(), QZ_MEMO_EMPTY);
+        m = memo_describe(lay, spar, tab.data(), rank.data(), idx.data(), (uint32_t)idx.size(), s_begin, s_count);
+        for (uint32_t sn = 0; sn < s_count; sn++)
+            for (uint32_t c = 0; c < m.n_cls; c++)
+                for (uint32_t d = 0; d < m.dims; d++, filled++)
+                    tab[((size_t)sn * m.n_cls + c) * m.stride + m.dim_off + d] = memo_entry_bits(g_sampler_table, spar, m, sn, c, d);
+        const uint32_t n_hot = (uint32_t)s.store.hot_spectra.size();
+        if (n_hot) {
+            DScene fill = s.store.view;
+            fill.memo = m;
+            fill.memo.n_hot = n_hot;
+            for (uint32_t k = 0; k < n_hot; k++) fill.memo.hot_id[k] = m.hot_id[k] = s.store.hot_spectra[k];
+            for (size_t r = 0; r < (size_t)s_count * m.n_cls; r++) memo_fill_hot(fill, tab.data() + r * m.stride);
+            m.n_hot = n_hot;
+        }
+        // negative control of the tests: a table whose entries are off in mantissa bit 12 (5e-4 relative) must change the film, or the paths
+        // are not reading it.  QZ_EMU_MEMO_CORRUPT = "dims" | "hot".
+        if (const char* e = std::getenv("QZ_EMU_MEMO_CORRUPT")) {
+            const bool hot = std::strcmp(e, "hot") == 0;
+            for (size_t r = 0; r < (size_t)s_count * m.n_cls; r++) {
+                uint32_t* row = tab.data() + r * m.stride;
+                if (hot) for (uint32_t k = 0; k < 4 * m.n_hot; k++) row[k] ^= 0x1000u;
+                else for (uint32_t d = 0; d < m.dims; d++) row[m.dim_off + d] ^= 0x1000u;
+            }
+        }
+    }
+};
+
+// per-pixel loop in the reference's order (render.cpp:260-294); no wavefront here.  With QZ_FLAG_FORCE_MEMO the paths
+// read their draws and hot spectra from a sample memo, as the wavefront's do (options->reserved: bounces per row, 0 = 8;
+// options->samples_per_pass: sample numbers the table covers, 0 = all -- the rest evaluate directly, like a later pass).
 int qz_render(qz_scene s, const qz_camera* camera, uint32_t n_samples, uint32_t max_bounces, const qz_region* region,
-              const qz_render_options*, float* color, float* normal, float* albedo, qz_stats* stats) {
+              const qz_render_options* options, float* color, float* normal, float* albedo, qz_stats* stats) {
     if (!s->store.committed) { g_error = "scene not committed"; return QZ_ERR_NOT_COMMITTED; }
     DCamera cam = make_camera(camera);
     SamplerParams spar = make_sampler_params((int)cam.width, (int)cam.height);
     qz_stats st{};
+    HostMemo memo;
+    struct Restore {   // the scene view carries the memo only for the duration of this call
+        DScene& v;
+        ~Restore() { v.memo = SampleMemo{}; }
+    } restore{s->store.view};
+    if (options && (options->flags & QZ_FLAG_FORCE_MEMO)) {
+        std::vector<uint32_t> rows;
+        for (uint32_t row = 0; row < cam.height; row++)
+            if (!(region && region->strip_rows && region->n_shards > 1 && (row / region->strip_rows) % region->n_shards != region->shard)) rows.push_back(row);
+        const uint32_t covered = options->samples_per_pass ? std::min(options->samples_per_pass, n_samples) : n_samples;
+        memo.build(*s, spar, cam.width, cam.height, rows, options->reserved ? options->reserved : 8u, 0, covered);
+        s->store.view.memo = memo.m;
+        st.shade_calls = memo.filled;   // (reported so that a test can see the table was really built)
+        st.iterations = memo.idx.size();
+    }
     for (uint32_t row = 0; row < cam.height; row++) {
         if (region && region->strip_rows && region->n_shards > 1 && (row / region->strip_rows) % region->n_shards != region->shard) continue;
         for (uint32_t x = 0; x < cam.width; x++) {

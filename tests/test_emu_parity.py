@@ -151,3 +151,71 @@ def test_tone_path_restatement(emu, oracle, gamma):
         ok = np.isnan(want_f) & np.isnan(got_f) | (np.abs(got_f - want_f) <= 2 * np.spacing(np.abs(want_f)))
         assert ok.all()
         assert (np.abs(got_u8.astype(int) - want_u8.astype(int)) <= 1).all() and (got_u8 != want_u8).mean() < 1e-3
+
+
+def _planes_equal(a, b, rows=slice(None)):
+    return all(bits_equal(getattr(a, p)[rows], getattr(b, p)[rows]).all() for p in ("color", "normal", "albedo"))
+
+
+@pytest.mark.parametrize("name,size,spp", [("cornell_box", (150, 140), 3), ("kitchen_sink", (131, 70), 2), ("textures", (140, 133), 2)])
+def test_sample_memo_on_the_host_does_not_change_the_film(emu, name, size, spp):
+    """SAMPLE MEMO (csrc/sampler.cuh, memo_plan.h) with the wavefront taken away: the emulation builds the table from the
+    product's own pieces -- the owned-class tables, the row layout, memo_entry_bits (what k_memo_fill stores),
+    memo_fill_hot (what k_memo_spectra runs) -- and the per-path loop reads draws and hot spectra through memo_row /
+    bounce_in_memo exactly as k_shade does.  Films must be bit-identical with the table, without it, with rows that
+    hold only two bounces, and with a table that covers only the first sample number (a later pass's samples)."""
+    from quetzalcoatlus_b200.harness import QZ_FLAG_FORCE_MEMO
+
+    w, h = size
+    with emu.build_scene(name, w, h) as sc:
+        plain, _ = sc.render_flags(spp)
+        memo, st = sc.render_flags(spp, flags=QZ_FLAG_FORCE_MEMO)
+        n_cls = min(w, 128) * min(h, 128)
+        assert st["iterations"] == n_cls and st["shade_calls"] == n_cls * spp * (3 + 8 * 8)   # the table really was built
+        assert _planes_equal(plain, memo)
+        short, _ = sc.render_flags(spp, flags=QZ_FLAG_FORCE_MEMO, reserved=2)
+        assert _planes_equal(plain, short)
+        partial, st1 = sc.render_flags(spp, flags=QZ_FLAG_FORCE_MEMO, samples_per_pass=1, reserved=1)
+        assert st1["shade_calls"] == n_cls * (3 + 8)
+        assert _planes_equal(plain, partial)
+
+
+def test_sample_memo_of_a_shard_holds_only_its_own_classes(emu):
+    """A multi-GPU shard (interleaved strips, qz_region) tabulates only the (x mod 128, y mod 128) classes of its own rows:
+    1/N of them when strip x N divides 128, and its rows of the film are those of the unsharded render, bit for bit."""
+    from quetzalcoatlus_b200.harness import QZ_FLAG_FORCE_MEMO
+
+    w, h, spp = 130, 256, 1
+    with emu.build_scene("cornell_box", w, h) as sc:
+        whole, _ = sc.render_flags(spp)
+        for strip, n in [(4, 8), (8, 2), (5, 3)]:
+            shard = n - 1
+            part, st = sc.render_flags(spp, flags=QZ_FLAG_FORCE_MEMO, region=(strip, n, shard))
+            own = np.array([(r // strip) % n == shard for r in range(h)])
+            if 128 % (strip * n) == 0:
+                assert st["iterations"] == 128 * 128 // n
+            else:
+                assert 128 * 128 // n < st["iterations"] <= 128 * 128
+            assert _planes_equal(whole, part, own)
+            assert not part.color[~own].any()
+
+
+@pytest.mark.parametrize("what", ["dims", "hot"])
+def test_sample_memo_negative_control(emu, monkeypatch, what):
+    """The paths really read the table: entries off by 5e-4 relative (the draws, or the hot spectra) change the film."""
+    from quetzalcoatlus_b200.harness import QZ_FLAG_FORCE_MEMO
+
+    with emu.build_scene("cornell_box", 40, 30) as sc:
+        plain, _ = sc.render_flags(2)
+        monkeypatch.setenv("QZ_EMU_MEMO_CORRUPT", what)
+        off, _ = sc.render_flags(2, flags=QZ_FLAG_FORCE_MEMO)
+        monkeypatch.delenv("QZ_EMU_MEMO_CORRUPT")
+        again, _ = sc.render_flags(2, flags=QZ_FLAG_FORCE_MEMO)
+    assert _planes_equal(plain, again)
+    lit = plain.color != 0   # (few pixels find the small light with two samples)
+    differing = (~bits_equal(plain.color, off.color))[lit].mean()
+    assert differing > 0.5, differing
+    if what == "dims":
+        assert (~bits_equal(plain.albedo, off.albedo)).mean() > 0.5
+    else:
+        assert _planes_equal(plain, off) is False and bits_equal(plain.normal, off.normal).all()   # geometry does not depend on the spectra
