@@ -313,6 +313,17 @@ class Harness:
             raise RuntimeError(f"{self.prefix}tone failed with code {rc}")
         return f, u8
 
+    def obj_load(self, path) -> dict:
+        """ObjData of an OBJ file as this library's loader reads it (obj/obj.hpp): vertices (n, 4), normals (n, 3),
+        faces (n, 13) = vertices[4], textures[4], normals[4], n_vertices.  None when the loader gives up."""
+        fn = self._fn("obj_load")
+        counts = (ctypes.c_long * 3)()
+        if fn(str(path).encode(), counts, None, None, None) != 0:
+            return None
+        v, n, f = np.zeros((counts[0], 4), np.float32), np.zeros((counts[1], 3), np.float32), np.zeros((counts[2], 13), np.int32)
+        fn(str(path).encode(), counts, v.ctypes.data_as(_c_float_p), n.ctypes.data_as(_c_float_p), f.ctypes.data_as(ctypes.c_void_p))
+        return {"vertices": v, "normals": n, "faces": f}
+
     def eval_spectrum(self, name: str, lambdas) -> np.ndarray:
         lam = _f32(lambdas).ravel()
         out = np.zeros(len(lam), np.float32)

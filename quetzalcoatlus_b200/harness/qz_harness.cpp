@@ -8,6 +8,7 @@
 #include <cstring>
 #include <string>
 
+#include "obj/obj.hpp"
 #include "render.hpp"
 #include "scenes.hpp"
 
@@ -179,6 +180,29 @@ void qzh_force_brute_force(int) {}
 // Image::save's tone path (image.cpp:7-19) through the C ABI
 int qzh_tone(const float* rgb, int n_pixels, float gamma, float* bgr255, unsigned char* bgr8) {
     return qz_tone(rgb, (uint32_t)n_pixels, gamma, bgr255, bgr8);
+}
+
+// ObjData of a file (obj/obj.hpp), flattened for the loader tests: counts = {vertices, normals, faces}; arrays may be null
+// (sizing call) and otherwise hold 4 floats per vertex (x y z w), 3 per normal, 13 ints per face (vertices[4], textures[4],
+// normals[4], n_vertices).  Returns 1 when the loader returns nullopt.
+int qzh_obj_load(const char* path, long* counts, float* vertices, float* normals, int* faces) {
+    auto data = obj::load_obj(path);
+    if (!data) return 1;
+    counts[0] = (long)data->vertices.size(); counts[1] = (long)data->vertex_normals.size(); counts[2] = (long)data->faces.size();
+    for (size_t i = 0; vertices && i < data->vertices.size(); i++) {
+        const auto& v = data->vertices[i];
+        vertices[4 * i] = v.x; vertices[4 * i + 1] = v.y; vertices[4 * i + 2] = v.z; vertices[4 * i + 3] = v.w;
+    }
+    for (size_t i = 0; normals && i < data->vertex_normals.size(); i++) {
+        const auto& n = data->vertex_normals[i];
+        normals[3 * i] = n.x; normals[3 * i + 1] = n.y; normals[3 * i + 2] = n.z;
+    }
+    for (size_t i = 0; faces && i < data->faces.size(); i++) {
+        const auto& f = data->faces[i];
+        for (int k = 0; k < 4; k++) { faces[13 * i + k] = f.vertices[k]; faces[13 * i + 4 + k] = f.textures[k]; faces[13 * i + 8 + k] = f.normals[k]; }
+        faces[13 * i + 12] = (int)f.n_vertices;
+    }
+    return 0;
 }
 
 }  // extern "C"

@@ -139,6 +139,125 @@ def test_obj_loader_semantics(emu, oracle, tmp_path):
             assert bits_equal(se.trace_paths(xys), so.trace_paths(xys)).all(), path.name
 
 
+def _torture_obj_lines(rng):
+    """Lines the reference's loader survives (its std::stof throws on a token without a number): number formats of every
+    kind, blank runs of every kind, CR line ends, indented records, foreign line types, every face form, faces with mixed,
+    truncated, surplus and malformed corners."""
+    def num():
+        k = rng.integers(0, 9)
+        sign = str(rng.choice(["", "-", "+"])) if rng.random() < 0.5 else ""
+        if k == 0: return sign + str(rng.integers(0, 10 ** int(rng.integers(1, 12))))
+        if k == 1: return sign + f"{abs(rng.uniform(-1, 1)) * 10.0 ** int(rng.integers(-6, 6)):.{rng.integers(0, 13)}f}"
+        if k == 2: return sign + f"{rng.uniform(0, 1000):.{rng.integers(1, 8)}e}"
+        if k == 3: return sign + "0" * int(rng.integers(1, 5)) + f"{rng.uniform(0, 10):.{rng.integers(0, 9)}f}"
+        if k == 4: return sign + f".{rng.integers(0, 10 ** 6)}"
+        if k == 5: return sign + f"{rng.integers(0, 1000)}."
+        if k == 6: return sign + f"{rng.integers(0, 2 ** 24 + 50)}"   # around the largest integer a float holds exactly
+        if k == 7: return sign + f"{rng.integers(16777000, 16777300) / 10.0 ** int(rng.integers(0, 11)):.{rng.integers(0, 11)}f}"
+        return sign + f"{rng.uniform(0, 3):.7g}" + str(rng.choice(["", "abc", "f", "e", "#"]))
+
+    lines = ["# torture", "", "   ", "\t", "\r", "vt 0.5 0.5", "g name", "o obj", "s off", "usemtl m", "vp 1 2 3", "vnn 1 2 3", "ff 1 2 3"]
+    for _ in range(250):
+        n, sep = rng.choice([3, 3, 3, 4, 5]), str(rng.choice([" ", "  ", "\t", " \t ", "\v", "\f "]))
+        lines.append("v" + sep + sep.join(num() for _ in range(n)) + str(rng.choice(["", " ", "\r", " \r"])))
+        if rng.random() < 0.5:
+            lines.append("vn" + sep + sep.join(num() for _ in range(rng.choice([3, 3, 4]))))
+    lines += [" v 1 2 3", "\tv 4 5 6", " vn 0 0 1", " f 1 2 3", "v 1 2", "vn 1 2", "v", "vn", "f", "f 1 2", "#v 1 2 3", "v 1 2 3#x",
+              "vv 1 2 3 v 1 2 3", "g v 1 2 3", "x f 1 2 3", "f 1 2 3 f 4 5 6", "f 1/2 f 3 4 5", "f 1/ 2 3 f 7/8 9/10 11/12", "f1 2 3", "v1 2 3"]
+    idx = lambda: str(rng.integers(1, 250))
+    for _ in range(200):
+        form, n = rng.integers(0, 6), rng.choice([3, 4, 5, 2])
+        if form == 0: c = [idx() for _ in range(n)]
+        elif form == 1: c = [idx() + "/" + idx() for _ in range(n)]
+        elif form == 2: c = [idx() + "//" + idx() for _ in range(n)]
+        elif form == 3: c = [idx() + "/" + idx() + "/" + idx() for _ in range(n)]
+        elif form == 4: c = [idx() + str(rng.choice(["", "/" + idx(), "//" + idx(), "/" + idx() + "/" + idx(), "/", "//"])) for _ in range(n)]
+        else:
+            c = [idx() for _ in range(n)]
+            c[rng.integers(0, n)] = str(rng.choice(["-1", "a", "1.5", "0", "+3", "3x"]))
+        lines.append("f " + str(rng.choice([" ", "  ", "\t"])).join(c) + str(rng.choice(["", " ", "\r"])))
+    return lines
+
+
+def test_obj_loader_records_equal_the_reference_loaders(emu, oracle, tmp_path):
+    """ObjData of a torture file, record by record, against the reference's own regex loader (obj/obj.cpp:9-175) compiled
+    into the oracle: vertices, normals, face indices and corner counts bit for bit -- well-formed and malformed lines
+    alike.  Only `textures` of `a//n` faces is left out: the reference leaves it indeterminate there."""
+    rng = np.random.default_rng(7)
+    path = tmp_path / "torture.obj"
+    path.write_bytes("\n".join(_torture_obj_lines(rng)).encode())   # (no newline at the end of the file)
+    got, want = emu.obj_load(path), oracle.obj_load(path)
+    assert got["vertices"].shape == want["vertices"].shape and len(got["vertices"]) > 240
+    assert (got["vertices"].view(np.uint32) == want["vertices"].view(np.uint32)).all()
+    assert got["normals"].shape == want["normals"].shape and (got["normals"].view(np.uint32) == want["normals"].view(np.uint32)).all()
+    gf, wf = got["faces"], want["faces"]
+    assert gf.shape == wf.shape and len(gf) > 80
+    assert (gf[:, :4] == wf[:, :4]).all() and (gf[:, 8:] == wf[:, 8:]).all()
+    textures_defined = (gf[:, 8:12] == 0).all(1) | (gf[:, 4:8] != 0).any(1)
+    assert textures_defined.sum() > 40 and (gf[textures_defined, 4:8] == wf[textures_defined, 4:8]).all()
+    assert (gf[~textures_defined, 4:8] == 0).all()
+
+
+def test_obj_loader_ranges_and_number_parsing_at_scale(emu, tmp_path):
+    """A file large enough to be cut into several ranges (one per host thread), with malformed and foreign lines spread
+    through every range: record order, counts and values against libc's strtof -- what std::stof calls -- on every token
+    (the loader's exact-decimal fast path must agree with it bit for bit)."""
+    import ctypes
+
+    libc = ctypes.CDLL(None)
+    libc.strtof.restype, libc.strtof.argtypes = ctypes.c_float, [ctypes.c_char_p, ctypes.c_void_p]
+    rng = np.random.default_rng(3)
+    n = 60000
+    coords = rng.uniform(-50, 50, (n, 3))
+    digits = rng.integers(0, 10, (n, 3))
+    lines, want_v, want_n, want_f = [], [], [], []
+    for i in range(n):
+        tok = [f"{coords[i, k]:.{digits[i, k]}f}" for k in range(3)]
+        lines.append("v " + " ".join(tok))
+        want_v.append(tok)
+        if i % 3 == 0:
+            lines.append("vn " + " ".join(tok[::-1]))
+            want_n.append(tok[::-1])
+        a, b, c = (int(x) for x in rng.integers(1, n, 3))
+        kind = i % 7
+        if kind == 0: lines.append(f"f {a} {b} {c}"); want_f.append([a, b, c, c, 0, 0, 0, 0, 0, 0, 0, 0, 3])
+        elif kind == 1: lines.append(f"f {a}//{c} {b}//{a} {c}//{b}"); want_f.append([a, b, c, c, 0, 0, 0, 0, c, a, b, b, 3])
+        elif kind == 2: lines.append(f"f {a}/{b} {b}/{c} {c}/{a} {a}/{a}"); want_f.append([a, b, c, a, b, c, a, a, 0, 0, 0, 0, 4])
+        elif kind == 3: lines.append(f"f {a}/{b}/{c} {b}/{c}/{a} {c}/{a}/{b}"); want_f.append([a, b, c, c, b, c, a, 0, c, a, b, b, 3])
+        elif kind == 4: lines += ["v 1 2", f"f {a} {b}", f" v {a} {b} {c}", "# v 1 2 3", "vt 0 0", ""]   # nothing of this is a record
+        elif kind == 5: lines.append(f"f {a} {b} {c}/{a}"); want_f.append([a, b, c, c, 0, 0, 0, 0, 0, 0, 0, 0, 3])
+        else: lines.append(f"f {a} {b} {c} {a} {b}"); want_f.append([a, b, c, a, 0, 0, 0, 0, 0, 0, 0, 0, 4])
+    path = tmp_path / "large.obj"
+    path.write_bytes(("\n".join(lines) + "\n").encode())
+    assert path.stat().st_size > 3 << 20
+    got = emu.obj_load(path)
+    value = lambda t: libc.strtof(t.encode(), None)
+    want_vertices = np.array([[value(t) for t in tok] + [1.0] for tok in want_v], np.float32)
+    want_normals = np.array([[value(t) for t in tok] for tok in want_n], np.float32)
+    assert got["vertices"].shape == want_vertices.shape and (got["vertices"].view(np.uint32) == want_vertices.view(np.uint32)).all()
+    assert got["normals"].shape == want_normals.shape and (got["normals"].view(np.uint32) == want_normals.view(np.uint32)).all()
+    assert got["faces"].shape == (len(want_f), 13) and (got["faces"] == np.array(want_f, np.int32)).all()
+
+
+def test_obj_loader_file_that_ends_exactly_at_a_page_boundary(emu, oracle, tmp_path):
+    """The loader parses the mapped file in place and relies on a NUL behind the last byte; a file that fills its last
+    page exactly and has no final newline takes the copying path instead.  Also: empty file, missing file."""
+    import mmap
+
+    tail = b"v 1.25 2.5 3.75\nvn 0 0 1\nf 1 1 1\nv 9 8 7.5"
+    for size in (mmap.PAGESIZE, 2 * mmap.PAGESIZE, 2 * mmap.PAGESIZE + 1):
+        path = tmp_path / f"exact_{size}.obj"
+        path.write_bytes(b"#" * (size - len(tail) - 1) + b"\n" + tail)
+        assert path.stat().st_size == size
+        got, want = emu.obj_load(path), oracle.obj_load(path)
+        assert got["vertices"].tolist() == want["vertices"].tolist() == [[1.25, 2.5, 3.75, 1.0], [9.0, 8.0, 7.5, 1.0]]
+        assert got["normals"].tolist() == [[0.0, 0.0, 1.0]] and got["faces"][:, :4].tolist() == [[1, 1, 1, 1]]
+    empty = tmp_path / "empty.obj"
+    empty.write_bytes(b"")
+    assert all(len(a) == 0 for a in emu.obj_load(empty).values())
+    assert emu.obj_load(tmp_path / "missing.obj") is None and oracle.obj_load(tmp_path / "missing.obj") is None
+
+
 def test_strip_rows_are_balanced_and_keep_a_shard_on_its_own_pixel_classes():
     """bench.py / qz_render's multi-GPU strips: every rank owns the same number of rows, and where a power-of-two height
     does that, strip * ranks divides 128 -- a rank then owns 1/ranks of the (y mod 128) pixel classes, which is what its
