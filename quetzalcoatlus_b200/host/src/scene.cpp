@@ -9,9 +9,12 @@
 //   set_bg_light; :22-25 commit; render.cpp:321-397 render().
 #include "../scene.hpp"
 
+#include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 
 #include "../obj/obj.hpp"
 #include "../onb.hpp"
@@ -23,6 +26,16 @@ inline float bits_to_float(uint32_t b) {
     float f;
     std::memcpy(&f, &b, 4);
     return f;
+}
+
+// f(begin, end) over [0, n) cut into one range per host thread (small n: the calling thread alone)
+template <class F>
+void parallel_ranges(size_t n, F f) {
+    const size_t parts = std::max<size_t>(1, std::min<size_t>({std::thread::hardware_concurrency(), 16, n / 65536}));
+    std::vector<std::thread> workers;
+    for (size_t k = 1; k < parts; k++) workers.emplace_back([&f, n, parts, k] { f(n * k / parts, n * (k + 1) / parts); });
+    f(0, n / parts);
+    for (auto& w : workers) w.join();
 }
 
 qz_prim make_prim(uint32_t kind, uint32_t geom_id, uint32_t prim_id, uint32_t cell, const Pt3* v, int nv) {
@@ -132,35 +145,46 @@ GeometryData* Scene::add_obj(const std::string& filename, const Material* materi
     const obj::ObjData& mesh = *obj_data;
     if (mesh.vertices.empty() || mesh.faces.empty()) return nullptr;
 
+    // every loop below is independent per element: one range per host thread (a 1M-face mesh is 64 MB of primitives)
     std::vector<Pt3> verts(mesh.vertices.size());
-    for (size_t i = 0; i < verts.size(); i++) verts[i] = transform * Pt3(mesh.vertices[i].x, mesh.vertices[i].y, mesh.vertices[i].z);
+    parallel_ranges(verts.size(), [&](size_t begin, size_t end) {
+        for (size_t i = begin; i < end; i++) verts[i] = transform * Pt3(mesh.vertices[i].x, mesh.vertices[i].y, mesh.vertices[i].z);
+    });
 
-    for (const auto& face : mesh.faces) {
-        for (int k = 0; k < 4; k++) {
-            if (face.vertices[k] < 1 || size_t(face.vertices[k]) > verts.size()) {
-                std::cerr << "Failed to create buffers for " << filename << " (face index out of range)" << std::endl;
-                return nullptr;
-            }
-        }
+    std::atomic<bool> in_range{true};
+    parallel_ranges(mesh.faces.size(), [&](size_t begin, size_t end) {
+        for (size_t i = begin; i < end; i++)
+            for (int k = 0; k < 4; k++)
+                if (mesh.faces[i].vertices[k] < 1 || size_t(mesh.faces[i].vertices[k]) > verts.size()) in_range = false;
+    });
+    if (!in_range) {
+        std::cerr << "Failed to create buffers for " << filename << " (face index out of range)" << std::endl;
+        return nullptr;
     }
 
     GeometryData* g = new_geometry(ShapeType::OBJ, material);
     const uint32_t geom_id = uint32_t(m_geom_data.size() - 1);
-    g->prims.reserve(mesh.faces.size());
-    for (size_t i = 0; i < mesh.faces.size(); i++) {
-        const auto& idx = mesh.faces[i].vertices;
-        const Pt3 v[4] = {verts[idx[0] - 1], verts[idx[1] - 1], verts[idx[2] - 1], verts[idx[3] - 1]};
-        g->prims.push_back(make_prim(QZ_PRIM_QUAD, geom_id, uint32_t(i), 0, v, 4));
-    }
+    g->prims.resize(mesh.faces.size());
+    parallel_ranges(mesh.faces.size(), [&](size_t begin, size_t end) {
+        for (size_t i = begin; i < end; i++) {
+            const auto& idx = mesh.faces[i].vertices;
+            const Pt3 v[4] = {verts[idx[0] - 1], verts[idx[1] - 1], verts[idx[2] - 1], verts[idx[3] - 1]};
+            g->prims[i] = make_prim(QZ_PRIM_QUAD, geom_id, uint32_t(i), 0, v, 4);
+        }
+    });
     if (!mesh.vertex_normals.empty()) {
         auto nd = std::make_unique<NormalData>();
-        nd->normals.reserve(mesh.vertex_normals.size());
-        for (const auto& n : mesh.vertex_normals) nd->normals.emplace_back(n.x, n.y, n.z);
-        nd->faces.reserve(mesh.faces.size());
-        for (const auto& face : mesh.faces) {
-            const auto& ns = face.normals;
-            nd->faces.push_back({ns[0] - 1, ns[1] - 1, ns[2] - 1, ns[3] - 1});
-        }
+        nd->normals.resize(mesh.vertex_normals.size());
+        parallel_ranges(nd->normals.size(), [&](size_t begin, size_t end) {
+            for (size_t i = begin; i < end; i++) nd->normals[i] = Vec3(mesh.vertex_normals[i].x, mesh.vertex_normals[i].y, mesh.vertex_normals[i].z);
+        });
+        nd->faces.resize(mesh.faces.size());
+        parallel_ranges(nd->faces.size(), [&](size_t begin, size_t end) {
+            for (size_t i = begin; i < end; i++) {
+                const auto& ns = mesh.faces[i].normals;
+                nd->faces[i] = {ns[0] - 1, ns[1] - 1, ns[2] - 1, ns[3] - 1};
+            }
+        });
         g->normals = std::move(nd);
     }
     return g;
@@ -248,12 +272,13 @@ void Scene::commit() {
         q.nindex_offset = -1;
         if (g.normals && g.shape == ShapeType::OBJ) {
             q.normal_offset = int32_t(f.normals.size() / 3);
+            f.normals.reserve(f.normals.size() + 3 * g.normals->normals.size());
             for (const auto& n : g.normals->normals) {
                 f.normals.push_back(n.x); f.normals.push_back(n.y); f.normals.push_back(n.z);
             }
             q.nindex_offset = int32_t(f.normal_indices.size() / 4);
-            for (const auto& fi : g.normals->faces)
-                for (int k = 0; k < 4; k++) f.normal_indices.push_back(fi[k]);
+            const auto& nf = g.normals->faces;   // (std::array<int, 4>: contiguous ints)
+            if (!nf.empty()) f.normal_indices.insert(f.normal_indices.end(), nf.front().data(), nf.front().data() + 4 * nf.size());
         }
         q.first_prim = uint32_t(f.prims.size());
         q.prim_count = uint32_t(g.prims.size());
