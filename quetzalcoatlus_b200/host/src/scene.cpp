@@ -201,20 +201,23 @@ GeometryData* Scene::add_grid(const Image& image, const Material* material, cons
     }
     const size_t W = image.width, H = image.height;
     std::vector<Pt3> verts(W * H);
-    for (size_t i = 0; i < W * H; i++)
-        verts[i] = transform * Pt3(image.color_buffer[i * 3 + 0], image.color_buffer[i * 3 + 1], image.color_buffer[i * 3 + 2]);
+    parallel_ranges(W * H, [&](size_t begin, size_t end) {
+        for (size_t i = begin; i < end; i++)
+            verts[i] = transform * Pt3(image.color_buffer[i * 3 + 0], image.color_buffer[i * 3 + 1], image.color_buffer[i * 3 + 2]);
+    });
 
     GeometryData* g = new_geometry(ShapeType::GRID, material);
     const uint32_t geom_id = uint32_t(m_geom_data.size() - 1);
     g->grid_dims = uint32_t(W - 1) | (uint32_t(H - 1) << 16);
-    g->prims.reserve((W - 1) * (H - 1));
-    // one cell = one quad (p[y][x], p[y][x+1], p[y+1][x+1], p[y+1][x]); primID 0 (a single RTCGrid)
-    for (size_t y = 0; y + 1 < H; y++) {
-        for (size_t x = 0; x + 1 < W; x++) {
+    g->prims.resize((W - 1) * (H - 1));
+    // one cell = one quad (p[y][x], p[y][x+1], p[y+1][x+1], p[y+1][x]); primID 0 (a single RTCGrid); cells in row-major order
+    parallel_ranges(g->prims.size(), [&](size_t begin, size_t end) {
+        for (size_t i = begin; i < end; i++) {
+            const size_t y = i / (W - 1), x = i - y * (W - 1);
             const Pt3 v[4] = {verts[y * W + x], verts[y * W + x + 1], verts[(y + 1) * W + x + 1], verts[(y + 1) * W + x]};
-            g->prims.push_back(make_prim(QZ_PRIM_GRIDCELL, geom_id, 0, uint32_t(x) | (uint32_t(y) << 16), v, 4));
+            g->prims[i] = make_prim(QZ_PRIM_GRIDCELL, geom_id, 0, uint32_t(x) | (uint32_t(y) << 16), v, 4);
         }
-    }
+    });
     return g;
 }
 
