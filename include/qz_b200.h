@@ -237,6 +237,13 @@ uint32_t qz_set_default_flags(uint32_t flags);
  * (so an unmodified application of the reference's API can be switched over from outside).  Returns the previous value. */
 int qz_set_device_count(int n);
 
+/* Rows per interleaved strip that qz_render() uses when it shards a film of `height` rows over `n_shards` devices, for a
+ * multi-process driver that wants the same partition (qz_region.strip_rows): the largest height <= 8 that gives every
+ * shard the same number of rows, powers of two first -- with strip * n_shards dividing 128 a shard owns 1/n_shards of the
+ * sampler's (y mod 128) pixel classes.  Pure function; needs no device.  (The reference tiles its film over host threads,
+ * render.cpp:339-382.)                                                                                              */
+uint32_t qz_strip_rows(uint32_t height, uint32_t n_shards);
+
 /* Scene::Scene / ~Scene (scene.hpp:44-49) */
 int qz_scene_create(qz_scene* out);
 int qz_scene_destroy(qz_scene scene);

@@ -343,6 +343,7 @@ uint32_t balanced_strip_rows(uint32_t height, uint32_t n) {
 extern "C" {
 
 const char* qz_last_error(void) { return g_error.c_str(); }
+uint32_t qz_strip_rows(uint32_t height, uint32_t n_shards) { return balanced_strip_rows(height, n_shards ? n_shards : 1u); }
 uint32_t qz_set_default_flags(uint32_t flags) { const uint32_t old = g_default_flags; g_default_flags = flags; return old; }
 int qz_abi_version(void) { return QZ_ABI_VERSION; }
 

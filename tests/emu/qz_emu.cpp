@@ -260,6 +260,7 @@ int qz_math_probe(int op, uint32_t n, const float* in, float* out) {
 }
 
 int qz_set_device_count(int) { return 0; }
+uint32_t qz_strip_rows(uint32_t, uint32_t) { return 1; }   // (no multi-device render in the emulation)
 int qz_scene_build_ms(qz_scene, float* ms) { if (ms) *ms = 0.0f; return QZ_OK; }
 int qz_film_device(qz_scene, float**, float**, float**, uint32_t*, uint32_t*) { g_error = "host emulation: no device film"; return QZ_ERR_NO_DEVICE; }
 int qz_tone_device(const float*, uint32_t, float, float*, uint8_t*, void*) { g_error = "host emulation: no device"; return QZ_ERR_NO_DEVICE; }

@@ -277,6 +277,12 @@ def test_strip_rows_are_balanced_and_keep_a_shard_on_its_own_pixel_classes():
                 classes = {(height - 1 - r) % 128 for r in range(height) if (r // rows) % world == 0}
                 assert len(classes) <= 128 // world, (height, world, rows, len(classes))
     assert bench.strip_rows_for(800, 8) == 4 and bench.strip_rows_for(2160, 8) == 2 and bench.strip_rows_for(800, 4) == 8
+    # the library's own rule (in-library multi-GPU render) is the same function
+    lib = ctypes.CDLL(str(ROOT / "quetzalcoatlus_b200" / "_lib" / "libqz_b200.so"))
+    lib.qz_strip_rows.restype, lib.qz_strip_rows.argtypes = ctypes.c_uint32, [ctypes.c_uint32, ctypes.c_uint32]
+    for height in (1, 7, 54, 96, 600, 800, 1080, 2160, 4320):
+        for world in (1, 2, 3, 4, 8, 16):
+            assert lib.qz_strip_rows(height, world) == bench.strip_rows_for(height, world), (height, world)
 
 
 def test_reference_arm_of_the_bench_runs_on_the_cpu(tmp_path):
