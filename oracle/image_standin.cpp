@@ -23,9 +23,10 @@ void RenderResult::save_normal(const std::string& filename) const { write_pfm(fi
 void RenderResult::save_albedo(const std::string& filename) const { write_pfm(filename, albedo_buffer, width, height); }
 
 // The arithmetic of Image::save (image.cpp:10-15), restated because image.cpp itself needs OpenCV: x255, powf gamma,
-// B and R swapped.  bgr8 is what cv::imwrite stores for an 8-bit file from that CV_32FC3 matrix (OpenCV converts with
-// saturate_cast<uchar>(float) = cvRound, i.e. lrint, clamped to 0..255) -- OpenCV is absent: that conversion is
-// recalled from its documentation, parity at the OpenCV boundary is UNPINNED.
+// B and R swapped.  bgr8 is what cv::imwrite stores for an 8-bit file from that CV_32FC3 matrix: OpenCV converts with
+// convertTo(CV_8U) -- cvRound (the x86 float -> int32 conversion: nearest even; INT_MIN for NaN, infinities and values
+// beyond int32), then saturation to 0..255.  The C++ OpenCV is absent here, but the image has its Python build:
+// tests/test_abi_and_host.py pins this function against cv2.imwrite / cv2.imread (OpenCV 4.13) on the same matrix.
 #include <cmath>
 extern "C" int orc_tone(const float* rgb, int n_pixels, float gamma, float* bgr255, unsigned char* bgr8) {
     for (long i = 0; i < n_pixels; i++) {
@@ -33,7 +34,8 @@ extern "C" int orc_tone(const float* rgb, int n_pixels, float gamma, float* bgr2
             const float v = 255.0f * powf(rgb[3 * i + 2 - k], gamma);
             if (bgr255) bgr255[3 * i + k] = v;
             if (bgr8) {
-                const long r = v != v ? 0 : lrintf(v < -1.0f ? -1.0f : (v > 256.0f ? 256.0f : v));
+                const bool in_int32 = std::fabs(v) < 2147483648.0f;   // false for NaN too
+                const long r = in_int32 ? lrintf(v) : 0;
                 bgr8[3 * i + k] = (unsigned char)(r < 0 ? 0 : (r > 255 ? 255 : r));
             }
         }

@@ -114,9 +114,12 @@ QZ_HD float tone_value(float c, float gamma) {
     const float p = gamma == 1.0f ? c : (float)pow((double)c, (double)gamma);
     return 255.0f * p;
 }
-// OpenCV's saturate_cast<uchar>(float) (what cv::imwrite applies to a CV_32F matrix for an 8-bit file): round to
-// nearest even, clamp to 0..255; NaN gives 0
+// What cv::imwrite stores for a CV_32F matrix in an 8-bit file (it converts with convertTo(CV_8U): cvRound, then
+// saturate): round to nearest even, clamp to 0..255.  cvRound is the x86 float -> int32 conversion, which answers
+// INT_MIN for NaN, the infinities and everything beyond the int32 range -- those all become 0, not 255 (pinned against
+// OpenCV 4.13's imwrite by tests/test_abi_and_host.py).
 QZ_HD uint8_t tone_u8(float v) {
+    if (!(fabsf(v) < 2147483648.0f)) return 0;
     const float r = rintf(v);
     return (uint8_t)(r >= 255.0f ? 255.0f : (r > 0.0f ? r : 0.0f));
 }

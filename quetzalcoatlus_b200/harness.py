@@ -313,6 +313,12 @@ class Harness:
             raise RuntimeError(f"{self.prefix}tone failed with code {rc}")
         return f, u8
 
+    def image_save(self, rgb, path, gamma: float = 1.0) -> None:
+        """Image::save (image.cpp:7-19) of an (H, W, 3) float plane through the host library."""
+        a = _f32(rgb)
+        h, w, _ = a.shape
+        self._fn("image_save")(a.ctypes.data_as(_c_float_p), h, w, str(path).encode(), ctypes.c_float(gamma))
+
     def obj_load(self, path) -> dict:
         """ObjData of an OBJ file as this library's loader reads it (obj/obj.hpp): vertices (n, 4), normals (n, 3),
         faces (n, 13) = vertices[4], textures[4], normals[4], n_vertices.  None when the loader gives up."""

@@ -182,6 +182,13 @@ int qzh_tone(const float* rgb, int n_pixels, float gamma, float* bgr255, unsigne
     return qz_tone(rgb, (uint32_t)n_pixels, gamma, bgr255, bgr8);
 }
 
+// Image::save (image.cpp:7-19) of an H x W x 3 float plane: "*.png" (what the reference's examples write), "*.ppm" or PFM
+int qzh_image_save(const float* rgb, int height, int width, const char* filename, float gamma) {
+    Image image(std::vector<float>(rgb, rgb + (size_t)height * width * 3), (size_t)height, (size_t)width);
+    image.save(filename, gamma);
+    return 0;
+}
+
 // ObjData of a file (obj/obj.hpp), flattened for the loader tests: counts = {vertices, normals, faces}; arrays may be null
 // (sizing call) and otherwise hold 4 floats per vertex (x y z w), 3 per normal, 13 ints per face (vertices[4], textures[4],
 // normals[4], n_vertices).  Returns 1 when the loader returns nullopt.

@@ -1,7 +1,7 @@
 // Image / RenderResult (reference image.hpp:8-45): float RGB planes, row 0 = image top.
-// save() writes a binary PPM (".ppm") or PFM (anything else) -- the reference's PNG writer
-// is OpenCV and its denoiser is OIDN (image.cpp:7-95); both are out of scope and absent
-// here, so denoise() only reports that.
+// save() writes an 8-bit RGB PNG (".png": the pixels cv::imwrite stores for the reference's matrix, image.cpp:7-19; own
+// encoder, host/src/png.cpp), a binary PPM (".ppm") or a PFM (anything else).  The reference's denoiser is OIDN
+// (image.cpp:21-95), out of scope and absent here: denoise() only reports that.
 #pragma once
 
 #include <cstddef>

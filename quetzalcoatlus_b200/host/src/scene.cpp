@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cctype>
 #include <chrono>
 #include <cstdlib>
 #include <cstring>
@@ -18,6 +19,7 @@
 
 #include "../obj/obj.hpp"
 #include "../onb.hpp"
+#include "../png.hpp"
 #include "../render.hpp"
 
 namespace {
@@ -494,13 +496,34 @@ RenderResult render(const Camera& camera, const Scene& scene, size_t n_samples, 
 }
 
 // ---------------------------------------------------------------- Image output
+static bool has_suffix(const std::string& name, const char* suffix) {
+    const size_t n = std::strlen(suffix);
+    if (name.size() < n) return false;
+    for (size_t i = 0; i < n; i++)
+        if (std::tolower((unsigned char)name[name.size() - n + i]) != suffix[i]) return false;
+    return true;
+}
+
 static void write_image(const std::string& filename, const std::vector<float>& buf, size_t w, size_t h, float gamma) {
+    if (has_suffix(filename, ".png")) {
+        // what the reference's examples save: the tone path of image.cpp:10-15 (x255, powf gamma, B and R swapped for
+        // OpenCV) runs as a kernel (qz_tone), the 8-bit values are the ones cv::imwrite stores for that CV_32FC3 matrix;
+        // OpenCV reads the matrix as BGR and writes RGB, so the PNG's pixels are in the film's own channel order
+        std::vector<unsigned char> px(w * h * 3);
+        if (qz_tone(buf.data(), uint32_t(w * h), gamma, nullptr, px.data()) != QZ_OK) {
+            std::cerr << "error: save failed: " << qz_last_error() << std::endl;
+            return;
+        }
+        for (size_t i = 0; i < w * h; i++) std::swap(px[3 * i], px[3 * i + 2]);
+        if (!qzhost::write_png_rgb8(filename, px.data(), w, h)) std::cerr << "Unable to write file " << filename << std::endl;
+        return;
+    }
     FILE* f = std::fopen(filename.c_str(), "wb");
     if (!f) {
         std::cerr << "Unable to open file " << filename << std::endl;
         return;
     }
-    bool ppm = filename.size() >= 4 && filename.compare(filename.size() - 4, 4, ".ppm") == 0;
+    bool ppm = has_suffix(filename, ".ppm");
     if (ppm) {
         // 8-bit: the tone path of image.cpp:10-15 (x255, powf gamma, BGR) runs as a kernel (qz_tone); a PPM stores RGB,
         // so the channel swap the reference does for OpenCV is undone when the rows are written

@@ -258,6 +258,79 @@ def test_obj_loader_file_that_ends_exactly_at_a_page_boundary(emu, oracle, tmp_p
     assert emu.obj_load(tmp_path / "missing.obj") is None and oracle.obj_load(tmp_path / "missing.obj") is None
 
 
+def _tone_torture_rgb():
+    rng = np.random.default_rng(21)
+    special = np.array([0.0, -0.0, 0.5 / 255, 1.5 / 255, 2.5 / 255, 127.5 / 255, 254.5 / 255, 1.0, 255.4 / 255, 255.5 / 255, 256.0 / 255, 2.0,
+                        -0.002, -1.0, np.nan, np.inf, -np.inf, 8.4e6, 8.5e6, 1e10, 1e30, -1e10, 3.4e38], np.float32)
+    rgb = np.concatenate([rng.uniform(0.0, 1.1, 30000), rng.uniform(-0.1, 40.0, 3000), rng.integers(0, 512, 3000) / 510.0,
+                          np.tile(special, 40), special[:3 * 7]]).astype(np.float32)
+    rgb = rgb[: len(rgb) // 3 * 3]
+    rng.shuffle(rgb)   # specials at every position of OpenCV's vector loops and their scalar tails
+    return rgb.reshape(1, -1, 3)
+
+
+def test_tone_path_against_opencv_itself(emu, oracle, tmp_path):
+    """The 8-bit values of Image::save (image.cpp:7-19) are whatever cv::imwrite makes of the CV_32FC3 matrix.  The C++
+    OpenCV the reference links is absent, but the image has OpenCV's Python build: the reference's matrix (255 * powf,
+    B and R swapped, from the oracle's libm expression) goes through cv2.imwrite -> cv2.imread, and both the oracle's
+    stand-in and the device-code restatement (csrc/math.cuh: tone_u8) must store the same bytes -- halves to even,
+    saturation, and NaN / infinities / values beyond int32 all 0."""
+    cv2 = pytest.importorskip("cv2")
+    rgb = _tone_torture_rgb()
+    for gamma in (1.0, 0.45454547):
+        bgr255, want_u8 = oracle.tone(rgb.reshape(-1, 3), gamma)
+        with np.errstate(all="ignore"):
+            assert cv2.imwrite(str(tmp_path / "ref.png"), bgr255.reshape(rgb.shape))
+        stored = cv2.imread(str(tmp_path / "ref.png"), cv2.IMREAD_UNCHANGED)
+        assert stored.dtype == np.uint8 and stored.shape == rgb.shape
+        assert (stored.reshape(-1, 3) == want_u8).all()
+        got_f, got_u8 = emu.tone(rgb.reshape(-1, 3), gamma)
+        if gamma == 1.0:
+            assert (got_u8 == stored.reshape(-1, 3)).all()
+        else:   # pow in double rounded once vs glibc powf: a value may sit on the other side of a half
+            assert (np.abs(got_u8.astype(int) - stored.reshape(-1, 3).astype(int)) <= 1).all() and (got_u8 != stored.reshape(-1, 3)).mean() < 1e-3
+
+
+def test_image_save_writes_the_png_opencv_would(emu, oracle, tmp_path):
+    """Image::save("*.png") of the host library (its own encoder, host/src/png.cpp) against the reference's recipe run
+    through OpenCV: same size, same pixels when decoded by OpenCV and by PIL; chunk CRCs and the zlib stream valid."""
+    import struct
+    import zlib
+
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(5)
+    for h, w in [(1, 1), (3, 5), (97, 131), (240, 320)]:   # (the last one spans several stored deflate blocks)
+        film = rng.uniform(-0.05, 1.3, (h, w, 3)).astype(np.float32)
+        film[0, 0] = [np.nan, np.inf, 2.0]
+        ours, ref = tmp_path / f"ours_{h}x{w}.PNG", tmp_path / f"ref_{h}x{w}.png"
+        emu.image_save(film, ours, 1.0)
+        bgr255, _ = oracle.tone(film.reshape(-1, 3), 1.0)
+        with np.errstate(all="ignore"):
+            assert cv2.imwrite(str(ref), bgr255.reshape(h, w, 3))
+        a, b = cv2.imread(str(ours), cv2.IMREAD_UNCHANGED), cv2.imread(str(ref), cv2.IMREAD_UNCHANGED)
+        assert a is not None and a.shape == b.shape == (h, w, 3) and (a == b).all()
+        # structure: signature, IHDR / IDAT / IEND with correct CRCs, stored zlib stream with a correct Adler-32
+        blob = ours.read_bytes()
+        assert blob[:8] == b"\x89PNG\r\n\x1a\n"
+        pos, chunks = 8, []
+        while pos < len(blob):
+            n, kind = struct.unpack(">I4s", blob[pos:pos + 8])
+            data = blob[pos + 8:pos + 8 + n]
+            assert struct.unpack(">I", blob[pos + 8 + n:pos + 12 + n])[0] == zlib.crc32(kind + data)
+            chunks.append((kind, data))
+            pos += 12 + n
+        assert [k for k, _ in chunks] == [b"IHDR", b"IDAT", b"IEND"]
+        assert chunks[0][1] == struct.pack(">IIBBBBB", w, h, 8, 2, 0, 0, 0)
+        raw = zlib.decompress(chunks[1][1])
+        rows = np.frombuffer(raw, np.uint8).reshape(h, 1 + 3 * w)
+        assert (rows[:, 0] == 0).all() and (rows[:, 1:].reshape(h, w, 3)[..., ::-1] == b).all()
+    try:
+        from PIL import Image as PILImage
+    except ImportError:
+        return
+    assert (np.asarray(PILImage.open(ours).convert("RGB"))[..., ::-1] == b).all()
+
+
 def test_strip_rows_are_balanced_and_keep_a_shard_on_its_own_pixel_classes():
     """bench.py / qz_render's multi-GPU strips: every rank owns the same number of rows, and where a power-of-two height
     does that, strip * ranks divides 128 -- a rank then owns 1/ranks of the (y mod 128) pixel classes, which is what its

@@ -405,6 +405,12 @@ def test_tone_path_against_oracle(qz, oracle, gamma):
         print(f"tone gamma {gamma}: {(got_f != want_f).mean():.2e} of values differ from glibc powf (by one ulp of the power)")
         assert ok.all()
         assert (np.abs(got_u8.astype(int) - want_u8.astype(int)) <= 1).all() and (got_u8 != want_u8).mean() < 1e-3
+    # NaN, infinities and values beyond int32 after the x255: OpenCV's conversion stores 0 for all of them (the oracle's
+    # stand-in is pinned against cv2.imwrite on the CPU, tests/test_abi_and_host.py)
+    special = np.array([[np.nan, np.inf, -np.inf], [1e10, 8.5e6, 8.4e6], [3.4e38, -1e10, 2.0]], np.float32)
+    assert (qz.tone(special, gamma)[1] == oracle.tone(special, gamma)[1]).all()
+    if gamma == 1.0:
+        assert qz.tone(special, gamma)[1].tolist() == [[0, 0, 0], [255, 0, 0], [255, 0, 0]]
 
 
 def test_film_stays_on_the_device_for_a_denoiser(qz):
