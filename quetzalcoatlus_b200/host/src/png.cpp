@@ -91,6 +91,7 @@ bool write_png_rgb8(const std::string& filename, const unsigned char* rgb, size_
         pos += n;
     }
     put_be32(z, (b << 16) | a);
+    ok = ok && z.size() <= 0x7fffffffu;   // (one IDAT chunk: a film beyond ~700 megapixels is refused, not truncated)
     ok = ok && write_chunk(f, "IDAT", z);
     ok = ok && write_chunk(f, "IEND", {});
     return (std::fclose(f) == 0) && ok;
