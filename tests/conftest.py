@@ -42,6 +42,10 @@ def oracle() -> Harness:
 
 @pytest.fixture(scope="session")
 def emu() -> Harness:
+    # QZ_EMU_LIB: another build of the emulation, e.g. one with -fsanitize=address,undefined (tests/emu/Makefile: sanitize)
+    override = os.environ.get("QZ_EMU_LIB")
+    if override:
+        return Harness(Path(override), "qzh_")
     _make(ROOT / "tests" / "emu")
     return Harness(EMU_LIB, "qzh_")
 
