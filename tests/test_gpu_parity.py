@@ -308,6 +308,35 @@ def test_bounce_limits(qz, oracle, mode, max_bounces):
             assert bits_equal(film.albedo, albedo / np.float32(4)).all(), name
 
 
+def test_paths_deeper_than_255_bounces(qz, oracle):
+    """max_bounces beyond the 8 bits the path depth had in round 1 (now a 16-bit field next to the sampler dimension):
+    kitchen_sink at max_bounces = 3000 keeps a twentieth of its paths alive for thousands of rays (lossless dielectrics).
+    The sampler dimension wraps the 1000-prime table many times on the way (sampler.cpp:404-454), all of it through the
+    late queue / k_sample.  Replay against the oracle within tolerance (ray counts included), and the wavefront film and its ray
+    statistics against the replay bit for bit."""
+    w, h, spp, deep_limit = 32, 24, 2, 3000
+    ys, xs, ss = np.meshgrid(np.arange(h), np.arange(w), np.arange(spp), indexing="ij")
+    all_xys = np.stack([xs.ravel(), (h - 1 - ys).ravel(), ss.ravel()], 1).astype(np.int32)
+    with qz.build_scene("kitchen_sink", w, h) as sg, oracle.build_scene("kitchen_sink", w, h) as so:
+        got = sg.trace_paths(all_xys, spp=spp, max_bounces=deep_limit)
+        want = so.trace_paths(all_xys, spp=spp, max_bounces=deep_limit)
+        assert (want[:, RAYS] > 1000).sum() >= 10, "the scene no longer has deep paths: pick another"
+        agree = path_agreement(want, got, REL_TOL)
+        print(f"deep paths: {(want[:, RAYS] > 1000).sum()} of {len(want)} beyond 1000 rays, longest {int(want[:, RAYS].max())}; "
+              f"{1.0 - agree.mean():.4%} outside rel {REL_TOL}")
+        assert 1.0 - agree.mean() <= MAX_DIVERGENT
+        film, st = sg.render_flags(spp, max_bounces=deep_limit)
+        rec = got.reshape(h, w, spp, 32)
+        color = np.zeros((h, w, 3), np.float32)
+        for s in range(spp):
+            color += rec[:, :, s, 20:23]
+        assert bits_equal(film.color, color / np.float32(spp)).all()
+        assert st["rays_closest"] + st["rays_shadow"] == int(got[:, RAYS].astype(np.int64).sum())
+    with pytest.raises(RuntimeError, match="65535"):
+        with qz.build_scene("cornell_box", 8, 8) as sc:
+            sc.render_flags(1, max_bounces=65536)
+
+
 def test_pipelines_do_not_change_the_film(qz, mode, small_mesh):
     """Renders large enough for the pool to be split into concurrent pipelines (two streams drawing
     paths from one cursor) against the single-pipeline run of the same call (stage timing forces one
