@@ -442,6 +442,19 @@ def test_tone_path_against_oracle(qz, oracle, gamma):
         assert qz.tone(special, gamma)[1].tolist() == [[0, 0, 0], [255, 0, 0], [255, 0, 0]]
 
 
+def test_image_save_png_through_the_product_library(qz, oracle, tmp_path):
+    """Image::save("*.png") of the host library as shipped -- tone kernel on the GPU, the library's own PNG encoder --
+    decodes to the bytes the reference's recipe stores (oracle's tone arithmetic, pinned against OpenCV on the CPU)."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(9)
+    film = rng.uniform(-0.05, 1.3, (60, 84, 3)).astype(np.float32)
+    film[0, 0] = [np.nan, np.inf, 1e10]
+    qz.image_save(film, tmp_path / "film.png", 1.0)
+    stored = cv2.imread(str(tmp_path / "film.png"), cv2.IMREAD_UNCHANGED)
+    _, want_bgr8 = oracle.tone(film.reshape(-1, 3), 1.0)
+    assert stored is not None and stored.shape == film.shape and (stored.reshape(-1, 3) == want_bgr8).all()
+
+
 def test_film_stays_on_the_device_for_a_denoiser(qz):
     """AOV hand-off (RenderResult::denoise, image.cpp:47-95): after render() the three planes are still on the device
     (qz_film_device) and equal what render() returned; the tone kernel runs on them in place (qz_tone_device)."""
