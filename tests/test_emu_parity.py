@@ -219,3 +219,15 @@ def test_sample_memo_negative_control(emu, monkeypatch, what):
         assert (~bits_equal(plain.albedo, off.albedo)).mean() > 0.5
     else:
         assert _planes_equal(plain, off) is False and bits_equal(plain.normal, off.normal).all()   # geometry does not depend on the spectra
+
+
+def test_paths_thousands_of_bounces_deep_bit_exact(emu, oracle):
+    """kitchen_sink at max_bounces = 3000: lossless dielectrics keep a twentieth of the paths alive for thousands of rays,
+    and the sampler's dimension counter wraps its 1000-prime table many times on the way (sampler.cpp:404-454)."""
+    from common import RAYS
+
+    with emu.build_scene("kitchen_sink", 64, 48) as se, oracle.build_scene("kitchen_sink", 64, 48) as so:
+        xys = pixel_samples(so, 1500, seed=12)
+        got, want = se.trace_paths(xys, max_bounces=3000), so.trace_paths(xys, max_bounces=3000)
+    assert (want[:, RAYS] > 1000).sum() >= 10
+    assert bits_equal(got, want).all()
