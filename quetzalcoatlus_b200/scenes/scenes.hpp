@@ -17,6 +17,8 @@
 
 #include <cmath>
 #include <complex>
+#include <cstdint>
+#include <cstdlib>
 #include <memory>
 #include <string>
 #include <vector>
@@ -280,6 +282,147 @@ inline void build_empty_sky(Bundle& b, const Options& o) {
     b.max_bounces = 8;
 }
 
+// Seeded random scenes for the parity tests ("fuzz:<seed>"): every material, texture, light and shape type of the
+// reference's scene API in combinations none of the shipped examples has -- rough and anisotropic conductors next to
+// dielectrics with dispersion, mixed materials of three children, emitters of every kind, with or without a
+// background.  Integer generator, float arithmetic and one draw per statement (argument evaluation order is
+// unspecified), so both builds of this header make the same scene.
+struct FuzzRng {
+    uint32_t state;
+    uint32_t next() { state = state * 1664525u + 1013904223u; return state >> 8; }
+    float uniform(float lo, float hi) { return lo + (hi - lo) * (float(next()) * (1.0f / 16777216.0f)); }
+    int pick(int n) { return int(next() % uint32_t(n)); }
+    Vec3 vec(float x0, float x1, float y0, float y1, float z0, float z1) {
+        const float x = uniform(x0, x1);
+        const float y = uniform(y0, y1);
+        const float z = uniform(z0, z1);
+        return Vec3(x, y, z);
+    }
+    Pt3 point(float x0, float x1, float y0, float y1, float z0, float z1) {
+        const Vec3 v = vec(x0, x1, y0, y1, z0, z1);
+        return Pt3(v.x, v.y, v.z);
+    }
+};
+
+inline std::shared_ptr<const Spectrum> fuzz_illuminant(FuzzRng& r) {
+    const int kind = r.pick(3);
+    if (kind == 0) return spectra::ILLUM_D65();
+    if (kind == 1) {
+        const Vec3 c = r.vec(0.2f, 3.f, 0.2f, 3.f, 0.2f, 3.f);
+        return std::make_shared<RGBIlluminantSpectrum>(RGB(c.x, c.y, c.z));
+    }
+    const float kelvin = r.uniform(2500.f, 9000.f);
+    return std::make_shared<BlackbodySpectrum>(kelvin);
+}
+
+// one non-mixed material, handed to `sink` as its concrete type (the reference's Material has no virtual destructor:
+// whoever stores it must know the type)
+template <class Sink>
+inline void fuzz_simple_material(FuzzRng& r, Sink&& sink) {
+    const int kind = r.pick(9);
+    const float a = r.uniform(0.f, 1.f);
+    const float c = r.uniform(0.f, 1.f);
+    const float d = r.uniform(0.f, 1.f);
+    const bool flag = r.pick(2) != 0;
+    switch (kind) {
+        case 0: sink(DiffuseMaterial(SolidColor(a, c, d))); break;
+        case 1: sink(DiffuseMaterial(DummyTexture{})); break;
+        case 2: sink(ConductiveMaterial(0.1f + 1.9f * a, 1.0f + 4.0f * c)); break;
+        case 3: sink(ConductiveMaterial::copper(0.6f * a, 0.6f * c)); break;
+        case 4: sink(ConductiveMaterial::alluminum(flag ? 0.01f + 0.5f * a : 0.0f, 0.5f * c)); break;
+        case 5: sink(DielectricMaterial(1.1f + 1.3f * a)); break;
+        case 6: sink(DielectricMaterial(flag ? spectra::GLASS_BK7_IOR() : spectra::GLASS_SF11_IOR())); break;
+        case 7: sink(ThinDielectricMaterial(1.1f + 0.9f * a)); break;
+        default: sink(DiffuseMaterial(SolidColor(spectra::CU_IOR()))); break;
+    }
+}
+
+inline std::unique_ptr<Material> fuzz_child(FuzzRng& r) {
+    std::unique_ptr<Material> out;
+    fuzz_simple_material(r, [&](auto&& m) { out = std::make_unique<std::decay_t<decltype(m)>>(std::move(m)); });
+    return out;
+}
+
+inline const Material* fuzz_material(Bundle& b, FuzzRng& r) {
+    const int kind = r.pick(6);
+    if (kind == 0) {
+        std::unique_ptr<Material> m0 = fuzz_child(r);
+        std::unique_ptr<Material> m1 = fuzz_child(r);
+        const float w0 = r.uniform(0.1f, 2.f);
+        const float w1 = r.uniform(0.1f, 2.f);
+        std::array<std::unique_ptr<Material>, 2> parts = {std::move(m0), std::move(m1)};
+        std::array<float, 2> weights = {w0, w1};
+        b.materials.push_back(std::make_shared<MixedMaterial<2>>(std::move(parts), std::move(weights)));
+        return b.materials.back().get();
+    }
+    if (kind == 1) {
+        std::unique_ptr<Material> m0 = fuzz_child(r);
+        std::unique_ptr<Material> m1 = fuzz_child(r);
+        std::unique_ptr<Material> m2 = fuzz_child(r);
+        const float w1 = r.uniform(0.1f, 2.f);
+        const float w2 = r.uniform(0.1f, 2.f);
+        std::array<std::unique_ptr<Material>, 3> parts = {std::move(m0), std::move(m1), std::move(m2)};
+        std::array<float, 3> weights = {1.0f, w1, w2};
+        b.materials.push_back(std::make_shared<MixedMaterial<3>>(std::move(parts), std::move(weights)));
+        return b.materials.back().get();
+    }
+    const Material* out = nullptr;
+    fuzz_simple_material(r, [&](auto&& m) { out = b.keep(std::move(m)); });
+    return out;
+}
+
+inline void build_fuzz(Bundle& b, const Options& o, uint32_t seed) {
+    FuzzRng r{seed * 2654435761u + 12345u};
+    for (int i = 0; i < 4; i++) r.next();
+    Scene& scene = *b.scene;
+    if (r.pick(3) != 0) {
+        auto spectrum = fuzz_illuminant(r);
+        const float scale = r.uniform(0.02f, 0.6f);
+        scene.set_bg_light(spectrum, scale);
+    }
+    const int n_lights = r.pick(4);   // (0: only the background, if any, lights the scene)
+    for (int i = 0; i < n_lights; i++) {
+        const Pt3 p = r.point(-3.f, 3.f, 0.5f, 3.5f, -8.f, -2.f);
+        const int kind = r.pick(3);
+        auto spectrum = fuzz_illuminant(r);
+        const float scale = r.uniform(1.f, 10.f);
+        const bool two_sided = r.pick(2) == 0;
+        if (kind == 0) {
+            scene.add_light(std::make_unique<PointLight>(p, spectrum, 3.0f * scale));
+        } else if (kind == 1) {
+            const float radius = r.uniform(0.15f, 0.6f);
+            scene.add_light(std::make_unique<AreaLight>(std::make_unique<Sphere>(p, radius), spectrum, scale, two_sided));
+        } else {
+            const Vec3 u = r.vec(0.3f, 1.5f, -0.3f, 0.3f, 0.f, 0.f);
+            const Vec3 v = r.vec(0.f, 0.f, -0.3f, 0.3f, 0.3f, 1.5f);
+            scene.add_light(std::make_unique<AreaLight>(std::make_unique<Quad>(p, u, v), spectrum, scale, two_sided));
+        }
+    }
+    scene.add_plane(Pt3(0.f, -2.f, 0.f), Vec3(0.f, 1.f, 0.f), fuzz_material(b, r), 40.0f);
+    if (r.pick(2)) {
+        const float tilt = r.uniform(-0.2f, 0.2f);
+        scene.add_plane(Pt3(0.f, 0.f, -10.f), Vec3(tilt, 0.f, 1.f), fuzz_material(b, r), 12.0f);
+    }
+    const int n_shapes = 3 + r.pick(6);
+    for (int i = 0; i < n_shapes; i++) {
+        const Pt3 c = r.point(-3.f, 3.f, -1.8f, 1.5f, -8.5f, -3.f);
+        const Material* m = fuzz_material(b, r);
+        const int kind = r.pick(3);
+        const Vec3 u = r.vec(0.5f, 2.f, -0.4f, 0.4f, -0.6f, 0.6f);
+        const Vec3 v = r.vec(-0.4f, 0.4f, 0.5f, 2.f, -0.6f, 0.6f);
+        if (kind == 0) scene.add_sphere(c, 0.5f * u.x, m);
+        else if (kind == 1) scene.add_triangle(c, c + u, c + v, m);
+        else scene.add_quad(c, c + u, c + u + v, c + v, m);
+    }
+    scene.commit();
+    const Vec3 eye = r.vec(-0.5f, 0.5f, -0.3f, 0.6f, 0.f, 1.5f);
+    const float yaw = r.uniform(-0.2f, 0.2f);
+    b.camera = std::make_unique<Camera>(o.width ? o.width : 96, o.height ? o.height : 72, M_PI / 3.0f,
+                                        Transform::translation(eye.x, eye.y, eye.z) * Transform::rotate_y(yaw));
+    b.n_samples = 4;
+    b.max_bounces = 24;
+}
+
 inline const char* const* scene_names(int* n) {
     static const char* const names[] = {"cornell_box", "glass_spheres", "textures", "opposing_planes",
                                         "obj_viewer", "cornell_mixed", "mandelbrot", "kitchen_sink"};
@@ -302,6 +445,7 @@ inline std::unique_ptr<Bundle> build(const std::string& name, const Options& o) 
     else if (name == "no_lights") build_no_lights(*b, o);
     else if (name == "empty_sky") build_empty_sky(*b, o);
     else if (name == "obj_viewer") { if (!build_obj_viewer(*b, o)) return nullptr; }
+    else if (name.rfind("fuzz:", 0) == 0) build_fuzz(*b, o, uint32_t(std::strtoul(name.c_str() + 5, nullptr, 10)));
     else return nullptr;
     return b;
 }
