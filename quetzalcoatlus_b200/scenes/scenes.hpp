@@ -305,12 +305,14 @@ struct FuzzRng {
 };
 
 inline std::shared_ptr<const Spectrum> fuzz_illuminant(FuzzRng& r) {
-    const int kind = r.pick(3);
-    if (kind == 0) return spectra::ILLUM_D65();
-    if (kind == 1) {
+    const int kind = r.pick(8);
+    if (kind < 3) return spectra::ILLUM_D65();
+    if (kind < 7) {
         const Vec3 c = r.vec(0.2f, 3.f, 0.2f, 3.f, 0.2f, 3.f);
         return std::make_shared<RGBIlluminantSpectrum>(RGB(c.x, c.y, c.z));
     }
+    // (one emitter in eight: the reference's BlackbodySpectrum is +inf at every wavelength -- its normalisation divides
+    // by blackbody(2.897721e-12 / T), which is 0 (spectrum.cpp:126-129) -- and so are the paths it lights)
     const float kelvin = r.uniform(2500.f, 9000.f);
     return std::make_shared<BlackbodySpectrum>(kelvin);
 }
