@@ -13,6 +13,7 @@ QZ_FLAG_EXACT_ARITHMETIC) and every path test runs in both:
 An ulp can flip a discrete decision (Russian roulette, a texel), so the tests bound the FRACTION
 of paths outside tolerance instead of demanding zero.
 """
+import os
 from pathlib import Path
 
 import numpy as np
@@ -335,6 +336,22 @@ def test_paths_deeper_than_255_bounces(qz, oracle):
     with pytest.raises(RuntimeError, match="65535"):
         with qz.build_scene("cornell_box", 8, 8) as sc:
             sc.render_flags(1, max_bounces=65536)
+
+
+@pytest.mark.skipif(not os.environ.get("QZ_GPU_FUZZ"), reason="opt-in (QZ_GPU_FUZZ=1): written after this round's GPU budget was spent, "
+                    "not yet run on a GPU; the same scenes are bit-exact in the CPU emulation (tests/test_emu_parity.py)")
+@pytest.mark.parametrize("seed", range(8))
+def test_random_scenes_against_oracle(qz, oracle, mode, seed):
+    """The seeded random scenes of the CPU suite through the GPU library: per-path agreement within the north-star
+    tolerance on the paths whose reference radiance is finite, and the same set of non-finite paths."""
+    name = f"fuzz:{seed}"
+    with qz.build_scene(name) as sg, oracle.build_scene(name) as so:
+        xys = pixel_samples(so, 3000, seed=seed)
+        got, want = sg.trace_paths(xys), so.trace_paths(xys)
+    finite = np.isfinite(want[:, RADIANCE]).all(1)
+    assert (np.isfinite(got[:, RADIANCE]).all(1) == finite).mean() >= 1.0 - MAX_DIVERGENT
+    if finite.any():
+        assert 1.0 - path_agreement(want[finite], got[finite], REL_TOL).mean() <= MAX_DIVERGENT
 
 
 def test_pipelines_do_not_change_the_film(qz, mode, small_mesh):
