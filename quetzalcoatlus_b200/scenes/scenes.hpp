@@ -409,12 +409,34 @@ inline void build_fuzz(Bundle& b, const Options& o, uint32_t seed) {
     for (int i = 0; i < n_shapes; i++) {
         const Pt3 c = r.point(-3.f, 3.f, -1.8f, 1.5f, -8.5f, -3.f);
         const Material* m = fuzz_material(b, r);
-        const int kind = r.pick(3);
+        const int kind = r.pick(4);
         const Vec3 u = r.vec(0.5f, 2.f, -0.4f, 0.4f, -0.6f, 0.6f);
         const Vec3 v = r.vec(-0.4f, 0.4f, 0.5f, 2.f, -0.6f, 0.6f);
-        if (kind == 0) scene.add_sphere(c, 0.5f * u.x, m);
-        else if (kind == 1) scene.add_triangle(c, c + u, c + v, m);
-        else scene.add_quad(c, c + u, c + u + v, c + v, m);
+        if (kind == 0) {
+            scene.add_sphere(c, 0.5f * u.x, m);
+        } else if (kind == 1) {
+            scene.add_triangle(c, c + u, c + v, m);
+        } else if (kind == 2) {
+            scene.add_quad(c, c + u, c + u + v, c + v, m);
+        } else {
+            // a height grid (Scene::add_grid, scene.cpp:375-430): rows x cols vertices over the patch u x v, bumpy
+            const int rows = 2 + r.pick(6);
+            const int cols = 2 + r.pick(6);
+            Image grid{size_t(rows), size_t(cols)};
+            for (int y = 0; y < rows; y++) {
+                for (int x = 0; x < cols; x++) {
+                    const float fu = float(x) / float(cols - 1);
+                    const float fv = float(y) / float(rows - 1);
+                    const float bump = r.uniform(-0.25f, 0.25f);
+                    const size_t at = 3 * (size_t(y) * size_t(cols) + size_t(x));
+                    grid.color_buffer[at + 0] = fu * u.x + fv * v.x;
+                    grid.color_buffer[at + 1] = fu * u.y + fv * v.y;
+                    grid.color_buffer[at + 2] = fu * u.z + fv * v.z + bump;
+                }
+            }
+            const float turn = r.uniform(-0.6f, 0.6f);
+            scene.add_grid(grid, m, Transform::translation(c.x, c.y, c.z) * Transform::rotate_x(turn));
+        }
     }
     scene.commit();
     const Vec3 eye = r.vec(-0.5f, 0.5f, -0.3f, 0.6f, 0.f, 1.5f);
