@@ -284,8 +284,8 @@ inline void build_empty_sky(Bundle& b, const Options& o) {
 
 // Seeded random scenes for the parity tests ("fuzz:<seed>"): every material, texture, light and shape type of the
 // reference's scene API in combinations none of the shipped examples has -- rough and anisotropic conductors next to
-// dielectrics with dispersion, mixed materials of three children, emitters of every kind, with or without a
-// background.  Integer generator, float arithmetic and one draw per statement (argument evaluation order is
+// dielectrics with dispersion, mixed materials of three children, image textures, bumpy height grids, emitters of
+// every kind, with or without a background.  Integer generator, float arithmetic and one draw per statement (argument evaluation order is
 // unspecified), so both builds of this header make the same scene.
 struct FuzzRng {
     uint32_t state;
@@ -321,11 +321,20 @@ inline std::shared_ptr<const Spectrum> fuzz_illuminant(FuzzRng& r) {
 // whoever stores it must know the type)
 template <class Sink>
 inline void fuzz_simple_material(FuzzRng& r, Sink&& sink) {
-    const int kind = r.pick(9);
+    const int kind = r.pick(10);
     const float a = r.uniform(0.f, 1.f);
     const float c = r.uniform(0.f, 1.f);
     const float d = r.uniform(0.f, 1.f);
     const bool flag = r.pick(2) != 0;
+    if (kind == 9) {
+        // an image texture of a few random texels (texture.cpp: ImageTexture::value -> RGB-to-spectrum lookup per texel)
+        const int rows = 1 + r.pick(7);
+        const int cols = 1 + r.pick(7);
+        Image image{size_t(rows), size_t(cols)};
+        for (size_t i = 0; i < image.color_buffer.size(); i++) image.color_buffer[i] = r.uniform(0.f, 1.f);
+        sink(DiffuseMaterial(ImageTexture(std::move(image))));
+        return;
+    }
     switch (kind) {
         case 0: sink(DiffuseMaterial(SolidColor(a, c, d))); break;
         case 1: sink(DiffuseMaterial(DummyTexture{})); break;
