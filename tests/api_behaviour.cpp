@@ -1,0 +1,42 @@
+// The same program against two libraries: the reference's sources (oracle/_ref) and the host library.  Prints what a
+// user of the scene API observes in the corner cases; the test compares the two outputs line by line.
+#include <cstdint>
+#include <cstring>
+#include <iostream>
+
+#include "render.hpp"
+
+static uint64_t plane_hash(const std::vector<float>& v) {
+    uint64_t h = 1469598103934665603ull;
+    for (float f : v) {
+        uint32_t u;
+        std::memcpy(&u, &f, 4);
+        for (int k = 0; k < 4; k++) { h ^= (u >> (8 * k)) & 0xffu; h *= 1099511628211ull; }
+    }
+    return h;
+}
+
+int main() {
+    Scene scene(initialize_device());
+    DiffuseMaterial grey(SolidColor(0.5f, 0.5f, 0.5f));
+    std::cout << "ready before commit: " << scene.ready() << std::endl;
+    auto* missing = scene.add_obj("/nonexistent/mesh.obj", &grey);
+    std::cout << "add_obj(missing file) -> " << (missing ? "geometry" : "nullptr") << std::endl;
+    Camera camera(8, 6, M_PI / 3.0f);
+    RenderResult early = render(camera, scene, 2, 4);
+    double sum = 0.0;
+    for (float f : early.color_buffer) sum += f;
+    std::cout << "render(not committed): " << early.width << "x" << early.height << " planes " << early.color_buffer.size() << " "
+              << early.normal_buffer.size() << " " << early.albedo_buffer.size() << " sum " << sum << std::endl;
+    scene.add_sphere(Pt3(0.f, 0.f, -4.f), 1.0f, &grey);
+    scene.add_plane(Pt3(0.f, -1.f, 0.f), Vec3(0.f, 1.f, 0.f), &grey, 20.0f);
+    scene.add_light(std::make_unique<PointLight>(Pt3(2.f, 3.f, -1.f), spectra::ILLUM_D65(), 20.0f));
+    scene.commit();
+    std::cout << "ready after commit: " << scene.ready() << std::endl;
+    RenderResult film = render(camera, scene, 3, 5);
+    std::cout << "film " << film.width << "x" << film.height << " color " << std::hex << plane_hash(film.color_buffer) << " normal "
+              << plane_hash(film.normal_buffer) << " albedo " << plane_hash(film.albedo_buffer) << std::dec << std::endl;
+    RenderResult none = render(camera, scene, 1, 0);
+    std::cout << "zero bounces color " << std::hex << plane_hash(none.color_buffer) << std::dec << std::endl;
+    return 0;
+}

@@ -2,6 +2,7 @@
 symbol include/qz_b200.h declares; without a device it fails LOUDLY (no CPU fallback); the
 reference's own example programs and colour test compile UNCHANGED against the host headers."""
 import ctypes
+import os
 import re
 import subprocess
 from pathlib import Path
@@ -99,6 +100,34 @@ def test_reference_examples_compile_unchanged_against_the_host_headers(example, 
 
 
 @pytest.mark.skipif(not REFERENCE.exists(), reason="/root/reference not present")
+def test_same_program_against_both_libraries_behaves_the_same(emu, oracle, tmp_path):
+    """tests/api_behaviour.cpp -- written against the reference's public scene API only -- is compiled twice: against
+    the reference's headers and linked with the reference's own objects (oracle/_ref), and against the host library's
+    headers linked with the host library (over the emulation of the device code, so that it runs here).  What a user
+    observes must be the same: ready() before / after commit, add_obj on a missing file, render() on a scene that was
+    not committed (message + zero film of the right size), and the films of two renders bit for bit."""
+    if not REFERENCE.exists():
+        pytest.skip("/root/reference is absent")
+    src = ROOT / "tests" / "api_behaviour.cpp"
+    common = ["g++", "-std=c++20", "-O2", "-ffp-contract=off", "-w", str(src)]
+    ref_dir, emu_dir = ROOT / "oracle" / "_ref", ROOT / "tests" / "emu" / "_build"
+    subprocess.run(common + ["-DNO_BOOST", f"-I{REFERENCE / 'src'}", f"-I{ROOT / 'oracle' / 'embree_shim'}", f"-L{ref_dir}", "-loracle_ref",
+                             f"-Wl,-rpath,{ref_dir}", "-o", str(tmp_path / "api_ref")], check=True, capture_output=True, timeout=300)
+    subprocess.run(common + [f"-I{ROOT / 'include'}", f"-I{ROOT / 'quetzalcoatlus_b200' / 'host'}", f"-L{emu_dir}", "-lqz_emu_harness",
+                             f"-Wl,-rpath,{emu_dir}", "-o", str(tmp_path / "api_emu")], check=True, capture_output=True, timeout=300)
+    env = dict(os.environ, QZ_DATA_DIR=str(ROOT / "quetzalcoatlus_b200" / "data"))
+
+    def observed(exe):
+        out = subprocess.run([str(tmp_path / exe)], capture_output=True, text=True, check=True, timeout=120, env=env,
+                             cwd=ROOT / "quetzalcoatlus_b200" / "data").stdout
+        skip = ("Rendering with", "Render time", "[")   # thread count, timing and the progress bar
+        return [line for line in out.splitlines() if line.strip() and not line.startswith(skip)]
+
+    ref, ours = observed("api_ref"), observed("api_emu")
+    assert ref == ours
+    assert "Scene must be committed before rendering." in ours and any(line.startswith("film 8x6 color") for line in ours)
+
+
 def test_reference_color_test_against_the_host_library(tmp_path):
     """The reference's colour smoke test, compiled unchanged against the host colour classes, prints
     the values the reference prints."""
