@@ -1,0 +1,144 @@
+"""Offline sweep of the seeded random parity scenes (scenes/scenes.hpp: build_fuzz) and random meshes through the
+device-code emulation (tests/emu) against the oracle, on seed ranges the test suite does not hold.
+
+TEST INFRASTRUCTURE, CPU only: loads oracle/_ref and tests/emu/_build, never the product library.
+
+    python tools/fuzz_sweep.py --exact 1000:3000 --fast 5000:5600 --mesh 1000:1400 --jobs 8 --out profiles/r02_fuzz_sweep.json
+
+exact: every field of every replayed path bit for bit (tests/test_emu_parity.py::test_random_scenes_bit_exact)
+fast : the radiometric build: discrete decisions identical, finite radiance within the reported relative deviation
+mesh : OBJ loader -> LBVH -> wide-BVH traversal: closest hits and paths bit for bit
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import sys
+import tempfile
+import time
+from concurrent.futures import ProcessPoolExecutor
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+N_PATHS = 1200
+
+
+def _libs():
+    from quetzalcoatlus_b200.harness import Harness
+
+    build = ROOT / "tests" / "emu" / "_build"
+    return (Harness(ROOT / "oracle" / "_ref" / "liboracle_ref.so", "orc_"), Harness(build / "libqz_emu_harness.so", "qzh_"),
+            Harness(build / "libqz_emu_fast_harness.so", "qzh_"))
+
+
+def run_exact(seed: int) -> dict:
+    from common import bits_equal, pixel_samples
+
+    oracle, emu, _ = _libs()
+    name = f"fuzz:{seed}"
+    with emu.build_scene(name) as se, oracle.build_scene(name) as so:
+        cam = bool(bits_equal(se.camera_fields(), so.camera_fields()).all())
+        xys = pixel_samples(so, N_PATHS, seed=seed)
+        got, want = se.trace_paths(xys), so.trace_paths(xys)
+    bad = ~bits_equal(got, want).all(1)
+    return {"kind": "exact", "seed": seed, "paths": len(bad), "differing": int(bad.sum()) + (0 if cam else len(bad))}
+
+
+def run_fast(seed: int) -> dict:
+    from common import NORMAL, RADIANCE, RAYS, bits_equal, pixel_samples
+
+    oracle, _, fast = _libs()
+    name = f"fuzz:{seed}"
+    with fast.build_scene(name) as sf, oracle.build_scene(name) as so:
+        xys = pixel_samples(so, N_PATHS, seed=seed)
+        got, want = sf.trace_paths(xys), so.trace_paths(xys)
+    discrete = (got[:, RAYS] == want[:, RAYS]) & bits_equal(got[:, :4], want[:, :4]).all(1) & bits_equal(got[:, NORMAL], want[:, NORMAL]).all(1)
+    g, w = got[:, RADIANCE].astype(np.float64), want[:, RADIANCE].astype(np.float64)
+    nonfinite_same = bool((np.isfinite(g) == np.isfinite(w)).all() and (g[~np.isfinite(w)] == w[~np.isfinite(w)]).all())
+    finite = np.isfinite(w).all(1) & np.isfinite(g).all(1)
+    worst = 0.0
+    if finite.any():
+        scale = max(np.abs(w[finite]).max(), 1e-6)
+        worst = float((np.abs(g[finite] - w[finite]) / np.maximum(np.abs(w[finite]), 1e-2 * scale)).max())
+    return {"kind": "fast", "seed": seed, "paths": len(discrete), "discrete_differing": int((~discrete).sum()),
+            "nonfinite_same": nonfinite_same, "worst_rel": worst}
+
+
+def run_mesh(seed: int) -> dict:
+    from common import bits_equal, pixel_samples
+    from test_emu_parity import _random_mesh_obj
+
+    oracle, emu, _ = _libs()
+    with tempfile.TemporaryDirectory() as tmp:
+        path = Path(tmp) / "mesh.obj"
+        rng = _random_mesh_obj(path, seed)
+        kw = dict(obj_path=str(path), obj_material=["diffuse", "glass", "alluminum", "copper"][seed % 4],
+                  obj_light=["point", "area", "ambient"][seed % 3])
+        with emu.build_scene("obj_viewer", 48, 36, **kw) as se, oracle.build_scene("obj_viewer", 48, 36, **kw) as so:
+            o = np.tile(so.camera_fields()[0], (3000, 1)) + rng.normal(0, 0.4, (3000, 3))
+            d = rng.normal(0, 1, (3000, 3))
+            d[:, 2] -= 1.5
+            rays = np.concatenate([o, d], 1).astype(np.float32)
+            hits = int((~bits_equal(se.intersect(rays), so.intersect(rays)).all(1)).sum())
+            xys = pixel_samples(so, 1000, seed=seed)
+            paths = int((~bits_equal(se.trace_paths(xys), so.trace_paths(xys)).all(1)).sum())
+    return {"kind": "mesh", "seed": seed, "rays": 3000, "paths": 1000, "hits_differing": hits, "paths_differing": paths}
+
+
+def _guard(fn, seed):
+    try:
+        return fn(seed)
+    except Exception as e:  # a failing seed must be reported, not lost
+        return {"kind": fn.__name__[4:], "seed": seed, "error": f"{type(e).__name__}: {e}"}
+
+
+def _span(s: str) -> range:
+    a, b = (int(v) for v in s.split(":"))
+    return range(a, b)
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--exact", default="")
+    ap.add_argument("--fast", default="")
+    ap.add_argument("--mesh", default="")
+    ap.add_argument("--jobs", type=int, default=8)
+    ap.add_argument("--out", default="")
+    a = ap.parse_args()
+    jobs = [(run_exact, s) for s in (_span(a.exact) if a.exact else [])]
+    jobs += [(run_fast, s) for s in (_span(a.fast) if a.fast else [])]
+    jobs += [(run_mesh, s) for s in (_span(a.mesh) if a.mesh else [])]
+    t0 = time.time()
+    with ProcessPoolExecutor(a.jobs) as pool:
+        rows = list(pool.map(_guard, *zip(*jobs), chunksize=4))
+    summary = {"command": " ".join(sys.argv), "seconds": round(time.time() - t0, 1)}
+    ex = [r for r in rows if r["kind"] == "exact" and "error" not in r]
+    fa = [r for r in rows if r["kind"] == "fast" and "error" not in r]
+    me = [r for r in rows if r["kind"] == "mesh" and "error" not in r]
+    if ex:
+        summary["exact"] = {"seeds": a.exact, "scenes": len(ex), "paths": sum(r["paths"] for r in ex),
+                            "differing_paths": sum(r["differing"] for r in ex), "seeds_with_differences": [r["seed"] for r in ex if r["differing"]]}
+    if fa:
+        worst = max(fa, key=lambda r: r["worst_rel"])
+        summary["fast"] = {"seeds": a.fast, "scenes": len(fa), "paths": sum(r["paths"] for r in fa),
+                           "paths_with_a_different_discrete_decision": sum(r["discrete_differing"] for r in fa),
+                           "seeds_with_a_different_discrete_decision": [r["seed"] for r in fa if r["discrete_differing"]],
+                           "seeds_with_different_nonfinite_paths": [r["seed"] for r in fa if not r["nonfinite_same"]],
+                           "worst_relative_radiance_deviation": worst["worst_rel"], "worst_seed": worst["seed"]}
+    if me:
+        summary["mesh"] = {"seeds": a.mesh, "meshes": len(me), "rays": sum(r["rays"] for r in me), "paths": sum(r["paths"] for r in me),
+                           "differing_hits": sum(r["hits_differing"] for r in me), "differing_paths": sum(r["paths_differing"] for r in me)}
+    summary["errors"] = [r for r in rows if "error" in r]
+    text = json.dumps(summary, indent=1)
+    print(text)
+    if a.out:
+        Path(a.out).write_text(text + "\n")
+
+
+if __name__ == "__main__":
+    main()
