@@ -258,7 +258,10 @@ int qz_scene_commit(qz_scene scene, const qz_scene_tables* tables);
 int qz_scene_build_ms(qz_scene scene, float* ms);
 
 /* render() (render.hpp:8-13, render.cpp:321-397) with HOST output buffers: H*W*3 floats
- * each, RGB interleaved, row 0 = top (image.hpp:26-45).  Any of normal/albedo may be NULL. */
+ * each, RGB interleaved, row 0 = top (image.hpp:26-45).  Any of normal/albedo may be NULL.
+ * Limits (QZ_ERR_INVALID beyond them): max_bounces <= 65535; n_samples * sampler stride < 2^31 (stride = 31104 from
+ * 128 x 128 pixels on, i.e. n_samples <= 69042) -- past that the reference's own `sample_index * sample_stride`
+ * (sampler.cpp:419, int * int) overflows, which is undefined there.  The probes below apply the same rule to `s`.   */
 int qz_render(qz_scene scene, const qz_camera* camera, uint32_t n_samples, uint32_t max_bounces,
               const qz_region* region, const qz_render_options* options,
               float* color, float* normal, float* albedo, qz_stats* stats);

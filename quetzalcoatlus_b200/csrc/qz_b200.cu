@@ -1045,6 +1045,16 @@ int qz_tone(const float* rgb, uint32_t n_pixels, float gamma, float* bgr255, uin
 }
 
 // ------------------------------------------------------------------ probes
+// The sampler's index is defined while (s + 1) * stride < 2^31: the reference multiplies two ints (sampler.cpp:419), beyond
+// that its result is undefined.  render_impl() refuses such sample counts; the probes refuse such sample numbers.
+static bool sample_numbers_defined(const int32_t* q, uint32_t n, int words, const SamplerParams& spar) {
+    for (uint32_t i = 0; i < n; i++) {
+        const int64_t s = q[(size_t)i * words + 2];
+        if (s < 0 || (uint64_t)(s + 1) * spar.stride >= (1ull << 31)) return false;
+    }
+    return true;
+}
+
 int qz_trace_paths(qz_scene s, const qz_camera* camera, uint32_t n_samples, uint32_t max_bounces, uint32_t n,
                    const int32_t* xys, float* records) {
     (void)n_samples;
@@ -1052,6 +1062,8 @@ int qz_trace_paths(qz_scene s, const qz_camera* camera, uint32_t n_samples, uint
     if (!s->store.committed) return fail(QZ_ERR_NOT_COMMITTED, "Scene must be committed before rendering.");
     QZ_CUDA(cudaSetDevice(s->device));
     if (!n) return QZ_OK;
+    if (!sample_numbers_defined(xys, n, 3, make_sampler_params((int)camera->image_width, (int)camera->image_height)))
+        return fail(QZ_ERR_INVALID, "sample number negative or too large for the 32-bit Halton index");
     DevBuf dx, dr, sensor;
     QZ_CUDA(dx.alloc((size_t)n * 12));
     QZ_CUDA(dr.alloc((size_t)n * 128));
@@ -1079,6 +1091,10 @@ int qz_sampler_eval(uint32_t n_samples, uint32_t width, uint32_t height, uint32_
     int rc = ensure_device();
     if (rc) return rc;
     if (!n) return QZ_OK;
+    if (!q || !out) return fail(QZ_ERR_INVALID, "null argument");
+    if (!width || !height) return fail(QZ_ERR_INVALID, "empty image");
+    if (!sample_numbers_defined(q, n, 4, make_sampler_params((int)width, (int)height)))
+        return fail(QZ_ERR_INVALID, "sample number negative or too large for the 32-bit Halton index");
     DeviceTables t;
     rc = device_tables(g_device, t);
     if (rc) return rc;

@@ -95,12 +95,22 @@ int qz_scene_commit(qz_scene s, const qz_scene_tables* t) {
     return QZ_OK;
 }
 
+// same rule as the product's probes (csrc/qz_b200.cu): the index is defined while (s + 1) * stride < 2^31 (sampler.cpp:419)
+static bool sample_numbers_defined(const int32_t* q, uint32_t n, int words, const SamplerParams& spar) {
+    for (uint32_t i = 0; i < n; i++) {
+        const int64_t s = q[(size_t)i * words + 2];
+        if (s < 0 || (uint64_t)(s + 1) * spar.stride >= (1ull << 31)) return false;
+    }
+    return true;
+}
+
 int qz_trace_paths(qz_scene s, const qz_camera* camera, uint32_t n_samples, uint32_t max_bounces, uint32_t n,
                    const int32_t* xys, float* records) {
     (void)n_samples;
     if (!s->store.committed) { g_error = "scene not committed"; return QZ_ERR_NOT_COMMITTED; }
     DCamera cam = make_camera(camera);
     SamplerParams spar = make_sampler_params((int)cam.width, (int)cam.height);
+    if (!sample_numbers_defined(xys, n, 3, spar)) { g_error = "sample number negative or too large for the 32-bit Halton index"; return QZ_ERR_INVALID; }
     for (uint32_t i = 0; i < n; i++) {
         PathState ps; PathAov aov; Spec4 lambda0;
         run_path<false>(s->store.view, cam, spar, (uint32_t)xys[3 * i], (uint32_t)xys[3 * i + 1], (uint32_t)xys[3 * i + 2],
@@ -208,6 +218,7 @@ int qz_render_device(qz_scene, const qz_camera*, uint32_t, uint32_t, const qz_re
 int qz_sampler_eval(uint32_t, uint32_t width, uint32_t height, uint32_t n, const int32_t* q, float* out) {
     ensure_tables();
     SamplerParams spar = make_sampler_params((int)width, (int)height);
+    if (!sample_numbers_defined(q, n, 4, spar)) { g_error = "sample number negative or too large for the 32-bit Halton index"; return QZ_ERR_INVALID; }
     for (uint32_t i = 0; i < n; i++) {
         Sampler smp = sampler_start(spar, (uint32_t)q[4 * i], (uint32_t)q[4 * i + 1], (uint32_t)q[4 * i + 2]);
         int dim = q[4 * i + 3];

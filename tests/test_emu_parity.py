@@ -31,6 +31,23 @@ def test_sampler_small_images_and_dimension_wrap(emu, oracle):
         assert bits_equal(emu.sampler_eval(64, w, h, q), oracle.sampler_eval(64, w, h, q)).all(), (w, h)
 
 
+def test_sampler_up_to_the_largest_defined_sample_number(emu, oracle):
+    """The reference computes `sample_index * sample_stride` in int (sampler.cpp:419): defined up to 69042 samples at the
+    stride of 31104 that images of 128 x 128 pixels and more have.  Bit-exact right up to that, refused beyond it (by
+    the probes here, by qz_render for the sample count: tests/test_gpu_parity.py::test_error_conventions)."""
+    rng = np.random.default_rng(5)
+    for w, h in [(128, 128), (800, 800), (3840, 2160)]:
+        q = np.stack([rng.integers(0, w, 400), rng.integers(0, h, 400), rng.integers(68000, 69042, 400), rng.integers(0, 1000, 400)], 1)
+        q[0, 2] = 69041
+        assert bits_equal(emu.sampler_eval(69042, w, h, q), oracle.sampler_eval(69042, w, h, q)).all(), (w, h)
+        q[0, 2] = 69042
+        with pytest.raises(RuntimeError):
+            emu.sampler_eval(69043, w, h, q)
+    # small images have a smaller stride (8 x 9 = 72 for 8 x 8 pixels) and a correspondingly larger range
+    q = np.stack([rng.integers(0, 8, 400), rng.integers(0, 8, 400), rng.integers(0, 2 ** 31 // 72 - 1, 400), rng.integers(0, 1000, 400)], 1)
+    assert bits_equal(emu.sampler_eval(1, 8, 8, q), oracle.sampler_eval(1, 8, 8, q)).all()
+
+
 @pytest.mark.parametrize("name", SPECTRA)
 def test_spectra_bit_exact(emu, oracle, name):
     lam = np.concatenate([np.random.default_rng(1).uniform(355, 835, 3000), np.arange(355, 836, dtype=np.float64)]).astype(np.float32)

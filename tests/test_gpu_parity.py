@@ -561,3 +561,8 @@ def test_error_conventions(qz):
     assert lib.qz_render(scene, ctypes.byref(cam), 1, 1, None, None, out.ctypes.data_as(ctypes.c_void_p), None, None, None) == 3
     assert b"committed" in lib.qz_last_error()
     assert lib.qz_scene_destroy(scene) == 0
+    # more samples than the sampler's index arithmetic defines: the reference computes `sample_index * sample_stride` in
+    # int (sampler.cpp:419), which overflows past 2^31 -- stride 31104 from 128 x 128 pixels on, i.e. beyond 69042 samples
+    with qz.build_scene("cornell_box", 128, 128) as sc:
+        with pytest.raises(RuntimeError, match="Halton"):
+            sc.render_flags(69043)

@@ -8,6 +8,8 @@ TEST INFRASTRUCTURE, CPU only: loads oracle/_ref and tests/emu/_build, never the
 exact: every field of every replayed path bit for bit (tests/test_emu_parity.py::test_random_scenes_bit_exact)
 fast : the radiometric build: discrete decisions identical, finite radiance within the reported relative deviation
 film : whole films (pixel loop, ordered accumulation, division) bit for bit, three planes
+obj  : OBJ text loader on torture files against the reference's own regex loader, record by record
+sampler: the Halton sampler at random resolutions / sample counts, bit for bit
 mesh : OBJ loader -> LBVH -> wide-BVH traversal: closest hits and paths bit for bit
 """
 from __future__ import annotations
@@ -105,6 +107,46 @@ def run_film(seed: int) -> dict:
     return {"kind": "film", "seed": seed, "values": 9 * w * h, "differing": bad}
 
 
+def run_obj(seed: int) -> dict:
+    """OBJ text loader on a torture file (tests/test_abi_and_host.py: _torture_obj_lines) against the reference's own regex
+    loader compiled into the oracle: ObjData record by record."""
+    from test_abi_and_host import _torture_obj_lines
+
+    oracle, emu, _ = _libs()
+    with tempfile.TemporaryDirectory() as tmp:
+        path = Path(tmp) / "torture.obj"
+        path.write_bytes("\n".join(_torture_obj_lines(np.random.default_rng(seed))).encode())
+        got, want = emu.obj_load(path), oracle.obj_load(path)
+    bad = 0
+    for key in ("vertices", "normals"):
+        if got[key].shape != want[key].shape:
+            bad += 1
+        else:
+            bad += int((got[key].view(np.uint32) != want[key].view(np.uint32)).sum())
+    gf, wf = got["faces"], want["faces"]
+    if gf.shape != wf.shape:
+        bad += 1
+    else:
+        defined = (gf[:, 8:12] == 0).all(1) | (gf[:, 4:8] != 0).any(1)
+        bad += int((gf[:, :4] != wf[:, :4]).sum() + (gf[:, 8:] != wf[:, 8:]).sum() + (gf[defined, 4:8] != wf[defined, 4:8]).sum())
+    return {"kind": "obj", "seed": seed, "records": int(len(want["vertices"]) + len(want["normals"]) + len(wf)), "differing": bad}
+
+
+def run_sampler(seed: int) -> dict:
+    """Owen-scrambled Halton sampler (sampler.cpp:161-454) at a random resolution and sample count: (x, y, s, dimension) ->
+    float, bit for bit; dimensions across the whole 1000-prime table."""
+    from common import bits_equal
+
+    oracle, emu, _ = _libs()
+    rng = np.random.default_rng(seed)
+    w, h = int(rng.integers(1, 8193)), int(rng.integers(1, 8193))
+    spp = int(rng.choice([1, 2, 3, 7, 24, 36, 128, 1000, 1024, 4096, int(rng.integers(1, 69000))]))   # (beyond 69042 x 31104 the reference's int index overflows: refused by qz_render)
+    n = 2000
+    q = np.stack([rng.integers(0, w, n), rng.integers(0, h, n), rng.integers(0, spp, n), rng.integers(0, 1000, n)], 1)
+    bad = int((~bits_equal(emu.sampler_eval(spp, w, h, q), oracle.sampler_eval(spp, w, h, q))).sum())
+    return {"kind": "sampler", "seed": seed, "values": n, "differing": bad}
+
+
 def _guard(fn, seed):
     try:
         return fn(seed)
@@ -123,6 +165,8 @@ def main() -> None:
     ap.add_argument("--fast", default="")
     ap.add_argument("--mesh", default="")
     ap.add_argument("--film", default="")
+    ap.add_argument("--obj", default="")
+    ap.add_argument("--sampler", default="")
     ap.add_argument("--jobs", type=int, default=8)
     ap.add_argument("--out", default="")
     a = ap.parse_args()
@@ -130,6 +174,8 @@ def main() -> None:
     jobs += [(run_fast, s) for s in (_span(a.fast) if a.fast else [])]
     jobs += [(run_mesh, s) for s in (_span(a.mesh) if a.mesh else [])]
     jobs += [(run_film, s) for s in (_span(a.film) if a.film else [])]
+    jobs += [(run_obj, s) for s in (_span(a.obj) if a.obj else [])]
+    jobs += [(run_sampler, s) for s in (_span(a.sampler) if a.sampler else [])]
     t0 = time.time()
     with ProcessPoolExecutor(a.jobs) as pool:
         rows = list(pool.map(_guard, *zip(*jobs), chunksize=4))
@@ -156,6 +202,14 @@ def main() -> None:
     if fi:
         summary["film"] = {"seeds": a.film, "films": len(fi), "values": sum(r["values"] for r in fi),
                            "differing_values": sum(r["differing"] for r in fi), "seeds_with_differences": [r["seed"] for r in fi if r["differing"]]}
+    ob = [r for r in rows if r["kind"] == "obj" and "error" not in r]
+    if ob:
+        summary["obj"] = {"seeds": a.obj, "files": len(ob), "records": sum(r["records"] for r in ob),
+                          "differing_values": sum(r["differing"] for r in ob), "seeds_with_differences": [r["seed"] for r in ob if r["differing"]]}
+    sa = [r for r in rows if r["kind"] == "sampler" and "error" not in r]
+    if sa:
+        summary["sampler"] = {"seeds": a.sampler, "configurations": len(sa), "values": sum(r["values"] for r in sa),
+                              "differing_values": sum(r["differing"] for r in sa), "seeds_with_differences": [r["seed"] for r in sa if r["differing"]]}
     summary["errors"] = [r for r in rows if "error" in r]
     text = json.dumps(summary, indent=1)
     print(text)
