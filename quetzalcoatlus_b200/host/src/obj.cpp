@@ -199,6 +199,7 @@ struct Range {
     Vertex* v = nullptr;
     VertexNormal* vn = nullptr;
     FaceElement* f = nullptr;
+    bool has_nul = false;   // (pass 1) the range holds a NUL byte: see parse_text
 };
 
 // Lines of text[begin, end), `begin` at a line start.  The text ends in NUL at text[size] (the last line may lack its
@@ -206,6 +207,7 @@ struct Range {
 template <bool PARSE>
 void scan_lines(const char* text, size_t size, size_t begin, size_t end, Range& r) {
     size_t pos = begin, nv = 0, nn = 0, nf = 0;
+    if (!PARSE) r.has_nul = end > begin && std::memchr(text + begin, '\0', end - begin) != nullptr;
     while (pos < end) {
         const char* p = text + pos;
         const void* nl = std::memchr(p, '\n', size - pos);
@@ -225,6 +227,12 @@ void scan_lines(const char* text, size_t size, size_t begin, size_t end, Range& 
         }
     }
     r.nv = nv, r.nn = nn, r.nf = nf;
+}
+
+std::string without_nul(const char* text, size_t size) {
+    std::string copy(text, size);
+    std::replace(copy.begin(), copy.end(), '\0', '\x01');
+    return copy;
 }
 
 template <class F>
@@ -250,6 +258,11 @@ ObjData parse_text(const char* text, size_t size) {
     }
     std::vector<Range> count(n_parts), done(n_parts);
     run_parts(n_parts, [&](size_t k) { scan_lines<false>(text, size, cut[k], cut[k + 1], count[k]); });
+    // A NUL byte INSIDE the text is an ordinary non-blank character to the reference (`\S` matches it; std::stof stops at
+    // it like at any other non-numeric character), but this parser's end-of-text sentinel.  Such a file is parsed from a
+    // copy in which every NUL is the byte 0x01, which the reference's patterns and strtof treat the same way.
+    for (const Range& c : count)
+        if (c.has_nul) return parse_text(without_nul(text, size).c_str(), size);
     size_t nv = 0, nn = 0, nf = 0;
     for (const Range& c : count) nv += c.nv, nn += c.nn, nf += c.nf;
     ObjData data;
@@ -280,11 +293,21 @@ ObjData parse_text(const char* text, size_t size) {
 }  // namespace
 
 // (the reference's per-record entry points, obj.hpp:12-33: regex_search, so the record may start anywhere in the line)
-std::optional<Vertex> Vertex::from_line(const std::string& line) { return search_record<Vertex>(line.c_str(), "v", vertex_at); }
+// (a std::string may hold NUL bytes: same substitution as in parse_text)
+std::optional<Vertex> Vertex::from_line(const std::string& line) {
+    if (line.find('\0') != std::string::npos) return from_line(without_nul(line.data(), line.size()));
+    return search_record<Vertex>(line.c_str(), "v", vertex_at);
+}
 
-std::optional<VertexNormal> VertexNormal::from_line(const std::string& line) { return search_record<VertexNormal>(line.c_str(), "vn", normal_at); }
+std::optional<VertexNormal> VertexNormal::from_line(const std::string& line) {
+    if (line.find('\0') != std::string::npos) return from_line(without_nul(line.data(), line.size()));
+    return search_record<VertexNormal>(line.c_str(), "vn", normal_at);
+}
 
-std::optional<FaceElement> FaceElement::from_line(const std::string& line) { return face_in(line.c_str()); }
+std::optional<FaceElement> FaceElement::from_line(const std::string& line) {
+    if (line.find('\0') != std::string::npos) return from_line(without_nul(line.data(), line.size()));
+    return face_in(line.c_str());
+}
 
 // The file is mapped, not copied: the parser reads the page cache in place.  It needs a NUL behind the last byte, which
 // the zero fill of the mapping's last page provides -- except for a file that fills its last page exactly and does not

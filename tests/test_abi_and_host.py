@@ -193,6 +193,11 @@ def _torture_obj_lines(rng):
             lines.append("vn" + sep + sep.join(num() for _ in range(rng.choice([3, 3, 4]))))
     lines += [" v 1 2 3", "\tv 4 5 6", " vn 0 0 1", " f 1 2 3", "v 1 2", "vn 1 2", "v", "vn", "f", "f 1 2", "#v 1 2 3", "v 1 2 3#x",
               "vv 1 2 3 v 1 2 3", "g v 1 2 3", "x f 1 2 3", "f 1 2 3 f 4 5 6", "f 1/2 f 3 4 5", "f 1/ 2 3 f 7/8 9/10 11/12", "f1 2 3", "v1 2 3"]
+    # NUL bytes inside the text: non-blank characters like any other to the reference's patterns (`\S`), the end of the
+    # number to std::stof (a token that STARTS with one makes the reference throw, like every token without a number:
+    # not in this file, the oracle would take the test process down with it)
+    lines += ["v 1 2 3\x00 4", "v 1 2\x00 3 4", "vn 0 0\x001 1 5", "f 1 2 3\x00 4", "f 1 2 3 \x004", "\x00v 1 2 3", "v\x00 1 2 3",
+              "v 5 6 7 8\x00", "f 1/2/3 4/5/6 7/8/9\x00 1/1/1"]
     idx = lambda: str(rng.integers(1, 250))
     for _ in range(200):
         form, n = rng.integers(0, 6), rng.choice([3, 4, 5, 2])
