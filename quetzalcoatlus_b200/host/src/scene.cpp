@@ -481,6 +481,14 @@ RenderResult render(const Camera& camera, const Scene& scene, size_t n_samples, 
         std::cout << "Scene must be committed before rendering." << std::endl;
         return result;
     }
+    if (n_samples == 0) {
+        // the reference divides the empty per-pixel sums by float(0) (render.cpp:280-282): every film value is 0.0f / 0.0f,
+        // the default NaN of the host's division.  (The library itself refuses a render without samples.)
+        volatile float zero = 0.0f;
+        const float nan = zero / zero;
+        for (auto* plane : {&result.color_buffer, &result.normal_buffer, &result.albedo_buffer}) std::fill(plane->begin(), plane->end(), nan);
+        return result;
+    }
     std::vector<float> sensor;
     qz_camera cam = qzhost::flatten_camera(camera, sensor);
     qz_stats stats{};

@@ -38,5 +38,31 @@ int main() {
               << plane_hash(film.normal_buffer) << " albedo " << plane_hash(film.albedo_buffer) << std::dec << std::endl;
     RenderResult none = render(camera, scene, 1, 0);
     std::cout << "zero bounces color " << std::hex << plane_hash(none.color_buffer) << std::dec << std::endl;
+    // no samples at all: the reference divides the empty sums by float(0) (render.cpp:280-282)
+    RenderResult empty = render(camera, scene, 0, 4);
+    std::cout << "zero samples color " << std::hex << plane_hash(empty.color_buffer) << " normal " << plane_hash(empty.normal_buffer)
+              << " albedo " << plane_hash(empty.albedo_buffer) << std::dec << std::endl;
+    // a second render of the same scene, another camera: nothing is left over from the first
+    Camera wide(5, 9, M_PI / 2.0f);
+    RenderResult again = render(wide, scene, 2, 3);
+    std::cout << "second camera " << again.width << "x" << again.height << " color " << std::hex << plane_hash(again.color_buffer)
+              << std::dec << std::endl;
+    // geometry data handed back by add_*: stays valid, carries the material
+    Scene other(initialize_device());
+    auto* tri = other.add_triangle(Pt3(0.f, 0.f, -3.f), Pt3(1.f, 0.f, -3.f), Pt3(0.f, 1.f, -3.f), &grey);
+    auto* quad = other.add_quad(Pt3(-1.f, -1.f, -5.f), Pt3(1.f, -1.f, -5.f), Pt3(1.f, 1.f, -5.f), Pt3(-1.f, 1.f, -5.f), &grey);
+    std::cout << "geometry material kept: " << (tri && tri->material == &grey) << (quad && quad->material == &grey) << std::endl;
+    other.set_bg_light(spectra::ILLUM_D65(), 0.5f);
+    other.commit();
+    RenderResult sky = render(camera, other, 2, 2);
+    std::cout << "background light color " << std::hex << plane_hash(sky.color_buffer) << " albedo " << plane_hash(sky.albedo_buffer)
+              << std::dec << std::endl;
+    // an empty committed scene
+    Scene nothing(initialize_device());
+    nothing.commit();
+    std::cout << "empty scene ready: " << nothing.ready() << std::endl;
+    RenderResult black = render(camera, nothing, 2, 2);
+    std::cout << "empty scene color " << std::hex << plane_hash(black.color_buffer) << " normal " << plane_hash(black.normal_buffer)
+              << std::dec << std::endl;
     return 0;
 }

@@ -105,7 +105,9 @@ def test_same_program_against_both_libraries_behaves_the_same(emu, oracle, tmp_p
     the reference's headers and linked with the reference's own objects (oracle/_ref), and against the host library's
     headers linked with the host library (over the emulation of the device code, so that it runs here).  What a user
     observes must be the same: ready() before / after commit, add_obj on a missing file, render() on a scene that was
-    not committed (message + zero film of the right size), and the films of two renders bit for bit."""
+    not committed (message + zero film of the right size), the films of two renders bit for bit, a render without
+    samples (the reference's 0 / 0 film), a second camera on the same scene, the geometry records add_* hands back, a
+    background light, and an empty committed scene."""
     if not REFERENCE.exists():
         pytest.skip("/root/reference is absent")
     src = ROOT / "tests" / "api_behaviour.cpp"
