@@ -197,11 +197,14 @@ GeometryData* Scene::add_grid(const Image& image, const Material* material, cons
         std::cerr << "Grid too large" << std::endl;
         return nullptr;
     }
-    if (image.width < 2 || image.height < 2) {
-        std::cerr << "Failed to create buffers for grid" << std::endl;
-        return nullptr;
-    }
     const size_t W = image.width, H = image.height;
+    if (W < 2 || H < 2) {
+        // a grid without a single cell: the reference still attaches it (scene.cpp:376-430 has no lower limit), so it takes
+        // a geometry ID and hands back its record; there is nothing to intersect
+        GeometryData* g = new_geometry(ShapeType::GRID, material);
+        g->grid_dims = 0;
+        return g;
+    }
     std::vector<Pt3> verts(W * H);
     parallel_ranges(W * H, [&](size_t begin, size_t end) {
         for (size_t i = begin; i < end; i++)

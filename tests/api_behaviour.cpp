@@ -1,8 +1,11 @@
 // The same program against two libraries: the reference's sources (oracle/_ref) and the host library.  Prints what a
 // user of the scene API observes in the corner cases; the test compares the two outputs line by line.
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
+#include <fstream>
 #include <iostream>
+#include <string>
 
 #include "render.hpp"
 
@@ -63,6 +66,25 @@ int main() {
     std::cout << "empty scene ready: " << nothing.ready() << std::endl;
     RenderResult black = render(camera, nothing, 2, 2);
     std::cout << "empty scene color " << std::hex << plane_hash(black.color_buffer) << " normal " << plane_hash(black.normal_buffer)
+              << std::dec << std::endl;
+    // degenerate inputs of add_grid / add_obj: which ones yield a geometry, and which geometry IDs the survivors take
+    Scene odd(initialize_device());
+    Image thin{size_t(5), size_t(1)};
+    std::cout << "grid without cells -> " << (odd.add_grid(thin, &grey) ? "geometry" : "nullptr") << std::endl;
+    Image too_wide{size_t(2), size_t(70000)};
+    std::cout << "grid 70000 wide -> " << (odd.add_grid(too_wide, &grey) ? "geometry" : "nullptr") << std::endl;
+    const std::string tmp = std::getenv("API_TMP") ? std::getenv("API_TMP") : "/tmp";
+    { std::ofstream f(tmp + "/api_empty.obj"); }
+    std::cout << "empty obj -> " << (odd.add_obj(tmp + "/api_empty.obj", &grey) ? "geometry" : "nullptr") << std::endl;
+    { std::ofstream f(tmp + "/api_verts.obj"); f << "v 0 0 -3\nv 1 0 -3\nv 0 1 -3\n"; }
+    std::cout << "obj without faces -> " << (odd.add_obj(tmp + "/api_verts.obj", &grey) ? "geometry" : "nullptr") << std::endl;
+    { std::ofstream f(tmp + "/api_tri.obj"); f << "v 0 0 -3\nv 1 0 -3\nv 0 1 -3\nf 1 2 3\n"; }
+    std::cout << "obj triangle -> " << (odd.add_obj(tmp + "/api_tri.obj", &grey) ? "geometry" : "nullptr") << std::endl;
+    for (unsigned id = 0; id < 2; id++) std::cout << "geometry " << id << " shape " << int(odd.get_geom_data(id)->shape) << std::endl;
+    odd.add_light(std::make_unique<PointLight>(Pt3(2.f, 3.f, -1.f), spectra::ILLUM_D65(), 20.0f));
+    odd.commit();
+    RenderResult odd_film = render(camera, odd, 3, 5);
+    std::cout << "degenerate scene color " << std::hex << plane_hash(odd_film.color_buffer) << " normal " << plane_hash(odd_film.normal_buffer)
               << std::dec << std::endl;
     return 0;
 }

@@ -107,7 +107,8 @@ def test_same_program_against_both_libraries_behaves_the_same(emu, oracle, tmp_p
     observes must be the same: ready() before / after commit, add_obj on a missing file, render() on a scene that was
     not committed (message + zero film of the right size), the films of two renders bit for bit, a render without
     samples (the reference's 0 / 0 film), a second camera on the same scene, the geometry records add_* hands back, a
-    background light, and an empty committed scene."""
+    background light, an empty committed scene, and degenerate add_grid / add_obj inputs (a grid without cells still
+    takes a geometry ID; a grid beyond 65535 per side, an empty OBJ and an OBJ without faces yield nullptr)."""
     if not REFERENCE.exists():
         pytest.skip("/root/reference is absent")
     src = ROOT / "tests" / "api_behaviour.cpp"
@@ -117,7 +118,7 @@ def test_same_program_against_both_libraries_behaves_the_same(emu, oracle, tmp_p
                              f"-Wl,-rpath,{ref_dir}", "-o", str(tmp_path / "api_ref")], check=True, capture_output=True, timeout=300)
     subprocess.run(common + [f"-I{ROOT / 'include'}", f"-I{ROOT / 'quetzalcoatlus_b200' / 'host'}", f"-L{emu_dir}", "-lqz_emu_harness",
                              f"-Wl,-rpath,{emu_dir}", "-o", str(tmp_path / "api_emu")], check=True, capture_output=True, timeout=300)
-    env = dict(os.environ, QZ_DATA_DIR=str(ROOT / "quetzalcoatlus_b200" / "data"))
+    env = dict(os.environ, QZ_DATA_DIR=str(ROOT / "quetzalcoatlus_b200" / "data"), API_TMP=str(tmp_path))
 
     def observed(exe):
         out = subprocess.run([str(tmp_path / exe)], capture_output=True, text=True, check=True, timeout=120, env=env,
