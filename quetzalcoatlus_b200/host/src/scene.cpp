@@ -15,6 +15,7 @@
 #include <chrono>
 #include <cstdlib>
 #include <cstring>
+#include <iomanip>
 #include <thread>
 
 #include "../obj/obj.hpp"
@@ -484,12 +485,22 @@ RenderResult render(const Camera& camera, const Scene& scene, size_t n_samples, 
         std::cout << "Scene must be committed before rendering." << std::endl;
         return result;
     }
+    const auto start_time = std::chrono::steady_clock::now();
+    // the reference's closing lines, character for character (render.cpp:392-394: the end of the progress-bar line, then
+    // wall-clock seconds of the render with three decimals and the unit chrono's operator<< appends) -- including what it leaves behind: std::cout
+    // stays in fixed notation with precision 3 for whatever the application prints next
+    auto render_time_line = [&] {
+        const std::chrono::duration<float> duration = std::chrono::steady_clock::now() - start_time;
+        std::cout << "[" << std::string(40, '=') << "] 100%\r";   // the final state of the reference's progress bar (render.cpp:220-236)
+        std::cout << std::endl << "Render time: " << std::fixed << std::setprecision(3) << duration.count() << "s" << std::endl;
+    };
     if (n_samples == 0) {
         // the reference divides the empty per-pixel sums by float(0) (render.cpp:280-282): every film value is 0.0f / 0.0f,
         // the default NaN of the host's division.  (The library itself refuses a render without samples.)
         volatile float zero = 0.0f;
         const float nan = zero / zero;
         for (auto* plane : {&result.color_buffer, &result.normal_buffer, &result.albedo_buffer}) std::fill(plane->begin(), plane->end(), nan);
+        render_time_line();
         return result;
     }
     std::vector<float> sensor;
@@ -502,7 +513,7 @@ RenderResult render(const Camera& camera, const Scene& scene, size_t n_samples, 
         return RenderResult(camera.image_height, camera.image_width);
     }
     qzhost::g_last_stats = stats;
-    std::cout << "Render time: " << stats.ms_total * 1e-3f << "s" << std::endl;
+    render_time_line();
     return result;
 }
 

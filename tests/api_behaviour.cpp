@@ -39,6 +39,8 @@ int main() {
     RenderResult film = render(camera, scene, 3, 5);
     std::cout << "film " << film.width << "x" << film.height << " color " << std::hex << plane_hash(film.color_buffer) << " normal "
               << plane_hash(film.normal_buffer) << " albedo " << plane_hash(film.albedo_buffer) << std::dec << std::endl;
+    // render() leaves std::cout the way its "Render time" line set it (render.cpp:394): fixed notation, three decimals
+    std::cout << "floats after render(): " << 0.2f << " " << 1234.56789 << " " << 3 << std::endl;
     RenderResult none = render(camera, scene, 1, 0);
     std::cout << "zero bounces color " << std::hex << plane_hash(none.color_buffer) << std::dec << std::endl;
     // no samples at all: the reference divides the empty sums by float(0) (render.cpp:280-282)
@@ -67,6 +69,35 @@ int main() {
     RenderResult black = render(camera, nothing, 2, 2);
     std::cout << "empty scene color " << std::hex << plane_hash(black.color_buffer) << " normal " << plane_hash(black.normal_buffer)
               << std::dec << std::endl;
+    // sensors, fields of view, camera transforms
+    ConductiveMaterial metal = ConductiveMaterial::copper(0.2f, 0.1f);
+    Scene lit(initialize_device());
+    lit.add_sphere(Pt3(0.f, 0.f, -4.f), 1.0f, &metal);
+    lit.add_plane(Pt3(0.f, -1.f, 0.f), Vec3(0.f, 1.f, 0.f), &grey, 20.0f);
+    lit.add_light(std::make_unique<PointLight>(Pt3(2.f, 3.f, -1.f), spectra::ILLUM_D65(), 20.0f));
+    lit.set_bg_light(spectra::ILLUM_D65(), 0.1f);
+    lit.commit();
+    {
+        Camera c(9, 7, M_PI / 3.0f, Transform::identity(), PixelSensor::CIE_XYZ());
+        RenderResult f = render(c, lit, 3, 6);
+        std::cout << "XYZ sensor " << std::hex << plane_hash(f.color_buffer) << " " << plane_hash(f.albedo_buffer) << std::dec << std::endl;
+        Camera c2(9, 7, M_PI / 3.0f, Transform::identity(), PixelSensor::CIE_XYZ(0.01f));
+        RenderResult f2 = render(c2, lit, 3, 6);
+        std::cout << "XYZ sensor, imaging ratio " << std::hex << plane_hash(f2.color_buffer) << std::dec << std::endl;
+        Camera c3(9, 7, M_PI / 3.0f, Transform::identity(), PixelSensor::CANON_EOS(0.05f));
+        RenderResult f3 = render(c3, lit, 3, 6);
+        std::cout << "Canon sensor, imaging ratio " << std::hex << plane_hash(f3.color_buffer) << std::dec << std::endl;
+    }
+    for (float fov : {0.2f, 1.0f, 2.5f, 3.0f}) {
+        Camera c(7, 11, fov, Transform::translation(0.3f, 0.5f, 1.0f) * Transform::rotate_z(0.3f) * Transform::rotate_x(-0.1f));
+        RenderResult f = render(c, lit, 2, 4);
+        std::cout << "fov " << fov << " " << std::hex << plane_hash(f.color_buffer) << " " << plane_hash(f.normal_buffer) << std::dec << std::endl;
+    }
+    {
+        Camera c(6, 6, 1.0f, Transform::scale(2.0f, 0.5f, 1.5f) * Transform::rotate_y(0.2f));
+        RenderResult f = render(c, lit, 2, 4);
+        std::cout << "scaled camera " << std::hex << plane_hash(f.color_buffer) << std::dec << std::endl;
+    }
     // degenerate inputs of add_grid / add_obj: which ones yield a geometry, and which geometry IDs the survivors take
     Scene odd(initialize_device());
     Image thin{size_t(5), size_t(1)};

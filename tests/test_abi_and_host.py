@@ -108,7 +108,9 @@ def test_same_program_against_both_libraries_behaves_the_same(emu, oracle, tmp_p
     not committed (message + zero film of the right size), the films of two renders bit for bit, a render without
     samples (the reference's 0 / 0 film), a second camera on the same scene, the geometry records add_* hands back, a
     background light, an empty committed scene, and degenerate add_grid / add_obj inputs (a grid without cells still
-    takes a geometry ID; a grid beyond 65535 per side, an empty OBJ and an OBJ without faces yield nullptr)."""
+    takes a geometry ID; a grid beyond 65535 per side, an empty OBJ and an OBJ without faces yield nullptr), both sensor
+    presets with explicit imaging ratios, four fields of view under a rotated camera, a scaled camera transform -- and
+    the state render() leaves std::cout in (fixed notation, three decimals: render.cpp:394)."""
     if not REFERENCE.exists():
         pytest.skip("/root/reference is absent")
     src = ROOT / "tests" / "api_behaviour.cpp"
