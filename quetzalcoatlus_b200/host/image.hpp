@@ -14,6 +14,12 @@ public:
     Image(const std::vector<float>& buffer, size_t height_, size_t width_) : height(height_), width(width_), color_buffer(buffer) {}
     Image(std::vector<float>&& buffer, size_t height_, size_t width_) : height(height_), width(width_), color_buffer(buffer) {}
     virtual ~Image() {}
+    // (declaring the destructor would otherwise take the implicit move operations away, which the reference's Image --
+    // no declared destructor -- has: returning a RenderResult by value must not copy its planes)
+    Image(const Image&) = default;
+    Image(Image&&) = default;
+    Image& operator=(const Image&) = default;
+    Image& operator=(Image&&) = default;
 
     void save(const std::string& filename, float gamma = 1.0) const;
     virtual void denoise(bool verbose = false);

@@ -15,6 +15,8 @@
 #include <chrono>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
+#include <exception>
 #include <iomanip>
 #include <thread>
 
@@ -480,15 +482,15 @@ qz_camera flatten_camera(const Camera& camera, std::vector<float>& sensor_storag
 }  // namespace qzhost
 
 RenderResult render(const Camera& camera, const Scene& scene, size_t n_samples, size_t max_bounces) {
-    RenderResult result(camera.image_height, camera.image_width);
+    const size_t H = camera.image_height, W = camera.image_width, n = H * W * 3;
     if (!scene.ready()) {
         std::cout << "Scene must be committed before rendering." << std::endl;
-        return result;
+        return RenderResult(H, W);
     }
     const auto start_time = std::chrono::steady_clock::now();
     // the reference's closing lines, character for character (render.cpp:392-394: the end of the progress-bar line, then
-    // wall-clock seconds of the render with three decimals and the unit chrono's operator<< appends) -- including what it leaves behind: std::cout
-    // stays in fixed notation with precision 3 for whatever the application prints next
+    // wall-clock seconds of the render with three decimals and the unit chrono's operator<< appends) -- including what it
+    // leaves behind: std::cout stays in fixed notation with precision 3 for whatever the application prints next
     auto render_time_line = [&] {
         const std::chrono::duration<float> duration = std::chrono::steady_clock::now() - start_time;
         std::cout << "[" << std::string(40, '=') << "] 100%\r";   // the final state of the reference's progress bar (render.cpp:220-236)
@@ -497,6 +499,7 @@ RenderResult render(const Camera& camera, const Scene& scene, size_t n_samples, 
     if (n_samples == 0) {
         // the reference divides the empty per-pixel sums by float(0) (render.cpp:280-282): every film value is 0.0f / 0.0f,
         // the default NaN of the host's division.  (The library itself refuses a render without samples.)
+        RenderResult result(H, W);
         volatile float zero = 0.0f;
         const float nan = zero / zero;
         for (auto* plane : {&result.color_buffer, &result.normal_buffer, &result.albedo_buffer}) std::fill(plane->begin(), plane->end(), nan);
@@ -506,15 +509,32 @@ RenderResult render(const Camera& camera, const Scene& scene, size_t n_samples, 
     std::vector<float> sensor;
     qz_camera cam = qzhost::flatten_camera(camera, sensor);
     qz_stats stats{};
-    int rc = qz_render(scene.handle(), &cam, uint32_t(n_samples), uint32_t(max_bounces), nullptr, nullptr,
-                       result.color_buffer.data(), result.normal_buffer.data(), result.albedo_buffer.data(), &stats);
+    // The RenderResult's three planes are fresh memory every call -- tens of megabytes whose first touch (the vectors'
+    // zero fill) costs milliseconds of page faults, a third of a 1920 x 1080 render.  A helper thread takes them while the
+    // GPU renders; the library writes into a scratch area this thread keeps between calls (its pages stay resident), and
+    // the planes are copied over once both are done.
+    static thread_local std::vector<float> scratch;
+    if (scratch.size() < 3 * n) scratch.resize(3 * n);
+    std::unique_ptr<RenderResult> result;
+    std::exception_ptr alloc_failure;
+    std::thread prepare([&] {
+        try { result = std::make_unique<RenderResult>(H, W); } catch (...) { alloc_failure = std::current_exception(); }
+    });
+    const int rc = qz_render(scene.handle(), &cam, uint32_t(n_samples), uint32_t(max_bounces), nullptr, nullptr,
+                             scratch.data(), scratch.data() + n, scratch.data() + 2 * n, &stats);
+    prepare.join();
+    if (alloc_failure) std::rethrow_exception(alloc_failure);
     if (rc != QZ_OK) {
         std::cerr << "error: render failed: " << qz_last_error() << std::endl;
-        return RenderResult(camera.image_height, camera.image_width);
+        return std::move(*result);   // (zeros)
     }
+    float* const planes[3] = {result->color_buffer.data(), result->normal_buffer.data(), result->albedo_buffer.data()};
+    parallel_ranges(n, [&](size_t begin, size_t end) {
+        for (int k = 0; k < 3; k++) std::memcpy(planes[k] + begin, scratch.data() + size_t(k) * n + begin, (end - begin) * sizeof(float));
+    });
     qzhost::g_last_stats = stats;
     render_time_line();
-    return result;
+    return std::move(*result);
 }
 
 // ---------------------------------------------------------------- Image output
