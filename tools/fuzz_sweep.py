@@ -10,6 +10,7 @@ fast : the radiometric build: discrete decisions identical, finite radiance with
 film : whole films (pixel loop, ordered accumulation, division) bit for bit, three planes
 obj  : OBJ text loader on torture files against the reference's own regex loader, record by record
 sampler: the Halton sampler at random resolutions / sample counts, bit for bit
+memo : the sample memo's host side at random resolutions / row lengths / pass sizes / shards: film with == film without
 mesh : OBJ loader -> LBVH -> wide-BVH traversal: closest hits and paths bit for bit
 """
 from __future__ import annotations
@@ -147,6 +148,30 @@ def run_sampler(seed: int) -> dict:
     return {"kind": "sampler", "seed": seed, "values": n, "differing": bad}
 
 
+def run_memo(seed: int) -> dict:
+    """Sample memo on the host (csrc/memo_plan.h, sampler.cuh: owned pixel classes, row layout, fill and read side shared
+    with the kernels) at a random resolution, sample count, row length, pass size and multi-GPU shard: the owned rows
+    of the film with the table forced on must equal the film without it, bit for bit."""
+    from common import bits_equal
+    from quetzalcoatlus_b200.harness import QZ_FLAG_FORCE_MEMO
+
+    _, emu, _ = _libs()
+    rng = np.random.default_rng(seed)
+    w, h, spp = int(rng.integers(1, 260)), int(rng.integers(1, 260)), int(rng.integers(1, 4))
+    name = str(rng.choice(["cornell_box", "textures", "kitchen_sink", f"fuzz:{seed}"]))
+    region = None
+    if rng.random() < 0.6:
+        n = int(rng.integers(1, 9))
+        region = (int(rng.integers(1, 17)), n, int(rng.integers(0, n)))
+    reserved = int(rng.choice([0, 1, 2, 5, 8]))
+    per_pass = int(rng.choice([0, 1, 2]))
+    with emu.build_scene(name, w, h) as sc:
+        plain, _ = sc.render_flags(spp, region=region)
+        memo, st = sc.render_flags(spp, flags=QZ_FLAG_FORCE_MEMO, region=region, reserved=reserved, samples_per_pass=per_pass)
+    bad = sum(int((~bits_equal(getattr(plain, p), getattr(memo, p))).sum()) for p in ("color", "normal", "albedo"))
+    return {"kind": "memo", "seed": seed, "values": 9 * w * h, "differing": bad, "classes": int(st["iterations"])}
+
+
 def _guard(fn, seed):
     try:
         return fn(seed)
@@ -167,6 +192,7 @@ def main() -> None:
     ap.add_argument("--film", default="")
     ap.add_argument("--obj", default="")
     ap.add_argument("--sampler", default="")
+    ap.add_argument("--memo", default="")
     ap.add_argument("--jobs", type=int, default=8)
     ap.add_argument("--out", default="")
     a = ap.parse_args()
@@ -176,6 +202,7 @@ def main() -> None:
     jobs += [(run_film, s) for s in (_span(a.film) if a.film else [])]
     jobs += [(run_obj, s) for s in (_span(a.obj) if a.obj else [])]
     jobs += [(run_sampler, s) for s in (_span(a.sampler) if a.sampler else [])]
+    jobs += [(run_memo, s) for s in (_span(a.memo) if a.memo else [])]
     t0 = time.time()
     with ProcessPoolExecutor(a.jobs) as pool:
         rows = list(pool.map(_guard, *zip(*jobs), chunksize=4))
@@ -210,6 +237,11 @@ def main() -> None:
     if sa:
         summary["sampler"] = {"seeds": a.sampler, "configurations": len(sa), "values": sum(r["values"] for r in sa),
                               "differing_values": sum(r["differing"] for r in sa), "seeds_with_differences": [r["seed"] for r in sa if r["differing"]]}
+    mm = [r for r in rows if r["kind"] == "memo" and "error" not in r]
+    if mm:
+        summary["memo"] = {"seeds": a.memo, "configurations": len(mm), "film_values": sum(r["values"] for r in mm),
+                           "differing_values": sum(r["differing"] for r in mm), "seeds_with_differences": [r["seed"] for r in mm if r["differing"]],
+                           "configurations_that_built_a_table": sum(1 for r in mm if r["classes"] > 0)}
     summary["errors"] = [r for r in rows if "error" in r]
     text = json.dumps(summary, indent=1)
     print(text)
