@@ -285,7 +285,9 @@ inline void build_empty_sky(Bundle& b, const Options& o) {
 // Seeded random scenes for the parity tests ("fuzz:<seed>"): every material, texture, light and shape type of the
 // reference's scene API in combinations none of the shipped examples has -- rough and anisotropic conductors next to
 // dielectrics with dispersion, mixed materials of three children, image textures, bumpy height grids, emitters of
-// every kind, with or without a background.  Integer generator, float arithmetic and one draw per statement (argument evaluation order is
+// every kind, with or without a background; grids under rotated and non-uniformly scaled transforms, triangles without
+// area, cameras with a field of view of 0.4 to 2.2 rad under yaw, pitch and roll, both sensor presets with and without
+// their own imaging ratio.  Integer generator, float arithmetic and one draw per statement (argument evaluation order is
 // unspecified), so both builds of this header make the same scene.
 struct FuzzRng {
     uint32_t state;
@@ -424,7 +426,9 @@ inline void build_fuzz(Bundle& b, const Options& o, uint32_t seed) {
         if (kind == 0) {
             scene.add_sphere(c, 0.5f * u.x, m);
         } else if (kind == 1) {
-            scene.add_triangle(c, c + u, c + v, m);
+            // (one triangle in eight has no area: its three corners lie on a line)
+            const bool flat = r.pick(8) == 0;
+            scene.add_triangle(c, c + u, flat ? c + u * 2.5f : c + v, m);
         } else if (kind == 2) {
             scene.add_quad(c, c + u, c + u + v, c + v, m);
         } else {
@@ -444,14 +448,28 @@ inline void build_fuzz(Bundle& b, const Options& o, uint32_t seed) {
                 }
             }
             const float turn = r.uniform(-0.6f, 0.6f);
-            scene.add_grid(grid, m, Transform::translation(c.x, c.y, c.z) * Transform::rotate_x(turn));
+            const float roll = r.uniform(-0.8f, 0.8f);
+            const Vec3 stretch = r.vec(0.5f, 1.6f, 0.5f, 1.6f, 0.5f, 1.6f);
+            scene.add_grid(grid, m, Transform::translation(c.x, c.y, c.z) * Transform::rotate_x(turn) * Transform::rotate_z(roll) *
+                                        Transform::scale(stretch.x, stretch.y, stretch.z));
         }
     }
     scene.commit();
     const Vec3 eye = r.vec(-0.5f, 0.5f, -0.3f, 0.6f, 0.f, 1.5f);
     const float yaw = r.uniform(-0.2f, 0.2f);
-    b.camera = std::make_unique<Camera>(o.width ? o.width : 96, o.height ? o.height : 72, M_PI / 3.0f,
-                                        Transform::translation(eye.x, eye.y, eye.z) * Transform::rotate_y(yaw));
+    const float pitch = r.uniform(-0.15f, 0.15f);
+    const float roll = r.uniform(-0.3f, 0.3f);
+    const float fov = r.uniform(0.4f, 2.2f);
+    const Transform pose = Transform::translation(eye.x, eye.y, eye.z) * Transform::rotate_y(yaw) * Transform::rotate_x(pitch) * Transform::rotate_z(roll);
+    const size_t cam_w = o.width ? o.width : 96, cam_h = o.height ? o.height : 72;
+    // (one camera in four carries the CIE XYZ sensor instead of the default Canon curves, half of those with their own
+    // imaging ratio: sensor.cpp:72-89)
+    const int sensor_kind = r.pick(8);
+    const float ratio = r.uniform(0.005f, 0.05f);
+    if (sensor_kind == 0) b.camera = std::make_unique<Camera>(cam_w, cam_h, fov, pose, PixelSensor::CIE_XYZ());
+    else if (sensor_kind == 1) b.camera = std::make_unique<Camera>(cam_w, cam_h, fov, pose, PixelSensor::CIE_XYZ(ratio));
+    else if (sensor_kind == 2) b.camera = std::make_unique<Camera>(cam_w, cam_h, fov, pose, PixelSensor::CANON_EOS(ratio));
+    else b.camera = std::make_unique<Camera>(cam_w, cam_h, fov, pose);
     b.n_samples = 4;
     b.max_bounces = 24;
 }
