@@ -11,6 +11,7 @@ film : whole films (pixel loop, ordered accumulation, division) bit for bit, thr
 obj  : OBJ text loader on torture files against the reference's own regex loader, record by record
 sampler: the Halton sampler at random resolutions / sample counts, bit for bit
 memo : the sample memo's host side at random resolutions / row lengths / pass sizes / shards: film with == film without
+rays : closest-hit probe with axis-aligned, vertex-aimed, edge-grazing, tiny and huge rays on random meshes
 mesh : OBJ loader -> LBVH -> wide-BVH traversal: closest hits and paths bit for bit
 """
 from __future__ import annotations
@@ -172,6 +173,50 @@ def run_memo(seed: int) -> dict:
     return {"kind": "memo", "seed": seed, "values": 9 * w * h, "differing": bad, "classes": int(st["iterations"])}
 
 
+def run_rays(seed: int) -> dict:
+    """Closest-hit probe on a random mesh with the rays a BVH finds hardest: one or two direction components exactly zero
+    (or -0), rays aimed exactly at a vertex along an axis, rays along the line through two vertices (grazing edges),
+    directions scaled by 1e-20 and 1e18.  (t, u, v, Ng, ids) bit for bit against the oracle."""
+    from common import bits_equal
+    from test_emu_parity import _random_mesh_obj
+
+    oracle, emu, _ = _libs()
+    with tempfile.TemporaryDirectory() as tmp:
+        path = Path(tmp) / "mesh.obj"
+        rng = _random_mesh_obj(path, seed)
+        verts = np.array([[float(x) for x in line.split()[1:4]] for line in open(path) if line.startswith("v ")], dtype=np.float32)
+        kw = dict(obj_path=str(path), obj_material="diffuse", obj_light="point")
+        with emu.build_scene("obj_viewer", 48, 36, **kw) as se, oracle.build_scene("obj_viewer", 48, 36, **kw) as so:
+            n = 2000
+            o = rng.normal(0, 2.0, (n, 3)).astype(np.float32)
+            d = rng.normal(0, 1, (n, 3)).astype(np.float32)
+            kind = rng.integers(0, 8, n)
+            for i in range(n):
+                if kind[i] == 0:
+                    d[i, rng.integers(0, 3)] = 0
+                elif kind[i] == 1:
+                    d[i, rng.choice(3, 2, replace=False)] = 0
+                elif kind[i] == 2:
+                    v, ax = verts[rng.integers(0, len(verts))], rng.integers(0, 3)
+                    o[i] = v
+                    o[i, ax] += np.float32(rng.choice([-3, 3]))
+                    d[i] = 0
+                    d[i, ax] = -np.sign(o[i, ax] - v[ax])
+                elif kind[i] == 3:
+                    d[i] *= np.float32(1e-20)
+                elif kind[i] == 4:
+                    d[i] *= np.float32(1e18)
+                elif kind[i] == 5:
+                    d[i, rng.integers(0, 3)] = -0.0
+                elif kind[i] == 6:
+                    a, b = verts[rng.integers(0, len(verts))], verts[rng.integers(0, len(verts))]
+                    o[i] = a - (b - a) * np.float32(0.5)
+                    d[i] = b - a
+            rays = np.concatenate([o, d], 1).astype(np.float32)
+            bad = int((~bits_equal(se.intersect(rays), so.intersect(rays)).all(1)).sum())
+    return {"kind": "rays", "seed": seed, "rays": n, "differing": bad}
+
+
 def _guard(fn, seed):
     try:
         return fn(seed)
@@ -193,6 +238,7 @@ def main() -> None:
     ap.add_argument("--obj", default="")
     ap.add_argument("--sampler", default="")
     ap.add_argument("--memo", default="")
+    ap.add_argument("--rays", default="")
     ap.add_argument("--jobs", type=int, default=8)
     ap.add_argument("--out", default="")
     a = ap.parse_args()
@@ -203,6 +249,7 @@ def main() -> None:
     jobs += [(run_obj, s) for s in (_span(a.obj) if a.obj else [])]
     jobs += [(run_sampler, s) for s in (_span(a.sampler) if a.sampler else [])]
     jobs += [(run_memo, s) for s in (_span(a.memo) if a.memo else [])]
+    jobs += [(run_rays, s) for s in (_span(a.rays) if a.rays else [])]
     t0 = time.time()
     with ProcessPoolExecutor(a.jobs) as pool:
         rows = list(pool.map(_guard, *zip(*jobs), chunksize=4))
@@ -242,6 +289,10 @@ def main() -> None:
         summary["memo"] = {"seeds": a.memo, "configurations": len(mm), "film_values": sum(r["values"] for r in mm),
                            "differing_values": sum(r["differing"] for r in mm), "seeds_with_differences": [r["seed"] for r in mm if r["differing"]],
                            "configurations_that_built_a_table": sum(1 for r in mm if r["classes"] > 0)}
+    ra = [r for r in rows if r["kind"] == "rays" and "error" not in r]
+    if ra:
+        summary["rays"] = {"seeds": a.rays, "meshes": len(ra), "rays": sum(r["rays"] for r in ra),
+                           "differing_hits": sum(r["differing"] for r in ra), "seeds_with_differences": [r["seed"] for r in ra if r["differing"]]}
     summary["errors"] = [r for r in rows if "error" in r]
     text = json.dumps(summary, indent=1)
     print(text)
