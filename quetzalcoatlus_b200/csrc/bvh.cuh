@@ -29,7 +29,9 @@
 // TRAVERSAL: one ray per thread, near-to-far with a per-thread stack; the kernels in
 // csrc/wf_trace.cuh wrap it in a persistent, warp-scheduled loop with warp-vote refill.  The
 // answer equals brute force over all primitives under the (t, key) order: boxes are
-// conservative, entry distances equal to the current best are still visited.
+// conservative, entry distances equal to the current best are still visited.  (For hits that lie inside the primitive's
+// padded box, that is: a ray exactly coplanar with a triangle can pass the Moeller-Trumbore test on rounding noise far from
+// the triangle, and brute force then reports a "hit" every BVH culls -- profiles/r02_summary.md, special-ray sweep.)
 #pragma once
 
 #include "intersect.cuh"
