@@ -520,8 +520,9 @@ RenderResult render(const Camera& camera, const Scene& scene, size_t n_samples, 
     std::thread prepare([&] {
         try { result = std::make_unique<RenderResult>(H, W); } catch (...) { alloc_failure = std::current_exception(); }
     });
+    float* const film = scratch.data();   // (a local: `scratch` named inside another thread would be THAT thread's own)
     const int rc = qz_render(scene.handle(), &cam, uint32_t(n_samples), uint32_t(max_bounces), nullptr, nullptr,
-                             scratch.data(), scratch.data() + n, scratch.data() + 2 * n, &stats);
+                             film, film + n, film + 2 * n, &stats);
     prepare.join();
     if (alloc_failure) std::rethrow_exception(alloc_failure);
     if (rc != QZ_OK) {
@@ -530,7 +531,7 @@ RenderResult render(const Camera& camera, const Scene& scene, size_t n_samples, 
     }
     float* const planes[3] = {result->color_buffer.data(), result->normal_buffer.data(), result->albedo_buffer.data()};
     parallel_ranges(n, [&](size_t begin, size_t end) {
-        for (int k = 0; k < 3; k++) std::memcpy(planes[k] + begin, scratch.data() + size_t(k) * n + begin, (end - begin) * sizeof(float));
+        for (int k = 0; k < 3; k++) std::memcpy(planes[k] + begin, film + size_t(k) * n + begin, (end - begin) * sizeof(float));
     });
     qzhost::g_last_stats = stats;
     render_time_line();

@@ -197,6 +197,19 @@ def test_sample_memo_on_the_host_does_not_change_the_film(emu, name, size, spp):
         assert _planes_equal(plain, partial)
 
 
+def test_render_hands_back_large_films_whole(emu):
+    """The host library's render() lets the C ABI write into a scratch area while a helper thread allocates the
+    RenderResult, then copies the planes over in several ranges (host/src/scene.cpp): a film large enough for several
+    ranges must equal the one the C ABI writes straight into caller buffers -- twice, the second call reusing the scratch."""
+    with emu.build_scene("textures", 331, 257) as sc:
+        direct, _ = sc.render_flags(1)
+        for _ in range(2):
+            assert _planes_equal(sc.render(1), direct)
+    with emu.build_scene("cornell_box", 64, 48) as sc:   # a smaller film after a larger one: the scratch is not resized down
+        direct, _ = sc.render_flags(2)
+        assert _planes_equal(sc.render(2), direct)
+
+
 def test_sample_memo_of_a_shard_holds_only_its_own_classes(emu):
     """A multi-GPU shard (interleaved strips, qz_region) tabulates only the (x mod 128, y mod 128) classes of its own rows:
     1/N of them when strip x N divides 128, and its rows of the film are those of the unsharded render, bit for bit."""
